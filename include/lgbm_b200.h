@@ -1,0 +1,179 @@
+/*
+ * lgbm_b200.h — C-ABI of the B200-native histogram tree learner (the drop-in boundary).
+ *
+ * This is the library a LightGBM maintainer binds under `device_type=cuda`: the entry points mirror,
+ * one for one, the internal plug-in interface `class TreeLearner`
+ * (reference include/LightGBM/tree_learner.h:27-114) as implemented today by
+ * `CUDASingleGPUTreeLearner` (reference src/treelearner/cuda/cuda_single_gpu_tree_learner.{hpp,cpp}).
+ * Plain C types only: pointers + sizes, no C++/torch types.  Every function returns 0 on success and
+ * -1 on error with the message retrievable through LGBMB200_GetLastError() — the same convention as
+ * the reference C API (reference include/LightGBM/c_api.h:1646-1664, src/c_api.cpp:41-55).
+ *
+ * Ownership: the learner owns its device copy of the bin matrix, the histogram pool, the row-index
+ * partition and all scratch; the caller owns grad/hess/score and the output buffers it passes in.
+ * INTEGRATION.md shows the ~150-line C++ adapter (`class B200TreeLearner : public TreeLearner`) and
+ * the factory line that slot this library into the reference.
+ */
+#ifndef LGBM_B200_H_
+#define LGBM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LGBMB200_EXPORT __attribute__((visibility("default")))
+#else
+#define LGBMB200_EXPORT
+#endif
+
+typedef void* LGBMB200_LearnerHandle;
+
+/* MissingType — reference include/LightGBM/bin.h:28-32 */
+enum { LGBMB200_MISSING_NONE = 0, LGBMB200_MISSING_ZERO = 1, LGBMB200_MISSING_NAN = 2 };
+
+/*
+ * The fields of `Config` the hot path reads (reference include/LightGBM/config.h:210-712; list in
+ * SURVEY.md §5 "Config / flags").  Replaces the `const Config*` argument of
+ * TreeLearner::CreateTreeLearner / ResetConfig (reference tree_learner.h:49,104-107).
+ */
+typedef struct {
+  int32_t num_leaves;
+  int32_t max_depth;                /* <= 0: no limit */
+  int32_t min_data_in_leaf;
+  int32_t gpu_device_id;            /* CUDA device ordinal; -1 = current device */
+  double  min_sum_hessian_in_leaf;
+  double  lambda_l1;
+  double  lambda_l2;
+  double  min_gain_to_split;
+  double  max_delta_step;
+  double  path_smooth;
+  int32_t use_cuda_graph;           /* 1: replay the whole per-tree launch sequence as one CUDA graph */
+  int32_t reserved;
+} LGBMB200_Config;
+
+/*
+ * The layout contract handed over at Init — what `Dataset` exposes to a tree learner through
+ * FeatureBinMapper(i), Feature2Group(i), feature_min_bin(i), RealFeatureIndex(i)
+ * (reference include/LightGBM/dataset.h:638-647,806-810,985-1000).
+ * `bins` is the row-major [num_data x num_columns] uint8 matrix of stored group values written by
+ * FeatureGroup::PushData (reference include/LightGBM/feature_group.h:253-267):
+ *   0               : every feature of that column is at its most-frequent bin
+ *   feat_lo[f] + i  : feature f is at bin (i + (feat_most_freq_bin[f] == 0))
+ */
+typedef struct {
+  int32_t num_data;
+  int32_t num_columns;
+  int32_t num_features;
+  const int32_t* feat_column;
+  const int32_t* feat_lo;
+  const int32_t* feat_num_bin;
+  const int32_t* feat_most_freq_bin;
+  const int32_t* feat_default_bin;
+  const int32_t* feat_missing_type;
+  const int32_t* feat_real_index;
+} LGBMB200_Layout;
+
+/* One chosen split = the SplitInfo the reference applies in SerialTreeLearner::SplitInner
+ * (reference src/treelearner/split_info.hpp:22-56, serial_tree_learner.cpp:769-925). */
+typedef struct {
+  int32_t leaf;                 /* leaf that was split: left child keeps the id, right child = index+1 */
+  int32_t feature;              /* inner feature index                                                  */
+  int32_t threshold;            /* threshold_in_bin                                                     */
+  int32_t default_left;
+  int32_t left_count;           /* true row counts after the partition                                  */
+  int32_t right_count;
+  double  gain;
+  double  left_sum_gradient, left_sum_hessian, left_output;
+  double  right_sum_gradient, right_sum_hessian, right_output;
+} LGBMB200_Split;
+
+/* Flat POD tree returned by Train: the fields Tree::Split fills (reference include/LightGBM/tree.h:543-585).
+ * All arrays are caller-allocated with capacity num_leaves (config) / num_leaves-1 for `splits`. */
+typedef struct {
+  int32_t num_leaves;           /* out: leaves actually grown                                           */
+  LGBMB200_Split* splits;       /* out [num_leaves-1], in split order (node i of the reference Tree)     */
+  double*  leaf_value;          /* out [num_leaves]                                                      */
+  double*  leaf_weight;         /* out [num_leaves] sum of hessians                                      */
+  int32_t* leaf_count;          /* out [num_leaves]                                                      */
+  int32_t* leaf_depth;          /* out [num_leaves]                                                      */
+  double   root_sum_gradient;   /* out                                                                   */
+  double   root_sum_hessian;    /* out                                                                   */
+} LGBMB200_Tree;
+
+LGBMB200_EXPORT const char* LGBMB200_GetLastError(void);
+
+/* TreeLearner::CreateTreeLearner("serial","cuda",config) — reference src/treelearner/tree_learner.cpp:17-55 */
+LGBMB200_EXPORT int LGBMB200_LearnerCreate(const LGBMB200_Config* config, LGBMB200_LearnerHandle* out);
+
+/* TreeLearner::Init(const Dataset*, bool is_constant_hessian) — reference tree_learner.h:38;
+ * cuda_single_gpu_tree_learner.cpp:36-93.  Copies the bin matrix (host pointer) to HBM. */
+LGBMB200_EXPORT int LGBMB200_LearnerInit(LGBMB200_LearnerHandle h, const LGBMB200_Layout* layout,
+                                         const uint8_t* bins_host, int32_t is_constant_hessian);
+
+/* TreeLearner::ResetConfig(const Config*) — reference tree_learner.h:56 */
+LGBMB200_EXPORT int LGBMB200_LearnerResetConfig(LGBMB200_LearnerHandle h, const LGBMB200_Config* config);
+
+/* ColSampler by-tree mask (reference src/treelearner/col_sampler.hpp; serial_tree_learner.cpp:297):
+ * feature_used[num_features] bytes on the host, or NULL for "all features". */
+LGBMB200_EXPORT int LGBMB200_LearnerSetFeatureMask(LGBMB200_LearnerHandle h, const uint8_t* feature_used);
+
+/* TreeLearner::SetBaggingData(subset, used_indices, num_data) — reference tree_learner.h:95-96,
+ * cuda_single_gpu_tree_learner.cpp:448-451.  used_indices == NULL restores "all rows". */
+LGBMB200_EXPORT int LGBMB200_LearnerSetBaggingData(LGBMB200_LearnerHandle h, const int32_t* used_indices,
+                                                   int32_t num_used, int32_t on_device);
+
+/* Tree* TreeLearner::Train(const score_t* gradients, const score_t* hessians, bool is_first_tree) —
+ * reference tree_learner.h:71; serial_tree_learner.cpp:182-248.  grad/hess are device pointers iff
+ * on_device (== boosting_on_cuda, cuda_single_gpu_tree_learner.cpp:101-106), else host pointers. */
+LGBMB200_EXPORT int LGBMB200_LearnerTrain(LGBMB200_LearnerHandle h, const float* gradients, const float* hessians,
+                                          int32_t on_device, LGBMB200_Tree* out_tree);
+
+/* TreeLearner::AddPredictionToScore(const Tree*, double* out_score) — reference tree_learner.h:85,
+ * serial_tree_learner.h:100-115: score[row] += leaf_value[leaf(row)] over the partition left by the last
+ * Train.  leaf_value is a host array (already shrunk by the caller, gbdt.cpp:421). */
+LGBMB200_EXPORT int LGBMB200_LearnerAddPredictionToScore(LGBMB200_LearnerHandle h, const double* leaf_value,
+                                                         int32_t num_leaves, double* score, int32_t on_device);
+
+/* DataPartition::GetIndexOnLeaf (reference src/treelearner/data_partition.hpp:85-91) for every leaf of
+ * the last tree: leaf_begin/leaf_count [num_leaves] and the row ids [num_data] (host outputs). */
+LGBMB200_EXPORT int LGBMB200_LearnerGetPartition(LGBMB200_LearnerHandle h, int32_t* leaf_begin, int32_t* leaf_count,
+                                                 int32_t* indices);
+
+/* Test hook: the histogram of one leaf of the last tree as fp64 (grad,hess) pairs, [num_columns*256*2],
+ * i.e. what ConstructHistograms + FixHistogram/Subtract left in the HistogramPool slot of that leaf. */
+LGBMB200_EXPORT int LGBMB200_LearnerGetLeafHistogram(LGBMB200_LearnerHandle h, int32_t leaf, double* out);
+
+/* Stand-alone ConstructHistograms (reference dataset.cpp:1293, serial_tree_learner.cpp:411-478) on an
+ * arbitrary row set (host indices, or NULL = all rows) — used by the kernel-level parity tests and
+ * the roofline micro-benchmark.  hist_out: host [num_columns*256*2] doubles. */
+LGBMB200_EXPORT int LGBMB200_LearnerConstructHistogram(LGBMB200_LearnerHandle h, const float* gradients,
+                                                       const float* hessians, int32_t on_device,
+                                                       const int32_t* indices_host, int32_t num_indices,
+                                                       double* hist_out, float* elapsed_ms);
+
+/* Device-resident boosting helpers ("next" row f-1 of SURVEY.md §8): L2 gradients
+ * (reference src/objective/regression_objective.hpp:127-142) and the number of kernels launched so far. */
+LGBMB200_EXPORT int LGBMB200_L2Gradients(LGBMB200_LearnerHandle h, const double* score_dev, const float* label_dev,
+                                         float* grad_dev, float* hess_dev, int32_t n);
+LGBMB200_EXPORT int64_t LGBMB200_LearnerKernelLaunches(LGBMB200_LearnerHandle h);
+/* Sum of CUDA-event time spent in histogram-construction launches since the last reset (ms) and the
+ * algorithmic bytes they covered; used by bench.py for the roofline of the dominant kernel. */
+LGBMB200_EXPORT int LGBMB200_LearnerHistStats(LGBMB200_LearnerHandle h, int32_t reset, double* hist_ms,
+                                              double* hist_rows, int64_t* hist_launches);
+LGBMB200_EXPORT int LGBMB200_LearnerSetProfiling(LGBMB200_LearnerHandle h, int32_t enable);
+
+/* Raw device pointer helpers so a host program without torch can keep grad/hess/score in HBM. */
+LGBMB200_EXPORT int LGBMB200_DeviceAlloc(void** ptr, int64_t bytes);
+LGBMB200_EXPORT int LGBMB200_DeviceFree(void* ptr);
+LGBMB200_EXPORT int LGBMB200_MemcpyH2D(void* dst_dev, const void* src_host, int64_t bytes);
+LGBMB200_EXPORT int LGBMB200_MemcpyD2H(void* dst_host, const void* src_dev, int64_t bytes);
+
+LGBMB200_EXPORT int LGBMB200_LearnerFree(LGBMB200_LearnerHandle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* LGBM_B200_H_ */

@@ -1,0 +1,8 @@
+"""lightgbm_b200 — B200-native histogram tree learner behind LightGBM's TreeLearner interface.
+
+Only what the hot path needs lives here: csrc/ (sm_100a kernels + C-ABI, include/lgbm_b200.h) and the
+host-side mirror of the reference interface (tree_learner.py, booster.py)."""
+from .tree_learner import B200TreeLearner, Config, Layout, Tree  # noqa: F401
+from .booster import B200Booster  # noqa: F401
+
+__all__ = ["B200TreeLearner", "B200Booster", "Config", "Layout", "Tree"]

@@ -1,0 +1,74 @@
+"""Minimal mirror of GBDT::TrainOneIter (reference src/boosting/gbdt.cpp:352-460) around the tree learner,
+for the objectives the BASELINE configs need (L2 regression; custom gradients).
+
+Two modes, matching the reference's `boosting_on_gpu_` switch (gbdt.cpp:110-135):
+  device_resident=True  : label / score / grad / hess live in HBM; gradients (regression_objective.hpp:127-142),
+                          Train and the score update never leave the device ("next" row f-1 of SURVEY.md §8).
+  device_resident=False : the caller (or this class) owns host arrays; every iteration copies grad/hess
+                          host->device inside Train and the scores device->host, i.e. the path the
+                          link-time seam of INTEGRATION.md exercises.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .tree_learner import B200TreeLearner, Config, DeviceArray, Layout, Tree
+
+
+class B200Booster:
+    def __init__(self, layout: Layout, label: np.ndarray, config: Config, learning_rate: float = 0.1,
+                 boost_from_average: bool = True, device_resident: bool = True):
+        self.learner = B200TreeLearner(config)
+        self.learner.init(layout, is_constant_hessian=True)
+        self.n = layout.num_data
+        self.lr = float(learning_rate)
+        self.device_resident = device_resident
+        self.label = np.ascontiguousarray(label, dtype=np.float32)
+        self.trees: list[Tree] = []
+        # BoostFromAverage (gbdt.cpp:328-350, RegressionL2loss::BoostFromScore): mean label
+        self.init_score = float(np.mean(self.label, dtype=np.float64)) if boost_from_average else 0.0
+        score0 = np.full(self.n, self.init_score, dtype=np.float64)
+        if device_resident:
+            self.d_label = DeviceArray(self.n * 4).upload(self.label)
+            self.d_score = DeviceArray(self.n * 8).upload(score0)
+            self.d_grad = DeviceArray(self.n * 4)
+            self.d_hess = DeviceArray(self.n * 4)
+        else:
+            self.score = score0
+            self.grad = np.empty(self.n, np.float32)
+            self.hess = np.ones(self.n, np.float32)
+
+    def update(self) -> Tree:
+        """One boosting iteration: gradients -> Train -> Shrinkage -> UpdateScore."""
+        if self.device_resident:
+            self.learner.l2_gradients(self.d_score, self.d_label, self.d_grad, self.d_hess, self.n)
+            tree = self.learner.train(self.d_grad, self.d_hess)
+        else:
+            np.subtract(self.score, self.label, out=self.grad, casting="unsafe")   # g = score - label, h = 1
+            tree = self.learner.train(self.grad, self.hess)
+        tree.shrinkage(self.lr)
+        if tree.num_leaves > 1:
+            if self.device_resident:
+                self.learner.add_prediction_to_score(tree, self.d_score)
+            else:
+                self.learner.add_prediction_to_score(tree, self.score)
+        if not self.trees and self.init_score != 0.0:
+            tree.add_bias(self.init_score)     # gbdt.cpp:424-427 (first tree carries the average)
+        self.trees.append(tree)
+        return tree
+
+    def update_custom(self, grad, hess) -> Tree:
+        """LGBM_BoosterUpdateOneIterCustom (c_api.h:801): caller-provided gradients."""
+        tree = self.learner.train(grad, hess)
+        tree.shrinkage(self.lr)
+        self.trees.append(tree)
+        return tree
+
+    def scores(self) -> np.ndarray:
+        if self.device_resident:
+            return self.d_score.download(np.float64, self.n)
+        return self.score
+
+    def l2(self) -> float:
+        s = self.scores()
+        return float(np.mean((s - self.label) ** 2))

@@ -1,0 +1,213 @@
+// hist_kernel.cuh — per-leaf gradient/hessian histogram construction (sm_100a).
+//
+// Replaces: Dataset::ConstructHistograms -> MultiValDenseBin::ConstructHistogramInner
+// (reference src/io/dataset.cpp:1293-1485, src/io/multi_val_dense_bin.hpp:58-102) and the reference
+// CUDA kernel CUDAConstructHistogramDenseKernel (src/treelearner/cuda/cuda_histogram_constructor.cu:20),
+// which does 2 shared-memory fp32 atomicAdds per cell — on sm_100a those compile to ATOMS.CAST.SPIN
+// (a compare-and-swap loop), the dominant cost of the reference.
+//
+// Design (not a port): scatter-add WITHOUT atomics in the inner loop.
+//   * A warp owns a group of 32 columns for a contiguous slice of the leaf's rows; lane L owns column L.
+//     Two lanes of a warp therefore never touch the same (column, bin) cell, and no other warp shares
+//     the warp's private histogram, so the update is a plain LDS.64 / FADD / STS.64.
+//   * The warp-private histogram is laid out [bin][lane] with 8-byte (grad,hess) cells: the shared
+//     memory bank of a cell depends on the lane only => every access is bank-conflict free whatever
+//     the bin values are.  64 KB per warp, 3 warps per SM (one CTA of 96 threads per SM).
+//   * The only hazard left is the same lane hitting the same bin in consecutive rows; rows are
+//     processed four at a time with in-register forwarding, which keeps 4 independent LDS in flight
+//     and preserves the exact sequential fp32 summation order (=> bitwise run-to-run determinism).
+//   * Rows are gathered through the leaf's index list: 32-byte row segments and the (grad,hess) pairs
+//     are staged into a per-warp 6-deep shared-memory ring with cp.async (LDGSTS), no registers, no
+//     block barriers (warp-local __syncwarp only).
+//   * Flush: fp32 partials -> int64 fixed point (power-of-two scale chosen per tree) added to the
+//     leaf's slot of the histogram pool with RED.ADD.64.  Integer adds are associative, so the global
+//     histogram does not depend on the order in which warps flush, and parent - child is exact.
+#pragma once
+#include "types.cuh"
+
+namespace b200 {
+
+constexpr int kHistWarps = 3;
+constexpr int kHistThreads = kHistWarps * 32;
+constexpr int kStageRows = 32;
+constexpr int kStages = 6;                       // ring depth; kStages-1 stages in flight
+constexpr int kWarpHistBytes = kBinsPerColumn * 32 * 8;           // 65536
+constexpr int kStageBinBytes = kStageRows * kColGroup;            // 1024
+constexpr int kStageBytes = kStageBinBytes + kStageRows * 8;      // + (g,h) pairs = 1280
+constexpr int kWarpSmemBytes = kWarpHistBytes + kStages * kStageBytes;
+constexpr int kHistSmemBytes = kHistWarps * kWarpSmemBytes;       // 219648 B <= 227 KB
+
+struct HistArgs {
+  const uint8_t* bins;            // [num_data x pitch] row-major stored values
+  int64_t pitch;                  // bytes per row, multiple of 32
+  const float2* gh;               // [num_data] (grad, hess)
+  const int32_t* idx0;            // ping-pong row-index buffers
+  const int32_t* idx1;
+  const Leaf* leaves;
+  const Ctl* ctl;
+  unsigned long long* pool;       // int64 fixed-point histogram pool [slot][column][256][2]
+  int64_t slot_stride;            // int64 elements per slot
+  int32_t num_colgroups;          // ceil(num_columns / 32)
+  int32_t min_rows_per_item;      // do not split a column group over more warps than n / this
+  // explicit mode (stand-alone ConstructHistogram hook): explicit_n >= 0
+  int32_t explicit_n;
+  int32_t explicit_slot;
+  const int32_t* explicit_idx;    // nullptr = identity
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Four rows of the lane's column, exact sequential semantics (see header comment).
+__device__ __forceinline__ void rmw4(float2* __restrict__ H, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
+                                     float4 q01, float4 q23) {
+  float2* p0 = H + b0 * 32;
+  float2* p1 = H + b1 * 32;
+  float2* p2 = H + b2 * 32;
+  float2* p3 = H + b3 * 32;
+  float2 v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3;
+  float2 n0, n1, n2, n3;
+  n0.x = v0.x + q01.x; n0.y = v0.y + q01.y;
+  if (b1 == b0) v1 = n0;
+  n1.x = v1.x + q01.z; n1.y = v1.y + q01.w;
+  if (b2 == b1) v2 = n1; else if (b2 == b0) v2 = n0;
+  n2.x = v2.x + q23.x; n2.y = v2.y + q23.y;
+  if (b3 == b2) v3 = n2; else if (b3 == b1) v3 = n1; else if (b3 == b0) v3 = n0;
+  n3.x = v3.x + q23.z; n3.y = v3.y + q23.w;
+  *p0 = n0; *p1 = n1; *p2 = n2; *p3 = n3;   // in order: the last store to a cell carries the full sum
+}
+
+__global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int n, begin, slot;
+  const int32_t* idx;
+  if (a.explicit_n >= 0) {
+    n = a.explicit_n; begin = 0; slot = a.explicit_slot; idx = a.explicit_idx;
+  } else {
+    const Ctl* c = a.ctl;
+    if (!c->cur_valid || !c->do_find) return;
+    const Leaf& L = a.leaves[c->smaller];
+    n = L.count; begin = L.begin; slot = L.slot;
+    // the root of an un-bagged tree is the identity list: skip the index load altogether
+    idx = (c->num_leaves == 1 && c->root_identity) ? nullptr : (L.buf ? a.idx1 : a.idx0);
+  }
+  if (n <= 0) return;
+
+  unsigned char* wbase = smem + warp * kWarpSmemBytes;
+  float2* H = reinterpret_cast<float2*>(wbase) + lane;            // lane's column of the [bin][lane] table
+  unsigned char* ring = wbase + kWarpHistBytes;
+
+  const int total_warps = gridDim.x * kHistWarps;
+  const int gw = warp * gridDim.x + blockIdx.x;                  // spread the first items over all SMs
+  const int CG = a.num_colgroups;
+  const int max_splits = max(1, total_warps / CG);
+  const int splits = min(max_splits, max(1, (n + a.min_rows_per_item - 1) / a.min_rows_per_item));
+  const int per = (((n + splits - 1) / splits) + 31) & ~31;
+  const int items = CG * splits;
+  const double gs = a.ctl->g_scale, hs = a.ctl->h_scale;
+
+  for (int item = gw; item < items; item += total_warps) {
+    const int cg = item % CG, part = item / CG;
+    const int r0 = part * per;
+    const int r1 = min(n, r0 + per);
+    if (r0 >= r1) continue;
+
+    // zero the warp-private histogram
+    {
+      float4* z = reinterpret_cast<float4*>(wbase);
+#pragma unroll 8
+      for (int i = lane; i < kWarpHistBytes / 16; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+
+    const uint8_t* colbase = a.bins + static_cast<int64_t>(cg) * kColGroup;
+    const int nst = (r1 - r0 + kStageRows - 1) / kStageRows;
+    constexpr int D = kStages - 1;
+    int row_next;
+    {
+      const int p = r0 + lane;
+      row_next = (p < r1) ? (idx ? __ldg(idx + begin + p) : p) : -1;
+    }
+    int wslot = 0, rslot = 0;
+    for (int s = 0; s < nst + D; ++s) {
+      if (s < nst) {
+        const int row = row_next;
+        const int p = r0 + (s + 1) * kStageRows + lane;
+        row_next = (p < r1) ? (idx ? __ldg(idx + begin + p) : p) : -1;
+        unsigned char* sb = ring + wslot * kStageBytes;
+        const int ra = __shfl_sync(0xffffffffu, row, lane >> 1);
+        const int rb = __shfl_sync(0xffffffffu, row, 16 + (lane >> 1));
+        const int half = (lane & 1) * 16;
+        if (ra >= 0) cp_async16(sb + (lane >> 1) * kColGroup + half, colbase + static_cast<int64_t>(ra) * a.pitch + half);
+        if (rb >= 0) cp_async16(sb + (16 + (lane >> 1)) * kColGroup + half, colbase + static_cast<int64_t>(rb) * a.pitch + half);
+        if (row >= 0) cp_async8(sb + kStageBinBytes + lane * 8, a.gh + row);
+        wslot = (wslot + 1 == kStages) ? 0 : wslot + 1;
+      }
+      cp_async_commit();
+      if (s >= D) {
+        cp_async_wait<D>();
+        __syncwarp();
+        const int st = s - D;
+        const int cnt = min(kStageRows, r1 - r0 - st * kStageRows);
+        const unsigned char* sb = ring + rslot * kStageBytes;
+        const unsigned char* sbin = sb + lane;
+        const float2* sgh = reinterpret_cast<const float2*>(sb + kStageBinBytes);
+        if (cnt == kStageRows) {
+          uint32_t b0 = sbin[0], b1 = sbin[32], b2 = sbin[64], b3 = sbin[96];
+          float4 q01 = *reinterpret_cast<const float4*>(sgh), q23 = *reinterpret_cast<const float4*>(sgh + 2);
+#pragma unroll
+          for (int r = 0; r < kStageRows; r += 4) {
+            // software pipeline: fetch the next batch from the stage before this batch's stores
+            uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            float4 t01 = q01, t23 = q23;
+            if (r + 4 < kStageRows) {
+              c0 = sbin[(r + 4) * 32]; c1 = sbin[(r + 5) * 32]; c2 = sbin[(r + 6) * 32]; c3 = sbin[(r + 7) * 32];
+              t01 = *reinterpret_cast<const float4*>(sgh + r + 4);
+              t23 = *reinterpret_cast<const float4*>(sgh + r + 6);
+            }
+            rmw4(H, b0, b1, b2, b3, q01, q23);
+            b0 = c0; b1 = c1; b2 = c2; b3 = c3; q01 = t01; q23 = t23;
+          }
+        } else {
+          for (int r = 0; r < cnt; ++r) {
+            const uint32_t b = sbin[r * 32];
+            const float2 q = sgh[r];
+            float2 v = H[b * 32];
+            v.x += q.x; v.y += q.y;
+            H[b * 32] = v;
+          }
+        }
+        __syncwarp();
+        rslot = (rslot + 1 == kStages) ? 0 : rslot + 1;
+      }
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+
+    // flush: fp32 partial -> int64 fixed point, RED.ADD.64 into the leaf's pool slot
+    unsigned long long* dst = a.pool + static_cast<int64_t>(slot) * a.slot_stride +
+                              (static_cast<int64_t>(cg) * kColGroup + lane) * (kBinsPerColumn * 2);
+#pragma unroll 4
+    for (int b = 0; b < kBinsPerColumn; ++b) {
+      const float2 v = H[b * 32];
+      if (v.x != 0.f || v.y != 0.f) {
+        atomicAdd(dst + 2 * b, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v.x) * gs)));
+        atomicAdd(dst + 2 * b + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v.y) * hs)));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace b200

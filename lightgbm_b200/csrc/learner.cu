@@ -1,0 +1,604 @@
+// learner.cu — host runtime + C-ABI of the B200 tree learner (see include/lgbm_b200.h).
+//
+// Host side of SerialTreeLearner::Train (reference src/treelearner/serial_tree_learner.cpp:182-248)
+// re-thought for a GPU that must not wait for the host: the leaf-wise loop is a FIXED launch sequence
+//   prep, root_init, [memset slot, hist, scan, select] x 1                      (root)
+//   { part_flags, part_scatter, memset slot, hist, scan, select } x (num_leaves-1)
+// whose every data-dependent decision (which leaf, which feature/threshold, smaller/larger child, early
+// stop) is taken on the device through the Ctl block.  The sequence is captured once into a CUDA graph
+// and replayed per tree; the host synchronises exactly once per tree, to read the split records back.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lgbm_b200.h"
+#include "hist_kernel.cuh"
+#include "partition_kernel.cuh"
+#include "scan_kernel.cuh"
+#include "types.cuh"
+
+namespace b200 {
+
+static thread_local std::string g_last_error = "everything is fine";
+
+struct CudaError {
+  std::string msg;
+};
+
+#define CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      char _buf[512];                                                                                 \
+      snprintf(_buf, sizeof(_buf), "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+               cudaGetErrorString(_e));                                                               \
+      throw CudaError{_buf};                                                                          \
+    }                                                                                                 \
+  } while (0)
+
+#define REQUIRE(cond, msg)                        \
+  do {                                            \
+    if (!(cond)) throw CudaError{std::string(msg)}; \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+class Learner {
+ public:
+  explicit Learner(const LGBMB200_Config& cfg) { SetConfig(cfg); }
+  ~Learner() { Destroy(); }
+
+  void SetConfig(const LGBMB200_Config& cfg) {
+    REQUIRE(cfg.num_leaves >= 2, "num_leaves must be >= 2");
+    const bool leaves_changed = cfg.num_leaves != cfg_.num_leaves;
+    cfg_ = cfg;
+    params_.num_leaves = cfg.num_leaves; params_.max_depth = cfg.max_depth; params_.min_data_in_leaf = cfg.min_data_in_leaf;
+    params_.pad = 0;
+    params_.min_sum_hessian = cfg.min_sum_hessian_in_leaf; params_.l1 = cfg.lambda_l1; params_.l2 = cfg.lambda_l2;
+    params_.min_gain_to_split = cfg.min_gain_to_split; params_.max_delta_step = cfg.max_delta_step;
+    params_.path_smooth = cfg.path_smooth;
+    InvalidateGraph();
+    if (inited_ && leaves_changed) AllocTreeState();
+  }
+
+  void Init(const LGBMB200_Layout& lay, const uint8_t* bins_host, int /*is_constant_hessian*/) {
+    REQUIRE(lay.num_data > 0 && lay.num_columns > 0 && lay.num_features > 0, "empty dataset");
+    if (cfg_.gpu_device_id >= 0) { CUDA_CHECK(cudaSetDevice(cfg_.gpu_device_id)); }
+    CUDA_CHECK(cudaGetDevice(&device_));
+    int major = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device_));
+    REQUIRE(major >= 10, "lgbm_b200 kernels are built for sm_100a (Blackwell) only");
+    CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device_));
+    if (!stream_) CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    InvalidateGraph();
+
+    N_ = lay.num_data; C_ = lay.num_columns; F_ = lay.num_features;
+    Cpad_ = (C_ + kColGroup - 1) / kColGroup * kColGroup;
+    pitch_ = Cpad_;
+    std::vector<FeatMeta> fm(F_);
+    for (int f = 0; f < F_; ++f) {
+      FeatMeta& m = fm[f];
+      m.col = lay.feat_column[f]; m.lo = lay.feat_lo[f]; m.num_bin = lay.feat_num_bin[f];
+      m.mfb = lay.feat_most_freq_bin[f]; m.offset = (m.mfb == 0) ? 1 : 0; m.nslice = m.num_bin - m.offset;
+      m.default_bin = lay.feat_default_bin[f]; m.missing = lay.feat_missing_type[f]; m.real_index = lay.feat_real_index[f];
+      REQUIRE(m.col >= 0 && m.col < C_, "feature column out of range");
+      REQUIRE(m.num_bin >= 1 && m.lo >= 0 && m.lo + m.nslice <= kBinsPerColumn,
+              "feature histogram slice exceeds 256 stored values per column (max_bin > 255 is not supported)");
+    }
+    feat_.alloc(F_);
+    CUDA_CHECK(cudaMemcpy(feat_.p, fm.data(), sizeof(FeatMeta) * F_, cudaMemcpyHostToDevice));
+
+    bins_.alloc(static_cast<size_t>(N_) * pitch_);
+    if (pitch_ != C_) CUDA_CHECK(cudaMemset(bins_.p, 0, static_cast<size_t>(N_) * pitch_));
+    CUDA_CHECK(cudaMemcpy2D(bins_.p, pitch_, bins_host, C_, C_, N_, cudaMemcpyHostToDevice));
+
+    gh_.alloc(N_); idx0_.alloc(N_); idx1_.alloc(N_); flags_.alloc(N_);
+    grad_stage_.alloc(N_); hess_stage_.alloc(N_);
+    part_blocks_ = num_sms_ * 2;
+    if (part_blocks_ > 1024) part_blocks_ = 1024;
+    block_left_.alloc(part_blocks_);
+    prep_blocks_ = num_sms_ * 2;
+    partials_.alloc(prep_blocks_);
+    ctl_.alloc(1);
+    feature_used_.alloc(F_);
+    have_feature_mask_ = false;
+    bag_count_ = -1;
+    CUDA_CHECK(cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+    inited_ = true;
+    AllocTreeState();
+    CUDA_CHECK(cudaDeviceSynchronize());
+  }
+
+  void SetFeatureMask(const uint8_t* mask) {
+    REQUIRE(inited_, "Init first");
+    if (mask == nullptr) { have_feature_mask_ = false; }
+    else {
+      CUDA_CHECK(cudaMemcpyAsync(feature_used_.p, mask, F_, cudaMemcpyHostToDevice, stream_));
+      CUDA_CHECK(cudaStreamSynchronize(stream_));
+      have_feature_mask_ = true;
+    }
+    InvalidateGraph();
+  }
+
+  void SetBagging(const int32_t* idx, int32_t n, int on_device) {
+    REQUIRE(inited_, "Init first");
+    if (idx == nullptr) { if (bag_count_ >= 0) InvalidateGraph(); bag_count_ = -1; return; }
+    REQUIRE(n > 0 && n <= N_, "bad bagging count");
+    if (bag_.n < static_cast<size_t>(N_)) bag_.alloc(N_);
+    CUDA_CHECK(cudaMemcpyAsync(bag_.p, idx, sizeof(int32_t) * n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (bag_count_ != n) InvalidateGraph();
+    bag_count_ = n;
+  }
+
+  void Train(const float* grad, const float* hess, int on_device, LGBMB200_Tree* out) {
+    REQUIRE(inited_, "Init first");
+    REQUIRE(out && out->splits && out->leaf_value && out->leaf_weight && out->leaf_count && out->leaf_depth, "null output buffers");
+    const float* g = grad; const float* h = hess;
+    if (!on_device) {
+      CUDA_CHECK(cudaMemcpyAsync(grad_stage_.p, grad, sizeof(float) * N_, cudaMemcpyHostToDevice, stream_));
+      CUDA_CHECK(cudaMemcpyAsync(hess_stage_.p, hess, sizeof(float) * N_, cudaMemcpyHostToDevice, stream_));
+      g = grad_stage_.p; h = hess_stage_.p;
+    }
+    const int NL = params_.num_leaves;
+    if (cfg_.use_cuda_graph && !profiling_) {
+      if (graph_exec_ == nullptr || graph_g_ != g || graph_h_ != h) BuildGraph(g, h);
+      CUDA_CHECK(cudaGraphLaunch(graph_exec_, stream_));
+      launches_ += launches_per_tree_;
+    } else {
+      EnqueueTree(g, h);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(h_splits_, splits_.p, sizeof(SplitRec) * (NL - 1), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(h_leaves_, leaves_.p, sizeof(Leaf) * NL, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(h_ctl_, ctl_.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));     // the one host sync per tree
+    if (profiling_) CollectHistTimes();
+
+    const int n_leaves = h_ctl_->num_leaves;
+    out->num_leaves = n_leaves;
+    out->root_sum_gradient = h_ctl_->root_sum_g; out->root_sum_hessian = h_ctl_->root_sum_h;
+    // Tree::Split replay (tree.h:543-585): leaf values/weights/counts/depths
+    out->leaf_value[0] = h_leaves_[0].output;   // overwritten below if the root was split
+    {
+      // root value when no split happened: the root output computed in k_root_init
+      // (children overwrite their own entries in split order)
+      double root_out = 0.0;
+      // recompute from sums exactly as k_root_init did is unnecessary: Leaf[0].output holds the latest
+      // output of leaf 0, which for an unsplit tree is the root output.
+      root_out = h_leaves_[0].output;
+      out->leaf_value[0] = root_out; out->leaf_weight[0] = h_ctl_->root_sum_h; out->leaf_count[0] = h_ctl_->root_count;
+      out->leaf_depth[0] = 0;
+    }
+    for (int i = 0; i < n_leaves - 1; ++i) {
+      const SplitRec& r = h_splits_[i];
+      LGBMB200_Split& s = out->splits[i];
+      s.leaf = r.leaf; s.feature = r.feature; s.threshold = r.threshold; s.default_left = r.default_left;
+      s.left_count = r.left_count; s.right_count = r.right_count; s.gain = r.gain;
+      s.left_sum_gradient = r.lsg; s.left_sum_hessian = r.lsh; s.left_output = r.lout;
+      s.right_sum_gradient = r.rsg; s.right_sum_hessian = r.rsh; s.right_output = r.rout;
+      const int right = i + 1;
+      out->leaf_value[r.leaf] = std::isnan(r.lout) ? 0.0 : r.lout;
+      out->leaf_weight[r.leaf] = r.lsh; out->leaf_count[r.leaf] = r.left_count;
+      out->leaf_value[right] = std::isnan(r.rout) ? 0.0 : r.rout;
+      out->leaf_weight[right] = r.rsh; out->leaf_count[right] = r.right_count;
+      out->leaf_depth[right] = out->leaf_depth[r.leaf] + 1;
+      out->leaf_depth[r.leaf] += 1;
+    }
+    last_num_leaves_ = n_leaves;
+  }
+
+  void AddPredictionToScore(const double* leaf_value, int num_leaves, double* score, int on_device) {
+    REQUIRE(inited_ && last_num_leaves_ > 0, "Train first");
+    REQUIRE(num_leaves == last_num_leaves_, "num_leaves does not match the last trained tree");
+    CUDA_CHECK(cudaMemcpyAsync(leaf_value_dev_.p, leaf_value, sizeof(double) * num_leaves, cudaMemcpyHostToDevice, stream_));
+    double* sc = score;
+    if (!on_device) {
+      if (score_stage_.n < static_cast<size_t>(N_)) score_stage_.alloc(N_);
+      CUDA_CHECK(cudaMemcpyAsync(score_stage_.p, score, sizeof(double) * N_, cudaMemcpyHostToDevice, stream_));
+      sc = score_stage_.p;
+    }
+    ScoreArgs sa{leaves_.p, idx0_.p, idx1_.p, leaf_value_dev_.p, sc};
+    dim3 grid(std::max(1, std::min(num_sms_ * 4, (N_ + 255) / 256)), num_leaves);
+    k_add_score<<<grid, 256, 0, stream_>>>(sa);
+    ++launches_;
+    CUDA_CHECK(cudaGetLastError());
+    if (!on_device) CUDA_CHECK(cudaMemcpyAsync(score, sc, sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+  }
+
+  void GetPartition(int32_t* leaf_begin, int32_t* leaf_count, int32_t* indices) {
+    REQUIRE(inited_ && last_num_leaves_ > 0, "Train first");
+    std::vector<int32_t> b0(N_), b1(N_);
+    CUDA_CHECK(cudaMemcpy(b0.data(), idx0_.p, sizeof(int32_t) * N_, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(b1.data(), idx1_.p, sizeof(int32_t) * N_, cudaMemcpyDeviceToHost));
+    for (int l = 0; l < last_num_leaves_; ++l) {
+      const Leaf& L = h_leaves_[l];
+      leaf_begin[l] = L.begin; leaf_count[l] = L.count;
+      const std::vector<int32_t>& src = L.buf ? b1 : b0;
+      std::memcpy(indices + L.begin, src.data() + L.begin, sizeof(int32_t) * L.count);
+    }
+  }
+
+  void GetLeafHistogram(int leaf, double* out) {
+    REQUIRE(inited_ && last_num_leaves_ > 0 && leaf >= 0 && leaf < last_num_leaves_, "bad leaf");
+    ReadSlot(h_leaves_[leaf].slot, h_ctl_->g_inv, h_ctl_->h_inv, out);
+  }
+
+  void ConstructHistogram(const float* grad, const float* hess, int on_device, const int32_t* idx_host, int n_idx,
+                          double* out, float* elapsed_ms) {
+    REQUIRE(inited_, "Init first");
+    const float* g = grad; const float* h = hess;
+    if (!on_device) {
+      CUDA_CHECK(cudaMemcpyAsync(grad_stage_.p, grad, sizeof(float) * N_, cudaMemcpyHostToDevice, stream_));
+      CUDA_CHECK(cudaMemcpyAsync(hess_stage_.p, hess, sizeof(float) * N_, cudaMemcpyHostToDevice, stream_));
+      g = grad_stage_.p; h = hess_stage_.p;
+    }
+    const int32_t* bag_saved_count = nullptr; (void)bag_saved_count;
+    // prep with "no bagging" semantics over all rows: packs gh and sets the fixed-point scales
+    PrepArgs pa = MakePrepArgs(g, h);
+    pa.bag = nullptr; pa.bag_count = 0;
+    k_prep<<<prep_blocks_, kPrepThreads, 0, stream_>>>(pa);
+    k_root_init<<<1, 32, 0, stream_>>>(pa);
+    const int32_t* didx = nullptr;
+    int n = N_;
+    if (idx_host != nullptr) {
+      REQUIRE(n_idx >= 0 && n_idx <= N_, "bad index count");
+      CUDA_CHECK(cudaMemcpyAsync(idx1_.p, idx_host, sizeof(int32_t) * n_idx, cudaMemcpyHostToDevice, stream_));
+      didx = idx1_.p; n = n_idx;
+    }
+    CUDA_CHECK(cudaMemsetAsync(pool_.p, 0, sizeof(long long) * slot_stride_, stream_));
+    HistArgs ha = MakeHistArgs();
+    ha.explicit_n = n; ha.explicit_slot = 0; ha.explicit_idx = didx;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, stream_));
+    k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha);
+    CUDA_CHECK(cudaEventRecord(e1, stream_));
+    launches_ += 3;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(h_ctl_, ctl_.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (elapsed_ms) *elapsed_ms = ms;
+    if (out) ReadSlot(0, h_ctl_->g_inv, h_ctl_->h_inv, out);
+    last_num_leaves_ = 0;
+  }
+
+  void L2Gradients(const double* score, const float* label, float* grad, float* hess, int n) {
+    k_l2_gradients<<<num_sms_ * 4, 256, 0, stream_>>>(score, label, grad, hess, n);
+    ++launches_;
+    CUDA_CHECK(cudaGetLastError());
+  }
+
+  void SetProfiling(int enable) {
+    profiling_ = enable != 0;
+    if (profiling_ && hist_events_.empty()) {
+      hist_events_.resize(2 * static_cast<size_t>(params_.num_leaves));
+      for (auto& e : hist_events_) CUDA_CHECK(cudaEventCreate(&e));
+    }
+  }
+  void HistStats(int reset, double* ms, double* rows, int64_t* launches) {
+    if (ms) *ms = hist_ms_;
+    if (rows) *rows = hist_rows_;
+    if (launches) *launches = hist_launches_;
+    if (reset) { hist_ms_ = 0; hist_rows_ = 0; hist_launches_ = 0; }
+  }
+  int64_t launches() const { return launches_; }
+  cudaStream_t stream() const { return stream_; }
+
+ private:
+  void AllocTreeState() {
+    const int NL = params_.num_leaves;
+    slot_stride_ = static_cast<int64_t>(Cpad_) * kBinsPerColumn * 2;
+    pool_.alloc(static_cast<size_t>(slot_stride_) * NL);
+    leaves_.alloc(NL); splits_.alloc(NL); cand_.alloc(2 * static_cast<size_t>(F_));
+    splittable_.alloc(static_cast<size_t>(NL) * F_);
+    leaf_value_dev_.alloc(NL);
+    if (h_splits_) { cudaFreeHost(h_splits_); cudaFreeHost(h_leaves_); cudaFreeHost(h_ctl_); }
+    CUDA_CHECK(cudaMallocHost(&h_splits_, sizeof(SplitRec) * NL));
+    CUDA_CHECK(cudaMallocHost(&h_leaves_, sizeof(Leaf) * NL));
+    CUDA_CHECK(cudaMallocHost(&h_ctl_, sizeof(Ctl)));
+    for (auto& e : hist_events_) cudaEventDestroy(e);
+    hist_events_.clear();
+    if (profiling_) SetProfiling(1);
+    InvalidateGraph();
+  }
+
+  PrepArgs MakePrepArgs(const float* g, const float* h) {
+    PrepArgs pa;
+    pa.grad = g; pa.hess = h; pa.gh = gh_.p; pa.idx0 = idx0_.p;
+    pa.bag = bag_count_ >= 0 ? bag_.p : nullptr; pa.bag_count = bag_count_ >= 0 ? bag_count_ : 0;
+    pa.num_data = N_; pa.partials = partials_.p; pa.leaves = leaves_.p; pa.ctl = ctl_.p; pa.params = params_;
+    pa.max_leaves = params_.num_leaves; pa.num_partials = prep_blocks_;
+    return pa;
+  }
+  HistArgs MakeHistArgs() {
+    HistArgs ha;
+    ha.bins = bins_.p; ha.pitch = pitch_; ha.gh = gh_.p; ha.idx0 = idx0_.p; ha.idx1 = idx1_.p;
+    ha.leaves = leaves_.p; ha.ctl = ctl_.p; ha.pool = reinterpret_cast<unsigned long long*>(pool_.p);
+    ha.slot_stride = slot_stride_; ha.num_colgroups = Cpad_ / kColGroup; ha.min_rows_per_item = 2048;
+    ha.explicit_n = -1; ha.explicit_slot = 0; ha.explicit_idx = nullptr;
+    return ha;
+  }
+
+  // The fixed per-tree launch sequence (see file header).
+  void EnqueueTree(const float* g, const float* h) {
+    const int NL = params_.num_leaves;
+    PrepArgs pa = MakePrepArgs(g, h);
+    HistArgs ha = MakeHistArgs();
+    ScanArgs sa;
+    sa.feat = feat_.p; sa.feature_used = have_feature_mask_ ? feature_used_.p : nullptr; sa.num_features = F_;
+    sa.params = params_; sa.leaves = leaves_.p; sa.ctl = ctl_.p; sa.pool = pool_.p; sa.slot_stride = slot_stride_;
+    sa.splittable = splittable_.p; sa.cand = cand_.p;
+    SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p};
+    PartArgs pt;
+    pt.bins = bins_.p; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flags = flags_.p;
+    pt.block_left = block_left_.p; pt.leaves = leaves_.p; pt.ctl = ctl_.p; pt.splits = splits_.p; pt.params = params_;
+    const int scan_blocks = (F_ + kScanWarps - 1) / kScanWarps;
+    int hist_ev = 0;
+
+    k_prep<<<prep_blocks_, kPrepThreads, 0, stream_>>>(pa);
+    k_root_init<<<1, 32, 0, stream_>>>(pa);
+    CUDA_CHECK(cudaMemsetAsync(splittable_.p, 1, static_cast<size_t>(NL) * F_, stream_));
+    launches_ += 2;
+    for (int it = 0; it < NL - 1 + 1; ++it) {
+      // it == 0: root pass; it >= 1: apply split it-1, then find splits for its two children
+      if (it > 0) {
+        k_part_flags<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
+        k_part_scatter<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
+        launches_ += 2;
+        if (it == NL - 1) break;   // the tree is full: no need to look for further splits
+      }
+      const int slot = it;         // fresh pool slot of the leaf histogrammed in this iteration
+      CUDA_CHECK(cudaMemsetAsync(pool_.p + static_cast<size_t>(slot) * slot_stride_, 0, sizeof(long long) * slot_stride_, stream_));
+      if (profiling_) CUDA_CHECK(cudaEventRecord(hist_events_[2 * hist_ev], stream_));
+      k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha);
+      if (profiling_) { CUDA_CHECK(cudaEventRecord(hist_events_[2 * hist_ev + 1], stream_)); ++hist_ev; }
+      k_scan<<<scan_blocks, kScanWarps * 32, 0, stream_>>>(sa);
+      k_select<<<1, 256, 0, stream_>>>(se);
+      launches_ += 3;
+    }
+    hist_events_used_ = hist_ev;
+    CUDA_CHECK(cudaGetLastError());
+  }
+
+  void BuildGraph(const float* g, const float* h) {
+    InvalidateGraph();
+    const int64_t before = launches_;
+    CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    try {
+      EnqueueTree(g, h);
+    } catch (...) {
+      cudaGraph_t junk = nullptr;
+      cudaStreamEndCapture(stream_, &junk);
+      if (junk) cudaGraphDestroy(junk);
+      throw;
+    }
+    CUDA_CHECK(cudaStreamEndCapture(stream_, &graph_));
+    CUDA_CHECK(cudaGraphInstantiate(&graph_exec_, graph_, 0));
+    launches_per_tree_ = launches_ - before;
+    launches_ = before;
+    graph_g_ = g; graph_h_ = h;
+  }
+
+  void InvalidateGraph() {
+    if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
+  }
+
+  void CollectHistTimes() {
+    // smaller-leaf row counts of every histogram pass are recoverable from the split records
+    for (int i = 0; i < hist_events_used_; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, hist_events_[2 * i], hist_events_[2 * i + 1]) == cudaSuccess) hist_ms_ += ms;
+    }
+    const int n_leaves = h_ctl_->num_leaves;
+    double rows = h_ctl_->root_count;
+    for (int i = 0; i < n_leaves - 1; ++i) {
+      if (i == params_.num_leaves - 2) break;   // children of the last split are never histogrammed
+      rows += std::min(h_splits_[i].left_count, h_splits_[i].right_count);
+    }
+    hist_rows_ += rows;
+    hist_launches_ += hist_events_used_;
+  }
+
+  void ReadSlot(int slot, double g_inv, double h_inv, double* out) {
+    std::vector<long long> tmp(static_cast<size_t>(C_) * kBinsPerColumn * 2);
+    CUDA_CHECK(cudaMemcpy(tmp.data(), pool_.p + static_cast<size_t>(slot) * slot_stride_, sizeof(long long) * tmp.size(), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < tmp.size(); i += 2) { out[i] = static_cast<double>(tmp[i]) * g_inv; out[i + 1] = static_cast<double>(tmp[i + 1]) * h_inv; }
+  }
+
+  void Destroy() {
+    InvalidateGraph();
+    for (auto& e : hist_events_) cudaEventDestroy(e);
+    hist_events_.clear();
+    if (h_splits_) { cudaFreeHost(h_splits_); cudaFreeHost(h_leaves_); cudaFreeHost(h_ctl_); h_splits_ = nullptr; }
+    if (stream_) { cudaStreamDestroy(stream_); stream_ = nullptr; }
+  }
+
+  LGBMB200_Config cfg_{};
+  Params params_{};
+  bool inited_ = false;
+  int device_ = 0, num_sms_ = 148;
+  cudaStream_t stream_ = nullptr;
+  int N_ = 0, C_ = 0, F_ = 0, Cpad_ = 0;
+  int64_t pitch_ = 0, slot_stride_ = 0;
+  int part_blocks_ = 296, prep_blocks_ = 296;
+  DevBuf<FeatMeta> feat_;
+  DevBuf<uint8_t> bins_, flags_, feature_used_, splittable_;
+  DevBuf<float2> gh_;
+  DevBuf<float> grad_stage_, hess_stage_;
+  DevBuf<double> score_stage_, leaf_value_dev_;
+  DevBuf<int32_t> idx0_, idx1_, block_left_, bag_;
+  DevBuf<PartialSum> partials_;
+  DevBuf<Ctl> ctl_;
+  DevBuf<Leaf> leaves_;
+  DevBuf<SplitRec> splits_;
+  DevBuf<Cand> cand_;
+  DevBuf<long long> pool_;
+  SplitRec* h_splits_ = nullptr;
+  Leaf* h_leaves_ = nullptr;
+  Ctl* h_ctl_ = nullptr;
+  bool have_feature_mask_ = false;
+  int bag_count_ = -1;
+  int last_num_leaves_ = 0;
+  cudaGraph_t graph_ = nullptr;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  const float* graph_g_ = nullptr;
+  const float* graph_h_ = nullptr;
+  int64_t launches_ = 0, launches_per_tree_ = 0;
+  bool profiling_ = false;
+  std::vector<cudaEvent_t> hist_events_;
+  int hist_events_used_ = 0;
+  double hist_ms_ = 0, hist_rows_ = 0;
+  int64_t hist_launches_ = 0;
+};
+
+}  // namespace b200
+
+// ------------------------------------------------------------------------------------------ C-ABI
+using b200::CudaError;
+using b200::Learner;
+
+#define API_BEGIN() try {
+#define API_END()                                            \
+  }                                                          \
+  catch (const CudaError& e) { b200::g_last_error = e.msg; return -1; } \
+  catch (const std::exception& e) { b200::g_last_error = e.what(); return -1; } \
+  catch (...) { b200::g_last_error = "unknown error"; return -1; } \
+  return 0;
+
+extern "C" {
+
+const char* LGBMB200_GetLastError(void) { return b200::g_last_error.c_str(); }
+
+int LGBMB200_LearnerCreate(const LGBMB200_Config* config, LGBMB200_LearnerHandle* out) {
+  API_BEGIN();
+  if (!config || !out) throw CudaError{"null argument"};
+  *out = new Learner(*config);
+  API_END();
+}
+int LGBMB200_LearnerInit(LGBMB200_LearnerHandle h, const LGBMB200_Layout* layout, const uint8_t* bins_host, int32_t is_constant_hessian) {
+  API_BEGIN();
+  if (!h || !layout || !bins_host) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->Init(*layout, bins_host, is_constant_hessian);
+  API_END();
+}
+int LGBMB200_LearnerResetConfig(LGBMB200_LearnerHandle h, const LGBMB200_Config* config) {
+  API_BEGIN();
+  if (!h || !config) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->SetConfig(*config);
+  API_END();
+}
+int LGBMB200_LearnerSetFeatureMask(LGBMB200_LearnerHandle h, const uint8_t* feature_used) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->SetFeatureMask(feature_used);
+  API_END();
+}
+int LGBMB200_LearnerSetBaggingData(LGBMB200_LearnerHandle h, const int32_t* used_indices, int32_t num_used, int32_t on_device) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->SetBagging(used_indices, num_used, on_device);
+  API_END();
+}
+int LGBMB200_LearnerTrain(LGBMB200_LearnerHandle h, const float* gradients, const float* hessians, int32_t on_device, LGBMB200_Tree* out_tree) {
+  API_BEGIN();
+  if (!h || !gradients || !hessians || !out_tree) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->Train(gradients, hessians, on_device, out_tree);
+  API_END();
+}
+int LGBMB200_LearnerAddPredictionToScore(LGBMB200_LearnerHandle h, const double* leaf_value, int32_t num_leaves, double* score, int32_t on_device) {
+  API_BEGIN();
+  if (!h || !leaf_value || !score) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->AddPredictionToScore(leaf_value, num_leaves, score, on_device);
+  API_END();
+}
+int LGBMB200_LearnerGetPartition(LGBMB200_LearnerHandle h, int32_t* leaf_begin, int32_t* leaf_count, int32_t* indices) {
+  API_BEGIN();
+  if (!h || !leaf_begin || !leaf_count || !indices) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->GetPartition(leaf_begin, leaf_count, indices);
+  API_END();
+}
+int LGBMB200_LearnerGetLeafHistogram(LGBMB200_LearnerHandle h, int32_t leaf, double* out) {
+  API_BEGIN();
+  if (!h || !out) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->GetLeafHistogram(leaf, out);
+  API_END();
+}
+int LGBMB200_LearnerConstructHistogram(LGBMB200_LearnerHandle h, const float* gradients, const float* hessians, int32_t on_device,
+                                       const int32_t* indices_host, int32_t num_indices, double* hist_out, float* elapsed_ms) {
+  API_BEGIN();
+  if (!h || !gradients || !hessians) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->ConstructHistogram(gradients, hessians, on_device, indices_host, num_indices, hist_out, elapsed_ms);
+  API_END();
+}
+int LGBMB200_L2Gradients(LGBMB200_LearnerHandle h, const double* score_dev, const float* label_dev, float* grad_dev, float* hess_dev, int32_t n) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->L2Gradients(score_dev, label_dev, grad_dev, hess_dev, n);
+  API_END();
+}
+int64_t LGBMB200_LearnerKernelLaunches(LGBMB200_LearnerHandle h) { return h ? static_cast<Learner*>(h)->launches() : 0; }
+int LGBMB200_LearnerHistStats(LGBMB200_LearnerHandle h, int32_t reset, double* hist_ms, double* hist_rows, int64_t* hist_launches) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->HistStats(reset, hist_ms, hist_rows, hist_launches);
+  API_END();
+}
+int LGBMB200_LearnerSetProfiling(LGBMB200_LearnerHandle h, int32_t enable) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->SetProfiling(enable);
+  API_END();
+}
+int LGBMB200_DeviceAlloc(void** ptr, int64_t bytes) {
+  API_BEGIN();
+  if (!ptr) throw CudaError{"null argument"};
+  CUDA_CHECK(cudaMalloc(ptr, static_cast<size_t>(bytes > 0 ? bytes : 1)));
+  API_END();
+}
+int LGBMB200_DeviceFree(void* ptr) {
+  API_BEGIN();
+  CUDA_CHECK(cudaFree(ptr));
+  API_END();
+}
+int LGBMB200_MemcpyH2D(void* dst_dev, const void* src_host, int64_t bytes) {
+  API_BEGIN();
+  CUDA_CHECK(cudaMemcpy(dst_dev, src_host, static_cast<size_t>(bytes), cudaMemcpyHostToDevice));
+  API_END();
+}
+int LGBMB200_MemcpyD2H(void* dst_host, const void* src_dev, int64_t bytes) {
+  API_BEGIN();
+  CUDA_CHECK(cudaMemcpy(dst_host, src_dev, static_cast<size_t>(bytes), cudaMemcpyDeviceToHost));
+  API_END();
+}
+int LGBMB200_LearnerFree(LGBMB200_LearnerHandle h) {
+  API_BEGIN();
+  delete static_cast<Learner*>(h);
+  API_END();
+}
+
+}  // extern "C"

@@ -1,0 +1,303 @@
+// partition_kernel.cuh — stable row-index partition after a split + per-tree preparation (sm_100a).
+//
+// Replaces: DataPartition::Split -> ParallelPartitionRunner::Run -> DenseBin::SplitInner
+// (reference src/treelearner/data_partition.hpp:101-120, include/LightGBM/utils/threading.h:92-193,
+// src/io/dense_bin.hpp:314-394), the child bookkeeping of SerialTreeLearner::SplitInner
+// (src/treelearner/serial_tree_learner.cpp:769-925) and BeforeTrain/LeafSplits::Init (:291-341).
+//
+// Two launches per split, no host involvement:
+//   k_part_flags   : go-left flag per row (decoded-bin form of SplitInner's 8 template cases) + per-block
+//                    left counts.  Reads one byte per row straight from the row-major bin matrix.
+//   k_part_scatter : every block re-derives its write offsets from the block counts, then writes the
+//                    left rows followed by the right rows into the OTHER index buffer (ping-pong, so no
+//                    copy-back pass as in the reference's two-buffer runner).  Stable in both halves.
+//                    Thread 0 of block 0 then plays SplitInner: child leaf records, smaller/larger
+//                    choice, histogram-slot hand-over, BeforeFindBestSplit gates, the split record.
+#pragma once
+#include "types.cuh"
+
+namespace b200 {
+
+constexpr int kPartThreads = 256;
+
+struct PartArgs {
+  const uint8_t* bins;
+  int64_t pitch;
+  int32_t* idx0;
+  int32_t* idx1;
+  uint8_t* flags;          // [num_data] scratch
+  int32_t* block_left;     // [gridDim.x]
+  Leaf* leaves;
+  Ctl* ctl;
+  SplitRec* splits;        // [num_leaves-1] output records
+  Params params;
+};
+
+// Decoded form of DenseBin::SplitInner (dense_bin.hpp:314-394): with b = the feature's bin of the row,
+//   missing Zero & b == default_bin  -> default side
+//   missing NaN  & b == num_bin - 1  -> default side
+//   otherwise                        -> left iff b <= threshold
+__device__ __forceinline__ bool goes_left(uint32_t v, const FeatMeta& m, int threshold, int default_left) {
+  const int rel = static_cast<int>(v) - m.lo;
+  const int b = (rel >= 0 && rel < m.nslice) ? rel + m.offset : m.mfb;
+  if ((m.missing == 1 && b == m.default_bin) || (m.missing == 2 && b == m.num_bin - 1)) return default_left != 0;
+  return b <= threshold;
+}
+
+__device__ __forceinline__ void part_block_range(int n, int nblocks, int b, int* lo, int* hi) {
+  int per = (n + nblocks - 1) / nblocks;
+  per = (per + kPartThreads - 1) / kPartThreads * kPartThreads;
+  *lo = min(n, b * per);
+  *hi = min(n, *lo + per);
+}
+
+__global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
+  const Ctl* c = a.ctl;
+  if (!c->cur_valid) return;
+  const int n = c->cur_count, begin = c->cur_begin;
+  const int32_t* src = (c->cur_buf ? a.idx1 : a.idx0) + begin;
+  const FeatMeta m = c->cur_meta;
+  const int threshold = c->cur_threshold, default_left = c->cur_default_left;
+  int lo, hi;
+  part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
+  int cnt = 0;
+  for (int i = lo + threadIdx.x; i < hi; i += kPartThreads) {
+    const int row = __ldg(src + i);
+    const uint32_t v = __ldg(a.bins + static_cast<int64_t>(row) * a.pitch + m.col);
+    const bool left = goes_left(v, m, threshold, default_left);
+    a.flags[begin + i] = left ? 1 : 0;
+    cnt += left ? 1 : 0;
+  }
+  __shared__ int s_cnt[kPartThreads / 32];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kPartThreads / 32; ++w) t += s_cnt[w];
+    a.block_left[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a) {
+  Ctl* c = a.ctl;
+  if (!c->cur_valid) return;
+  const int n = c->cur_count, begin = c->cur_begin;
+  const int32_t* src = (c->cur_buf ? a.idx1 : a.idx0) + begin;
+  int32_t* dst = (c->cur_buf ? a.idx0 : a.idx1) + begin;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // offsets from the per-block counts (gridDim.x <= 1024)
+  __shared__ int s_red[kPartThreads / 32];
+  __shared__ int s_before, s_total;
+  int before = 0, total = 0;
+  for (int j = tid; j < static_cast<int>(gridDim.x); j += kPartThreads) {
+    const int v = a.block_left[j];
+    total += v;
+    if (j < static_cast<int>(blockIdx.x)) before += v;
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) { total += __shfl_xor_sync(0xffffffffu, total, d); before += __shfl_xor_sync(0xffffffffu, before, d); }
+  __shared__ int s_tot[kPartThreads / 32], s_bef[kPartThreads / 32];
+  if (lane == 0) { s_tot[warp] = total; s_bef[warp] = before; }
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0, b = 0;
+#pragma unroll
+    for (int w = 0; w < kPartThreads / 32; ++w) { t += s_tot[w]; b += s_bef[w]; }
+    s_total = t; s_before = b;
+  }
+  __syncthreads();
+  const int total_left = s_total;
+  int left_run = s_before;          // lefts before the current tile (whole leaf)
+
+  int lo, hi;
+  part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
+  for (int base = lo; base < hi; base += kPartThreads) {
+    const int i = base + tid;
+    const bool valid = i < hi;
+    const int flag = valid ? a.flags[begin + i] : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int wcnt = __popc(bal);
+    const int rank_in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_red[warp] = wcnt;
+    __syncthreads();
+    int wbefore = 0, tile_left = 0;
+#pragma unroll
+    for (int w = 0; w < kPartThreads / 32; ++w) { const int v = s_red[w]; if (w < warp) wbefore += v; tile_left += v; }
+    if (valid) {
+      const int lefts_before_me = left_run + wbefore + rank_in_warp;
+      const int row = src[i];
+      if (flag) dst[lefts_before_me] = row;
+      else dst[total_left + (i - lefts_before_me)] = row;
+    }
+    left_run += tile_left;
+    __syncthreads();
+  }
+
+  // ---- SplitInner bookkeeping (one thread): serial_tree_learner.cpp:769-925, tree.h:543-585
+  if (blockIdx.x == 0 && tid == 0) {
+    const int leaf = c->cur_leaf;
+    const int right = c->num_leaves;          // next_leaf_id
+    Leaf& L = a.leaves[leaf];
+    Leaf& R = a.leaves[right];
+    const Cand s = L.best;
+    const int left_count = total_left, right_count = n - total_left;
+    SplitRec& rec = a.splits[right - 1];
+    rec.leaf = leaf; rec.feature = s.feature; rec.threshold = s.threshold; rec.default_left = s.default_left;
+    rec.left_count = left_count; rec.right_count = right_count;
+    rec.gain = s.gain; rec.lsg = s.lsg; rec.lsh = s.lsh; rec.lout = s.lout; rec.rsg = s.rsg; rec.rsh = s.rsh; rec.rout = s.rout;
+
+    const int parent_slot = L.slot, parent_depth = L.depth, child_buf = 1 - L.buf;
+    R.begin = begin + left_count; R.count = right_count; R.buf = child_buf; R.depth = parent_depth + 1;
+    R.sum_g = s.rsg; R.sum_h = s.rsh; R.output = s.rout;
+    R.best.gain = -INFINITY; R.best.feature = -1;
+    L.count = left_count; L.buf = child_buf; L.depth = parent_depth + 1;
+    L.sum_g = s.lsg; L.sum_h = s.lsh; L.output = s.lout;
+    L.best.gain = -INFINITY; L.best.feature = -1;
+    // smaller / larger (serial_tree_learner.cpp:858): the parent's pool slot becomes the larger child's,
+    // the smaller child gets the fresh slot `right` (one new slot per split, zeroed by the host sequence)
+    int smaller, larger;
+    if (left_count < right_count) { smaller = leaf; larger = right; } else { smaller = right; larger = leaf; }
+    a.leaves[larger].slot = parent_slot;
+    a.leaves[smaller].slot = right;
+    c->smaller = smaller; c->larger = larger;
+    c->num_leaves = right + 1;
+    // BeforeFindBestSplit (serial_tree_learner.cpp:343-370)
+    int do_find = 1;
+    if (a.params.max_depth > 0 && parent_depth + 1 >= a.params.max_depth) do_find = 0;
+    if (right_count < a.params.min_data_in_leaf * 2 && left_count < a.params.min_data_in_leaf * 2) do_find = 0;
+    c->do_find = do_find;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-tree preparation: pack (grad,hess), identity index list, root sums (BeforeTrain).
+struct PrepArgs {
+  const float* grad;
+  const float* hess;
+  float2* gh;
+  int32_t* idx0;
+  const int32_t* bag;       // device bag indices or nullptr
+  int32_t bag_count;
+  int32_t num_data;
+  PartialSum* partials;     // [gridDim.x]
+  Leaf* leaves;
+  Ctl* ctl;
+  Params params;
+  int32_t max_leaves;
+  int32_t num_partials;
+};
+
+constexpr int kPrepThreads = 256;
+
+__global__ void __launch_bounds__(kPrepThreads) k_prep(const PrepArgs a) {
+  // fixed block -> row-range assignment and a fixed-order final reduction => deterministic root sums
+  const int N = a.num_data;
+  const int nb = gridDim.x;
+  int per = (N + nb - 1) / nb;
+  per = (per + kPrepThreads - 1) / kPrepThreads * kPrepThreads;
+  const int lo = min(N, static_cast<int>(blockIdx.x) * per), hi = min(N, lo + per);
+  double sg = 0.0, sh = 0.0; float mg = 0.f, mh = 0.f;
+  for (int i = lo + threadIdx.x; i < hi; i += kPrepThreads) {
+    const float g = a.grad[i], h = a.hess[i];
+    a.gh[i] = make_float2(g, h);
+    mg = fmaxf(mg, fabsf(g)); mh = fmaxf(mh, fabsf(h));
+    if (a.bag == nullptr) { sg += g; sh += h; a.idx0[i] = i; }
+  }
+  if (a.bag != nullptr) {
+    int perb = (a.bag_count + nb - 1) / nb;
+    perb = (perb + kPrepThreads - 1) / kPrepThreads * kPrepThreads;
+    const int blo = min(a.bag_count, static_cast<int>(blockIdx.x) * perb), bhi = min(a.bag_count, blo + perb);
+    for (int i = blo + threadIdx.x; i < bhi; i += kPrepThreads) {
+      const int r = a.bag[i];
+      a.idx0[i] = r;
+      sg += a.grad[r]; sh += a.hess[r];
+    }
+  }
+  __shared__ double s_g[kPrepThreads / 32], s_h[kPrepThreads / 32];
+  __shared__ float s_mg[kPrepThreads / 32], s_mh[kPrepThreads / 32];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    sg += __shfl_xor_sync(0xffffffffu, sg, d); sh += __shfl_xor_sync(0xffffffffu, sh, d);
+    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, d)); mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, d));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_g[warp] = sg; s_h[warp] = sh; s_mg[warp] = mg; s_mh[warp] = mh; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    PartialSum p; p.g = 0; p.h = 0; p.gmax = 0; p.hmax = 0;
+    for (int w = 0; w < kPrepThreads / 32; ++w) { p.g += s_g[w]; p.h += s_h[w]; p.gmax = fmaxf(p.gmax, s_mg[w]); p.hmax = fmaxf(p.hmax, s_mh[w]); }
+    a.partials[blockIdx.x] = p;
+  }
+}
+
+__device__ __forceinline__ double pow2_scale(double bound) {
+  // largest power of two s with bound * s < 2^61 (bound = rows * max|value|)
+  if (!(bound > 0.0)) return 1.0;
+  int e; frexp(bound, &e);            // bound < 2^e
+  int k = 61 - e;
+  if (k > 1000) k = 1000;
+  if (k < -1000) k = -1000;
+  return ldexp(1.0, k);
+}
+
+__global__ void k_root_init(const PrepArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double sg = 0.0, sh = 0.0; float mg = 0.f, mh = 0.f;
+  for (int b = 0; b < a.num_partials; ++b) { sg += a.partials[b].g; sh += a.partials[b].h; mg = fmaxf(mg, a.partials[b].gmax); mh = fmaxf(mh, a.partials[b].hmax); }
+  const int n_root = a.bag ? a.bag_count : a.num_data;
+  for (int i = 0; i < a.max_leaves; ++i) {
+    Leaf& L = a.leaves[i];
+    L.begin = 0; L.count = 0; L.buf = 0; L.depth = 0; L.slot = 0; L.pad = 0;
+    L.sum_g = 0; L.sum_h = 0; L.output = 0;
+    L.best.gain = -INFINITY; L.best.feature = -1;
+  }
+  Leaf& R = a.leaves[0];
+  R.count = n_root; R.sum_g = sg; R.sum_h = sh;
+  // root output (serial_tree_learner.cpp:207-211): L1 + max_delta_step, no smoothing
+  {
+    double ret = -sg;
+    if (a.params.l1 > 0.0) { double r = fabs(sg) - a.params.l1; if (r < 0) r = 0; ret = -((sg > 0) - (sg < 0)) * r; }
+    ret /= (sh + a.params.l2);
+    if (a.params.max_delta_step > 0 && fabs(ret) > a.params.max_delta_step) ret = ((ret > 0) - (ret < 0)) * a.params.max_delta_step;
+    R.output = ret;
+  }
+  Ctl* c = a.ctl;
+  c->cur_valid = 1; c->cur_leaf = 0; c->cur_begin = 0; c->cur_count = n_root; c->cur_buf = 0;
+  c->smaller = 0; c->larger = -1; c->do_find = 1; c->num_leaves = 1;
+  // BeforeFindBestSplit at the root: too few rows to ever split
+  if (n_root < a.params.min_data_in_leaf * 2) c->do_find = 0;
+  c->g_scale = pow2_scale(static_cast<double>(n_root) * mg);
+  c->h_scale = pow2_scale(static_cast<double>(n_root) * mh);
+  c->g_inv = 1.0 / c->g_scale; c->h_inv = 1.0 / c->h_scale;
+  c->root_sum_g = sg; c->root_sum_h = sh; c->root_count = n_root; c->root_identity = a.bag ? 0 : 1;
+}
+
+// AddPredictionToScore (serial_tree_learner.h:100-115): one grid row per leaf
+struct ScoreArgs {
+  const Leaf* leaves;
+  const int32_t* idx0;
+  const int32_t* idx1;
+  const double* leaf_value;   // device [num_leaves]
+  double* score;
+};
+
+__global__ void __launch_bounds__(256) k_add_score(const ScoreArgs a) {
+  const Leaf& L = a.leaves[blockIdx.y];
+  const int32_t* idx = (L.buf ? a.idx1 : a.idx0) + L.begin;
+  const double v = a.leaf_value[blockIdx.y];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < L.count; i += gridDim.x * 256) a.score[idx[i]] += v;
+}
+
+// L2 objective gradients (regression_objective.hpp:127-142, unweighted): g = score - label, h = 1
+__global__ void k_l2_gradients(const double* score, const float* label, float* grad, float* hess, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    grad[i] = static_cast<float>(score[i] - label[i]);
+    hess[i] = 1.0f;
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,450 @@
+// scan_kernel.cuh — FixHistogram + histogram subtraction + split-gain scan, fused (sm_100a).
+//
+// Replaces: Dataset::FixHistogram (reference src/io/dataset.cpp:1519-1537), FeatureHistogram::Subtract
+// (src/treelearner/feature_histogram.hpp:96-145), FeatureHistogram::FindBestThreshold ->
+// FindBestThresholdSequentially (feature_histogram.hpp:165-175, :830-1057) and the per-leaf arg-max of
+// SerialTreeLearner::FindBestSplitsFromHistograms (src/treelearner/serial_tree_learner.cpp:480-624).
+//
+// One warp per feature handles BOTH children of the last split: it loads the smaller child's slice
+// (<=256 bins, 8 per lane), fixes the most-frequent-bin entry, scans it, then forms
+// larger = parent - smaller in exact int64 arithmetic (written back in place into the parent's pool
+// slot, which becomes the larger child's) and scans that.  The sequential right->left / left->right
+// accumulation of the reference becomes: lane-local totals -> 5-step warp shuffle scan of lane
+// offsets -> lane-local sequential pass evaluating candidates -> warp arg-max with the reference's
+// tie-break (first candidate in scan order wins, strict '>').
+//
+// Tie consistency: in the reference two thresholds separated by an EMPTY bin give bit-identical sums
+// and the first in scan order wins.  A parallel prefix is not bit-consistent across lanes, so the
+// rule is applied explicitly: a candidate whose just-accumulated bin is empty is a duplicate of the
+// previous candidate and is skipped.  With the int64 pool an empty bin is exactly (0,0).
+#pragma once
+#include "types.cuh"
+
+namespace b200 {
+
+struct GainCfg {
+  int use_l1, use_max_output, use_smoothing;
+  double l1, l2, max_delta_step, smoothing;
+};
+
+__device__ __forceinline__ GainCfg make_gain_cfg(const Params& P) {
+  GainCfg c;
+  c.use_l1 = P.l1 > 0.0;
+  c.use_max_output = P.max_delta_step > 0.0;
+  c.use_smoothing = P.path_smooth > B200_KEPS;
+  c.l1 = P.l1; c.l2 = P.l2; c.max_delta_step = P.max_delta_step; c.smoothing = P.path_smooth;
+  return c;
+}
+
+__device__ __forceinline__ double sign_of(double x) { return static_cast<double>((x > 0.0) - (x < 0.0)); }
+
+// feature_histogram.hpp:711-714
+__device__ __forceinline__ double threshold_l1(double s, double l1) {
+  double r = fabs(s) - l1;
+  if (r < 0.0) r = 0.0;
+  return sign_of(s) * r;
+}
+
+// feature_histogram.hpp:716-738 CalculateSplittedLeafOutput (no monotone constraints)
+__device__ __forceinline__ double leaf_output(const GainCfg& c, double sg, double sh, int n, double parent_output) {
+  double ret = c.use_l1 ? -threshold_l1(sg, c.l1) / (sh + c.l2) : -sg / (sh + c.l2);
+  if (c.use_max_output) {
+    if (c.max_delta_step > 0 && fabs(ret) > c.max_delta_step) ret = sign_of(ret) * c.max_delta_step;
+  }
+  if (c.use_smoothing) {
+    const double w = n / c.smoothing;
+    ret = ret * w / (w + 1) + parent_output / (w + 1);
+  }
+  return ret;
+}
+
+// feature_histogram.hpp:799-828 GetLeafGain / GetLeafGainGivenOutput
+__device__ __forceinline__ double leaf_gain(const GainCfg& c, double sg, double sh, int n, double parent_output) {
+  const double g = c.use_l1 ? threshold_l1(sg, c.l1) : sg;
+  if (!c.use_max_output && !c.use_smoothing) return (g * g) / (sh + c.l2);
+  const double out = leaf_output(c, sg, sh, n, parent_output);
+  return -(2.0 * g * out + (sh + c.l2) * out * out);
+}
+
+__device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+
+struct DirBest {
+  double gain, slg, slh;
+  int threshold, left_count, pos;   // pos: rank in scan order (smaller = earlier)
+};
+
+// One scan direction over the lane's 8 slice entries g[k], h[k] (entry e = lane*8+k <-> bin e+offset).
+// Returns the warp-wide best candidate (all lanes hold the same result); *any_splittable is OR-ed.
+template <bool REVERSE>
+__device__ __forceinline__ DirBest scan_direction(const double (&g)[8], const double (&h)[8], int lane, const FeatMeta& m,
+                                                  const Params& P, const GainCfg& gc, double sum_g, double sum_h,
+                                                  int num_data, double min_gain_shift, double parent_output,
+                                                  bool skip_default, bool na_as_missing, int* any_splittable) {
+  const double cnt_factor = num_data / sum_h;
+  const int nslice = m.nslice, offset = m.offset;
+  // entries that take part in the accumulation (feature_histogram.hpp:861-867 / :964-970)
+  int e_lo, e_hi;
+  if (REVERSE) { e_lo = 1 - offset; e_hi = nslice - 1 - (na_as_missing ? 1 : 0); }
+  else { e_lo = 0; e_hi = m.num_bin - 2 - offset; }
+  const int skip_e = skip_default ? (m.default_bin - offset) : -1000;
+
+  // pass 1: lane totals
+  double tg = 0.0, th = 0.0; int tc = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = lane * 8 + k;
+    if (e >= e_lo && e <= e_hi && e != skip_e) { tg += g[k]; th += h[k]; tc += static_cast<int>(h[k] * cnt_factor + 0.5); }
+  }
+  // inclusive scan of lane totals in scan order (REVERSE: lanes above me come first), then shift by one
+  double og = tg, oh = th; int oc = tc;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    if (REVERSE) {
+      const double xg = shfl_down_d(og, d), xh = shfl_down_d(oh, d); const int xc = __shfl_down_sync(0xffffffffu, oc, d);
+      if (lane + d < 32) { og += xg; oh += xh; oc += xc; }
+    } else {
+      const double xg = shfl_up_d(og, d), xh = shfl_up_d(oh, d); const int xc = __shfl_up_sync(0xffffffffu, oc, d);
+      if (lane >= d) { og += xg; oh += xh; oc += xc; }
+    }
+  }
+  {
+    const double ig = REVERSE ? shfl_down_d(og, 1) : shfl_up_d(og, 1);
+    const double ih = REVERSE ? shfl_down_d(oh, 1) : shfl_up_d(oh, 1);
+    const int ic = REVERSE ? __shfl_down_sync(0xffffffffu, oc, 1) : __shfl_up_sync(0xffffffffu, oc, 1);
+    const bool first = REVERSE ? (lane == 31) : (lane == 0);
+    og = first ? 0.0 : ig; oh = first ? 0.0 : ih; oc = first ? 0 : ic;
+  }
+
+  // running sums at the start of this lane's entries
+  double ag, ah; int ac;
+  if (REVERSE) { ag = og; ah = B200_KEPS + oh; ac = oc; }
+  else {
+    ag = og; ah = B200_KEPS + oh; ac = oc;
+    if (na_as_missing && offset == 1) {
+      // implicit bin 0 = total - sum(all slice entries) (feature_histogram.hpp:945-961)
+      double ag_all = 0.0, ah_all = 0.0; int ac_all = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = lane * 8 + k;
+        if (e < nslice) { ag_all += g[k]; ah_all += h[k]; ac_all += static_cast<int>(h[k] * cnt_factor + 0.5); }
+      }
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        ag_all += __shfl_xor_sync(0xffffffffu, ag_all, d);
+        ah_all += __shfl_xor_sync(0xffffffffu, ah_all, d);
+        ac_all += __shfl_xor_sync(0xffffffffu, ac_all, d);
+      }
+      ag = (sum_g - ag_all) + og;
+      ah = ((sum_h - B200_KEPS) - ah_all) + oh;
+      ac = (num_data - ac_all) + oc;
+    }
+  }
+
+  DirBest best; best.gain = -INFINITY; best.slg = 0; best.slh = 0; best.threshold = 0; best.left_count = 0; best.pos = 0x7fffffff;
+  int splittable = 0;
+
+  auto evaluate = [&](double acc_g, double acc_h, int acc_c, int threshold, int pos) {
+    // acc_* are the sums of the side being accumulated (right for REVERSE, left for forward)
+    if (acc_c < P.min_data_in_leaf || acc_h < P.min_sum_hessian) return;
+    const int other_c = num_data - acc_c;
+    if (other_c < P.min_data_in_leaf) return;
+    const double other_h = sum_h - acc_h;
+    if (other_h < P.min_sum_hessian) return;
+    const double other_g = sum_g - acc_g;
+    double cur;
+    if (REVERSE) cur = leaf_gain(gc, other_g, other_h, other_c, parent_output) + leaf_gain(gc, acc_g, acc_h, acc_c, parent_output);
+    else cur = leaf_gain(gc, acc_g, acc_h, acc_c, parent_output) + leaf_gain(gc, other_g, other_h, other_c, parent_output);
+    if (cur <= min_gain_shift) return;
+    splittable = 1;
+    if (cur > best.gain) {
+      best.gain = cur; best.threshold = threshold; best.pos = pos;
+      if (REVERSE) { best.slg = other_g; best.slh = other_h; best.left_count = other_c; }
+      else { best.slg = acc_g; best.slh = acc_h; best.left_count = acc_c; }
+    }
+  };
+
+  if (!REVERSE && na_as_missing && offset == 1 && lane == 0) {
+    // the t = -1 candidate: only the implicit bin 0 on the left (threshold 0)
+    evaluate(ag, ah, ac, 0, -1);
+  }
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const int k = REVERSE ? 7 - kk : kk;
+    const int e = lane * 8 + k;
+    if (e >= e_lo && e <= e_hi && e != skip_e) {
+      ag += g[k]; ah += h[k]; ac += static_cast<int>(h[k] * cnt_factor + 0.5);
+      // duplicate-of-previous rule: an empty bin does not create a new candidate
+      const bool empty = (g[k] == 0.0 && h[k] == 0.0);
+      if (!empty) {
+        if (REVERSE) evaluate(ag, ah, ac, e - 1 + offset, 255 - e);
+        else evaluate(ag, ah, ac, e + offset, e);
+      }
+    }
+  }
+
+  // warp arg-max: larger gain, then earlier scan position
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const double og2 = __shfl_xor_sync(0xffffffffu, best.gain, d);
+    const int op = __shfl_xor_sync(0xffffffffu, best.pos, d);
+    const double oslg = __shfl_xor_sync(0xffffffffu, best.slg, d);
+    const double oslh = __shfl_xor_sync(0xffffffffu, best.slh, d);
+    const int ot = __shfl_xor_sync(0xffffffffu, best.threshold, d);
+    const int olc = __shfl_xor_sync(0xffffffffu, best.left_count, d);
+    if (og2 > best.gain || (og2 == best.gain && op < best.pos)) {
+      best.gain = og2; best.pos = op; best.slg = oslg; best.slh = oslh; best.threshold = ot; best.left_count = olc;
+    }
+  }
+  if (__any_sync(0xffffffffu, splittable)) *any_splittable = 1;
+  return best;
+}
+
+// FeatureHistogram::FindBestThreshold for one feature; all lanes return the same Cand.
+__device__ __forceinline__ Cand find_best_threshold(const double (&g)[8], const double (&h)[8], int lane, int f,
+                                                    const FeatMeta& m, const Params& P, const GainCfg& gc,
+                                                    double sum_g, double sum_h_in, int num_data, double parent_output,
+                                                    int* is_splittable) {
+  Cand out;
+  out.gain = -INFINITY; out.feature = f; out.threshold = 0; out.default_left = 1;
+  out.lsg = out.lsh = out.lout = out.rsg = out.rsh = out.rout = 0.0; out.left_count = out.right_count = 0; out.pad = 0;
+  const double sum_h = sum_h_in + 2 * B200_KEPS;
+  const double min_gain_shift = leaf_gain(gc, sum_g, sum_h, num_data, parent_output) + P.min_gain_to_split;
+  int splittable = 0;
+
+  auto apply = [&](const DirBest& b, bool reverse) {
+    // feature_histogram.hpp:1031-1056
+    if (splittable && b.gain > out.gain + min_gain_shift) {
+      out.threshold = b.threshold;
+      out.lout = leaf_output(gc, b.slg, b.slh, b.left_count, parent_output);
+      out.left_count = b.left_count;
+      out.lsg = b.slg;
+      out.lsh = b.slh - B200_KEPS;
+      out.rout = leaf_output(gc, sum_g - b.slg, sum_h - b.slh, num_data - b.left_count, parent_output);
+      out.right_count = num_data - b.left_count;
+      out.rsg = sum_g - b.slg;
+      out.rsh = sum_h - b.slh - B200_KEPS;
+      out.gain = b.gain - min_gain_shift;
+      out.default_left = reverse ? 1 : 0;
+    }
+  };
+
+  // direction dispatch: feature_histogram.hpp:396-441
+  if (m.num_bin > 2 && m.missing != 0) {
+    const bool zero = (m.missing == 1);
+    DirBest r = scan_direction<true>(g, h, lane, m, P, gc, sum_g, sum_h, num_data, min_gain_shift, parent_output, zero, !zero, &splittable);
+    apply(r, true);
+    DirBest fw = scan_direction<false>(g, h, lane, m, P, gc, sum_g, sum_h, num_data, min_gain_shift, parent_output, zero, !zero, &splittable);
+    apply(fw, false);
+  } else {
+    DirBest r = scan_direction<true>(g, h, lane, m, P, gc, sum_g, sum_h, num_data, min_gain_shift, parent_output, false, false, &splittable);
+    apply(r, true);
+    if (m.missing == 2) out.default_left = 0;
+  }
+  *is_splittable = splittable;
+  return out;
+}
+
+struct ScanArgs {
+  const FeatMeta* feat;
+  const uint8_t* feature_used;      // by-tree mask or nullptr
+  int32_t num_features;
+  Params params;
+  const Leaf* leaves;
+  const Ctl* ctl;
+  long long* pool;
+  int64_t slot_stride;
+  uint8_t* splittable;              // [slot][num_features] FeatureHistogram::is_splittable_
+  Cand* cand;                       // [2][num_features]: smaller, larger
+};
+
+constexpr int kScanWarps = 8;
+
+__global__ void __launch_bounds__(kScanWarps * 32, 1) k_scan(const ScanArgs a) {
+  const Ctl* c = a.ctl;
+  if (!c->cur_valid || !c->do_find) return;
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
+  if (f >= a.num_features) return;
+  const int F = a.num_features;
+  const int smaller = c->smaller, larger = c->larger;
+  const Leaf& LS = a.leaves[smaller];
+  Cand none; none.gain = -INFINITY; none.feature = -1; none.threshold = 0; none.default_left = 1;
+  none.lsg = none.lsh = none.lout = none.rsg = none.rsh = none.rout = 0.0; none.left_count = none.right_count = 0; none.pad = 0;
+
+  bool used = (a.feature_used == nullptr) || a.feature_used[f];
+  uint8_t* sp_small = a.splittable + static_cast<int64_t>(LS.slot) * F;
+  uint8_t* sp_large = larger >= 0 ? a.splittable + static_cast<int64_t>(a.leaves[larger].slot) * F : nullptr;
+  if (used && sp_large != nullptr && !sp_large[f]) {
+    // parent was not splittable on this feature (serial_tree_learner.cpp:397-402)
+    if (lane == 0) sp_small[f] = 0;
+    used = false;
+  }
+  if (!used) {
+    if (lane == 0) { a.cand[f] = none; a.cand[F + f] = none; }
+    return;
+  }
+
+  const FeatMeta m = a.feat[f];
+  const GainCfg gc = make_gain_cfg(a.params);
+  const double g_inv = c->g_inv, h_inv = c->h_inv;
+  const int64_t slice = (static_cast<int64_t>(m.col) * kBinsPerColumn + m.lo) * 2;
+  long long* hs = a.pool + static_cast<int64_t>(LS.slot) * a.slot_stride + slice;
+
+  // ---- smaller child: load slice, FixHistogram, scan
+  long long ig[8], ih[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = lane * 8 + k;
+    if (e < m.nslice) {
+      const longlong2 v = *reinterpret_cast<const longlong2*>(hs + 2 * e);
+      ig[k] = v.x; ih[k] = v.y;
+    } else { ig[k] = 0; ih[k] = 0; }
+  }
+  if (m.mfb > 0) {
+    // Dataset::FixHistogram: entry[mfb] = leaf total - sum(other entries), exact in fixed point
+    long long og = 0, oh = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (lane * 8 + k != m.mfb) { og += ig[k]; oh += ih[k]; } }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { og += __shfl_xor_sync(0xffffffffu, og, d); oh += __shfl_xor_sync(0xffffffffu, oh, d); }
+    const long long tg = __double2ll_rn(LS.sum_g * c->g_scale) - og;
+    const long long th = __double2ll_rn(LS.sum_h * c->h_scale) - oh;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (lane * 8 + k == m.mfb) {
+        ig[k] = tg; ih[k] = th;
+        *reinterpret_cast<longlong2*>(hs + 2 * m.mfb) = make_longlong2(tg, th);
+      }
+    }
+  }
+  double g[8], h[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { h[k] = static_cast<double>(ih[k]) * h_inv; g[k] = (ih[k] == 0) ? 0.0 : static_cast<double>(ig[k]) * g_inv; }
+
+  const double po_small = (c->num_leaves == 1)
+      ? leaf_output(GainCfg{1, 1, 0, a.params.l1, a.params.l2, a.params.max_delta_step, a.params.path_smooth}, LS.sum_g, LS.sum_h, LS.count, 0.0)
+      : LS.output;
+  int splittable = 0;
+  Cand cs = find_best_threshold(g, h, lane, f, m, a.params, gc, LS.sum_g, LS.sum_h, LS.count, po_small, &splittable);
+  if (lane == 0) { a.cand[f] = cs; sp_small[f] = static_cast<uint8_t>(splittable); }
+
+  if (larger < 0) { if (lane == 0) a.cand[F + f] = none; return; }
+
+  // ---- larger child = parent - smaller (exact), in place in the parent's slot
+  const Leaf& LL = a.leaves[larger];
+  long long* hl = a.pool + static_cast<int64_t>(LL.slot) * a.slot_stride + slice;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = lane * 8 + k;
+    if (e < m.nslice) {
+      longlong2 v = *reinterpret_cast<const longlong2*>(hl + 2 * e);
+      v.x -= ig[k]; v.y -= ih[k];
+      *reinterpret_cast<longlong2*>(hl + 2 * e) = v;
+      h[k] = static_cast<double>(v.y) * h_inv;
+      g[k] = (v.y == 0) ? 0.0 : static_cast<double>(v.x) * g_inv;
+    } else { g[k] = 0.0; h[k] = 0.0; }
+  }
+  splittable = 0;
+  Cand cl = find_best_threshold(g, h, lane, f, m, a.params, gc, LL.sum_g, LL.sum_h, LL.count, LL.output, &splittable);
+  if (lane == 0) { a.cand[F + f] = cl; sp_large[f] = static_cast<uint8_t>(splittable); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_select: per-leaf arg-max over features (SplitInfo::operator>, split_info.hpp:138-164), then the
+// arg-max over leaves (array_args.h:45-60) and the snapshot of the split to apply next.
+struct SelectArgs {
+  const FeatMeta* feat;
+  int32_t num_features;
+  int32_t max_leaves;
+  Leaf* leaves;
+  Ctl* ctl;
+  const Cand* cand;
+};
+
+__device__ __forceinline__ bool cand_better(double ga, int fa_real, double gb, int fb_real) {
+  if (ga != gb) return ga > gb;
+  return fa_real < fb_real;
+}
+
+__global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
+  Ctl* c = a.ctl;
+  if (!c->cur_valid) return;
+  __shared__ double s_gain[256];
+  __shared__ int s_real[256];
+  __shared__ int s_idx[256];
+  const int tid = threadIdx.x;
+  const int F = a.num_features;
+  const int smaller = c->smaller, larger = c->larger;
+
+  for (int which = 0; which < 2; ++which) {
+    const int leaf = which == 0 ? smaller : larger;
+    if (leaf < 0) continue;
+    double bg = -INFINITY; int br = 0x7fffffff, bi = -1;
+    if (c->do_find) {
+      for (int f = tid; f < F; f += 256) {
+        const Cand& cd = a.cand[which * F + f];
+        if (cd.feature < 0) continue;
+        const int real = a.feat[f].real_index;
+        if (cand_better(cd.gain, real, bg, br)) { bg = cd.gain; br = real; bi = f; }
+      }
+    }
+    s_gain[tid] = bg; s_real[tid] = br; s_idx[tid] = bi;
+    __syncthreads();
+    for (int st = 128; st >= 1; st >>= 1) {
+      if (tid < st) {
+        if (cand_better(s_gain[tid + st], s_real[tid + st], s_gain[tid], s_real[tid])) {
+          s_gain[tid] = s_gain[tid + st]; s_real[tid] = s_real[tid + st]; s_idx[tid] = s_idx[tid + st];
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      Leaf& L = a.leaves[leaf];
+      if (s_idx[0] >= 0) L.best = a.cand[which * F + s_idx[0]];
+      else { L.best.gain = -INFINITY; L.best.feature = -1; }
+    }
+    __syncthreads();
+  }
+
+  // arg-max over all leaf slots (ungrown leaves hold gain = -inf, feature = -1)
+  {
+    double bg = -INFINITY; int br = 0x7fffffff, bi = 0x7fffffff;
+    for (int i = tid; i < a.max_leaves; i += 256) {
+      const Cand& cd = a.leaves[i].best;
+      const int real = cd.feature < 0 ? 0x7fffffff : a.feat[cd.feature].real_index;
+      // first maximum in leaf order: strict operator> (array_args.h:52-58)
+      if (cand_better(cd.gain, real, bg, br) || (bi == 0x7fffffff)) { bg = cd.gain; br = real; bi = i; }
+    }
+    s_gain[tid] = bg; s_real[tid] = br; s_idx[tid] = bi;
+    __syncthreads();
+    for (int st = 128; st >= 1; st >>= 1) {
+      if (tid < st) {
+        const bool other_valid = s_idx[tid + st] != 0x7fffffff;
+        const bool mine_valid = s_idx[tid] != 0x7fffffff;
+        bool take = false;
+        if (other_valid && !mine_valid) take = true;
+        else if (other_valid && mine_valid) {
+          if (cand_better(s_gain[tid + st], s_real[tid + st], s_gain[tid], s_real[tid])) take = true;
+          else if (!cand_better(s_gain[tid], s_real[tid], s_gain[tid + st], s_real[tid + st]) && s_idx[tid + st] < s_idx[tid]) take = true;
+        }
+        if (take) { s_gain[tid] = s_gain[tid + st]; s_real[tid] = s_real[tid + st]; s_idx[tid] = s_idx[tid + st]; }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const int best_leaf = s_idx[0];
+      const Leaf& L = a.leaves[best_leaf];
+      // serial_tree_learner.cpp:232: stop when the best gain is <= 0; also when the tree is full
+      if (L.best.gain <= 0.0 || L.best.feature < 0 || c->num_leaves >= a.max_leaves) {
+        c->cur_valid = 0;
+      } else {
+        c->cur_leaf = best_leaf; c->cur_begin = L.begin; c->cur_count = L.count; c->cur_buf = L.buf;
+        c->cur_feature = L.best.feature; c->cur_threshold = L.best.threshold; c->cur_default_left = L.best.default_left;
+        c->cur_meta = a.feat[L.best.feature];
+      }
+    }
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,83 @@
+// types.cuh — device-resident state of one tree learner (sm_100a).
+// Everything the per-tree launch sequence needs lives in HBM so that a whole tree is grown without
+// a single host round-trip (the reference CUDA learner synchronises 7x per split).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+constexpr int kBinsPerColumn = 256;      // one histogram column = 256 slots of (grad, hess)
+constexpr int kColGroup = 32;            // columns owned by one warp of the histogram kernel
+// meta.h:54 — kEpsilon is a *float* literal widened to double at every use in the reference.
+#define B200_KEPS (static_cast<double>(1e-15f))
+
+// Per inner feature: the layout contract (reference feature_group.h:40-76, feature_histogram.hpp:1415-1454)
+struct FeatMeta {
+  int32_t col;          // column (feature group) in the bin matrix
+  int32_t lo;           // stored value of slice entry 0  (bin_offsets_[sub_feature])
+  int32_t nslice;       // num_bin - offset entries in the histogram slice
+  int32_t num_bin;
+  int32_t offset;       // most_freq_bin == 0
+  int32_t mfb;
+  int32_t default_bin;
+  int32_t missing;      // 0 none, 1 zero, 2 nan
+  int32_t real_index;   // tie-break key (split_info.hpp:138-164)
+};
+
+struct Params {
+  int32_t num_leaves, max_depth, min_data_in_leaf, pad;
+  double min_sum_hessian, l1, l2, min_gain_to_split, max_delta_step, path_smooth;
+};
+
+// The best split found for one (leaf[, feature]) — reference split_info.hpp:22-56
+struct Cand {
+  double gain;                 // -inf when none
+  double lsg, lsh, lout;       // left sums / output
+  double rsg, rsh, rout;
+  int32_t feature;             // inner feature index, -1 when none
+  int32_t threshold;
+  int32_t default_left;
+  int32_t left_count, right_count;   // estimated (RoundInt(hess*cnt_factor)) until the partition ran
+  int32_t pad;
+};
+
+// LeafSplits + DataPartition entry + HistogramPool slot of one leaf
+struct Leaf {
+  int32_t begin, count;        // segment of the index buffer (data_partition.hpp:101-120)
+  int32_t buf;                 // which of the two ping-pong index buffers holds the segment
+  int32_t depth;
+  int32_t slot;                // histogram pool slot
+  int32_t pad;
+  double sum_g, sum_h, output; // leaf_splits.hpp: sum_gradients_, sum_hessians_, weight_
+  Cand best;                   // best_split_per_leaf_[leaf]
+};
+
+// Control block: what the next kernel in the sequence should work on.  Written by single threads of
+// the `select` / `scatter` kernels, read by every block of the following launches.
+struct Ctl {
+  // current split to apply (snapshot taken by k_select so that k_scatter's bookkeeping cannot race)
+  int32_t cur_valid;           // 0 => no further split (gain <= 0): every later kernel exits at once
+  int32_t cur_leaf, cur_begin, cur_count, cur_buf;
+  int32_t cur_feature, cur_threshold, cur_default_left;
+  FeatMeta cur_meta;
+  // leaves to histogram/scan next
+  int32_t smaller, larger;     // larger = -1 for the root pass
+  int32_t do_find;             // BeforeFindBestSplit() result (serial_tree_learner.cpp:343-370)
+  int32_t num_leaves;          // leaves grown so far
+  // fixed-point scales of the int64 histogram (power of two), set once per tree
+  double g_scale, h_scale, g_inv, h_inv;
+  double root_sum_g, root_sum_h;
+  int32_t root_count;          // rows in the root (bag size or num_data)
+  int32_t root_identity;       // 1: root index list is 0..N-1 (no bagging) => histogram skips the index load
+};
+
+// One applied split, copied back to the host once per tree (mirrors LGBMB200_Split)
+struct SplitRec {
+  int32_t leaf, feature, threshold, default_left, left_count, right_count;
+  double gain, lsg, lsh, lout, rsg, rsh, rout;
+};
+
+struct PartialSum { double g, h; float gmax, hmax; };
+
+}  // namespace b200
