@@ -67,23 +67,35 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Four rows of the lane's column, exact sequential semantics (see header comment).
-__device__ __forceinline__ void rmw4(float2* __restrict__ H, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
+__device__ __forceinline__ float2 lds64(unsigned addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(unsigned addr, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y));
+}
+
+// Four rows of the lane's column.  All four cells are loaded BEFORE any store, so rows that hit the same
+// bin see the same old value v; the new value of row j is v + (sum of the q_i, i <= j, with b_i == b_j).
+// Those partial sums do not depend on the loads and are formed while the LDS are in flight, so the
+// critical path per batch is LDS -> FADD -> STS.  Stores are issued in row order: the last store to a
+// cell carries the complete sum.  Fixed evaluation order => bitwise run-to-run determinism.
+__device__ __forceinline__ void rmw4(unsigned hbase, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
                                      float4 q01, float4 q23) {
-  float2* p0 = H + b0 * 32;
-  float2* p1 = H + b1 * 32;
-  float2* p2 = H + b2 * 32;
-  float2* p3 = H + b3 * 32;
-  float2 v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3;
-  float2 n0, n1, n2, n3;
-  n0.x = v0.x + q01.x; n0.y = v0.y + q01.y;
-  if (b1 == b0) v1 = n0;
-  n1.x = v1.x + q01.z; n1.y = v1.y + q01.w;
-  if (b2 == b1) v2 = n1; else if (b2 == b0) v2 = n0;
-  n2.x = v2.x + q23.x; n2.y = v2.y + q23.y;
-  if (b3 == b2) v3 = n2; else if (b3 == b1) v3 = n1; else if (b3 == b0) v3 = n0;
-  n3.x = v3.x + q23.z; n3.y = v3.y + q23.w;
-  *p0 = n0; *p1 = n1; *p2 = n2; *p3 = n3;   // in order: the last store to a cell carries the full sum
+  const unsigned a0 = hbase + (b0 << 8), a1 = hbase + (b1 << 8), a2 = hbase + (b2 << 8), a3 = hbase + (b3 << 8);
+  const float2 v0 = lds64(a0), v1 = lds64(a1), v2 = lds64(a2), v3 = lds64(a3);
+  float2 s1 = make_float2(q01.z, q01.w), s2 = make_float2(q23.x, q23.y), s3 = make_float2(q23.z, q23.w);
+  if (b1 == b0) { s1.x += q01.x; s1.y += q01.y; }
+  if (b2 == b0) { s2.x += q01.x; s2.y += q01.y; }
+  if (b2 == b1) { s2.x += q01.z; s2.y += q01.w; }
+  if (b3 == b0) { s3.x += q01.x; s3.y += q01.y; }
+  if (b3 == b1) { s3.x += q01.z; s3.y += q01.w; }
+  if (b3 == b2) { s3.x += q23.x; s3.y += q23.y; }
+  sts64(a0, make_float2(v0.x + q01.x, v0.y + q01.y));
+  sts64(a1, make_float2(v1.x + s1.x, v1.y + s1.y));
+  sts64(a2, make_float2(v2.x + s2.x, v2.y + s2.y));
+  sts64(a3, make_float2(v3.x + s3.x, v3.y + s3.y));
 }
 
 __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a) {
@@ -107,6 +119,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a) {
   unsigned char* wbase = smem + warp * kWarpSmemBytes;
   float2* H = reinterpret_cast<float2*>(wbase) + lane;            // lane's column of the [bin][lane] table
   unsigned char* ring = wbase + kWarpHistBytes;
+  const unsigned hbase = static_cast<unsigned>(__cvta_generic_to_shared(H));   // + bin*256 = the lane's cell
 
   const int total_warps = gridDim.x * kHistWarps;
   const int gw = warp * gridDim.x + blockIdx.x;                  // spread the first items over all SMs
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a) {
               t01 = *reinterpret_cast<const float4*>(sgh + r + 4);
               t23 = *reinterpret_cast<const float4*>(sgh + r + 6);
             }
-            rmw4(H, b0, b1, b2, b3, q01, q23);
+            rmw4(hbase, b0, b1, b2, b3, q01, q23);
             b0 = c0; b1 = c1; b2 = c2; b3 = c3; q01 = t01; q23 = t23;
           }
         } else {

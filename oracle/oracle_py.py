@@ -84,7 +84,11 @@ def make_layout(lay):
     """lay: oracle.refapi.Layout (or anything with the same attributes).  Returns (struct, keepalive)."""
     keep = [np.ascontiguousarray(getattr(lay, k), dtype=np.int32) for k in
             ("feat_column", "feat_lo", "feat_num_bin", "feat_mfb", "feat_default_bin", "feat_missing",
-             "feat_real_index", "feat_in_group")]
+             "feat_real_index")]
+    in_group = getattr(lay, "feat_in_group", None)
+    if in_group is None:
+        in_group = np.bincount(keep[0], minlength=lay.num_columns)[keep[0]]
+    keep.append(np.ascontiguousarray(in_group, dtype=np.int32))
     s = _OrcLayout(lay.num_data, lay.num_columns, lay.num_features, *[_p(a) for a in keep])
     return s, keep
 

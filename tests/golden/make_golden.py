@@ -1,0 +1,131 @@
+"""Generates the golden fixtures under tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE
+(oracle/_ref/lib_lightgbm.so built by oracle/Makefile.ref from /root/reference) in this container.
+
+Each fixture holds: the binned matrix + layout metadata read back from the reference Dataset (probe),
+the fp32 gradients/hessians fed through LGBM_BoosterUpdateOneIterCustom, the learner parameters, and the
+tree the reference CPU learner (serial, col-wise, num_threads=1, deterministic) grew from them, parsed from
+LGBM_BoosterSaveModelToString.  The missing-value tables are the reference's own known-answer tests
+(tests/python_package_test/test_engine.py:161-292).
+
+Usage:  python tests/golden/make_golden.py      (needs oracle/_ref; the GPU box only reads the .npz)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import refapi  # noqa: E402
+
+BASE_DS = dict(verbosity=-1, num_threads=1, min_data_in_bin=1, feature_pre_filter="false", max_bin=255)
+BASE_BOOST = dict(objective="custom", learning_rate=1.0, force_col_wise="true", deterministic="true", num_threads=1,
+                  verbosity=-1)
+LEARNER_KEYS = ("num_leaves", "max_depth", "min_data_in_leaf", "min_sum_hessian_in_leaf", "lambda_l1", "lambda_l2",
+                "min_gain_to_split", "max_delta_step", "path_smooth")
+DEFAULTS = dict(num_leaves=31, max_depth=-1, min_data_in_leaf=20, min_sum_hessian_in_leaf=1e-3, lambda_l1=0.0,
+                lambda_l2=0.0, min_gain_to_split=0.0, max_delta_step=0.0, path_smooth=0.0)
+
+
+def thresholds_to_bins(lay, tree):
+    """real-valued thresholds of the model -> threshold_in_bin via the BinMapper upper bounds."""
+    inner_of_real = {int(r): i for i, r in enumerate(lay.feat_real_index)}
+    feats, bins = [], []
+    for rf, th in zip(tree.split_feature, tree.threshold):
+        f = inner_of_real[int(rf)]
+        ub = lay.bin_upper_bound[f]
+        ubc = np.clip(np.nan_to_num(ub, nan=1e300), -1e300, 1e300)      # Common::AvoidInf (model text writes +-1e300)
+        thc = float(np.clip(th, -1e300, 1e300))
+        b = int(np.argmin(np.abs(ubc - thc)))
+        assert abs(ubc[b] - thc) <= 1e-12 * max(1.0, abs(thc)), (ub[b], th)
+        feats.append(f); bins.append(b)
+    return np.array(feats, np.int32), np.array(bins, np.int32)
+
+
+def run_case(name, X, grad, hess, ds_params=None, learner=None, y=None):
+    ds_params = dict(BASE_DS, **(ds_params or {}))
+    lp = dict(DEFAULTS, **(learner or {}))
+    ds = refapi.RefDataset(np.asarray(X, dtype=np.float64), np.zeros(len(X), np.float32), ds_params)
+    lay = ds.layout()
+    bp = dict(ds_params, **BASE_BOOST, **lp)
+    bp["device_type"] = "cpu"     # Dataset may be *constructed* with cuda rules (dense bundles); training is CPU
+    bst = refapi.RefBooster(ds, bp)
+    g = np.ascontiguousarray(grad, np.float32); h = np.ascontiguousarray(hess, np.float32)
+    bst.update_custom(g, h)
+    t = bst.trees()[0]
+    feats, tbins = (thresholds_to_bins(lay, t) if t.num_leaves > 1 else (np.zeros(0, np.int32), np.zeros(0, np.int32)))
+    d = lay.to_npz_dict()
+    d.update(grad=g, hess=h, params=np.array([lp[k] for k in LEARNER_KEYS], np.float64),
+             ref_num_leaves=np.int64(t.num_leaves), ref_split_feature_inner=feats, ref_threshold_bin=tbins,
+             ref_split_leaf=t.split_leaf() if t.num_leaves > 1 else np.zeros(0, np.int32),
+             ref_default_left=t.default_left.astype(np.int32), ref_split_gain=t.split_gain,
+             ref_internal_count=t.internal_count, ref_leaf_value=t.leaf_value, ref_leaf_count=t.leaf_count,
+             ref_leaf_weight=t.leaf_weight, ref_threshold_real=t.threshold)
+    if y is not None:
+        d["kat_y"] = np.asarray(y, np.float64)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name}: N={lay.num_data} C={lay.num_columns} F={lay.num_features} leaves={t.num_leaves} "
+          f"missing={sorted(set(lay.feat_missing.tolist()))} mfb>0={int((lay.feat_mfb > 0).sum())} "
+          f"multi_feature_cols={int((lay.feat_in_group > 1).sum())} -> {os.path.getsize(path)} B")
+    bst.free(); ds.free()
+
+
+def main():
+    rng = np.random.default_rng(2024)
+    nan = np.nan
+    # --- the reference's own known-answer tables (test_engine.py:201-292): 1 tree, lr 1, pred == y
+    kat = dict(num_leaves=2, min_data_in_leaf=1, min_sum_hessian_in_leaf=1e-3)
+    x9 = np.array([0, 1, 2, 3, 4, 5, 6, 7, nan]).reshape(-1, 1)
+    y_na = np.array([1, 1, 1, 1, 0, 0, 0, 0, 1.0])
+    y_zero = np.array([0, 1, 1, 1, 0, 0, 0, 0, 0.0])
+    run_case("kat_missing_na", x9, -y_na, np.ones(9), dict(zero_as_missing="false"), kat, y=y_na)
+    run_case("kat_missing_zero", x9, -y_zero, np.ones(9), dict(zero_as_missing="true"), kat, y=y_zero)
+    run_case("kat_missing_none", x9, -y_zero, np.ones(9), dict(use_missing="false"), kat, y=y_zero)
+    # test_missing_value_handle (:161) / _more_na (:180): 100 rows, one feature, NaN marks the positives
+    x = np.zeros((100, 1)); y = np.zeros(100); idx = rng.choice(100, 20, replace=False); x[idx, 0] = nan; y[idx] = 1
+    run_case("kat_missing_handle", x, -y, np.ones(100), None, dict(num_leaves=31), y=y)
+    x = np.ones((100, 1)); y = np.ones(100); idx = rng.choice(100, 80, replace=False); x[idx, 0] = nan; y[idx] = 0
+    run_case("kat_missing_more_na", x, -y, np.ones(100), None, dict(num_leaves=31), y=y)
+
+    # --- integer-valued features: bin == value
+    n, f = 4000, 12
+    bins = rng.integers(0, 255, (n, f))
+    yv = (bins[:, :6] / 127.0 - 1) @ rng.normal(size=6) + 0.3 * rng.normal(size=n)
+    run_case("identity_l2", bins, -yv, np.ones(n), dict(enable_bundle="false"), dict(num_leaves=31))
+    run_case("identity_l2_reg", bins, -yv, np.ones(n), dict(enable_bundle="false"),
+             dict(num_leaves=24, lambda_l1=0.3, lambda_l2=2.0, min_gain_to_split=1.0, max_depth=6))
+    run_case("identity_l2_smooth", bins, -yv, np.ones(n), dict(enable_bundle="false"),
+             dict(num_leaves=16, path_smooth=5.0, max_delta_step=0.4, min_data_in_leaf=50))
+
+    # --- continuous features binned by the reference, NaN + zeros + a "mostly one value" feature
+    n, f = 5000, 10
+    X = rng.normal(size=(n, f))
+    X[rng.random((n, f)) < 0.08] = nan                     # NaN-missing features
+    X[:, 3] = np.where(rng.random(n) < 0.85, 0.0, X[:, 3])   # sparse: default bin is the most frequent
+    X[:, 4] = np.where(rng.random(n) < 0.8, 2.5, rng.normal(size=n))   # most frequent bin != zero bin
+    X[:, 5] = np.round(X[:, 5])                            # few distinct values
+    X[:, 6] = (rng.random(n) < 0.5).astype(float)          # 2 bins
+    logit = np.nan_to_num(X[:, 0]) - 0.7 * np.nan_to_num(X[:, 1]) + (X[:, 4] == 2.5) * 0.8 + np.isnan(X[:, 2]) * 1.0
+    yb = (rng.random(n) < 1 / (1 + np.exp(-logit))).astype(float)
+    p = np.full(n, 0.5)
+    run_case("mixed_missing_binary", X, p - yb, p * (1 - p) + 0.05 * rng.random(n), dict(max_bin=63, device_type="cuda"), dict(num_leaves=31, min_data_in_leaf=10))
+    run_case("mixed_zero_as_missing", X, p - yb, p * (1 - p) + 0.05 * rng.random(n),
+             dict(max_bin=63, zero_as_missing="true", device_type="cuda"), dict(num_leaves=31, min_data_in_leaf=10))
+
+    # --- EFB: mutually exclusive sparse features bundled into shared columns (dense storage as on cuda)
+    n, f = 6000, 24
+    X = np.zeros((n, f))
+    for blk in range(0, f, 4):
+        who = rng.integers(0, 6, n)                         # which of the 4 features (or none) is non-zero
+        for j in range(4):
+            m = who == j
+            X[m, blk + j] = rng.integers(1, 40, m.sum())
+    yv = X[:, 0] * 0.05 - X[:, 5] * 0.03 + (X[:, 9] > 20) * 1.0 + 0.2 * rng.normal(size=n)
+    run_case("efb_bundled", X, -yv, np.ones(n), dict(enable_bundle="true", device_type="cuda", max_bin=63),
+             dict(num_leaves=31, min_data_in_leaf=10))
+
+
+if __name__ == "__main__":
+    main()

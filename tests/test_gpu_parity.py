@@ -82,16 +82,7 @@ def test_tree_matches_oracle(mods, n, f, leaves, kw):
 
 
 def lay_for_oracle(lay):
-    """oracle_py.make_layout wants feat_in_group too."""
-    class _L:
-        pass
-    o = _L()
-    for k in ("bins", "feat_column", "feat_lo", "feat_num_bin", "feat_mfb", "feat_default_bin", "feat_missing",
-              "feat_real_index", "num_data", "num_columns", "num_features"):
-        setattr(o, k, getattr(lay, k))
-    cnt = np.bincount(lay.feat_column, minlength=lay.num_columns)
-    o.feat_in_group = cnt[lay.feat_column].astype(np.int32)
-    return o
+    return lay        # oracle_py.make_layout derives feat_in_group when the layout has none
 
 
 def test_non_constant_hessian_and_graph_replay(mods):
