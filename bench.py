@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py — boosting iterations/sec of the histogram tree-learner hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU path
+
+One "step" = one boosting iteration (L2 gradients -> Train one tree -> score update) on the synthetic
+10M x 1024, 255-bin, 127-leaf regression workload of BASELINE.json (C3 in SURVEY.md §8d).
+  value : whole-job it/s with label/score/grad/hess already resident in HBM (device-resident boosting),
+          timed with CUDA events on the learner's stream, max over ranks.
+  e2e   : the same iteration through the reference-facing C-ABI call with HOST buffers: grad/hess are
+          copied host->device inside Train (from pinned memory) and the per-row leaf ids device->host
+          inside AddPredictionToScore, every step, inside the timed region.
+  roofline : dominant kernel = k_hist; algorithmic bytes = n_leaf*(C*1 + 8 [+4 index]) + C*256*16 per
+          launch, divided by the CUDA-event time of the k_hist launches (measured live, profiling pass).
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref/lib_lightgbm.so) on the host cores, bounded sample.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "boosting iters/sec, 10M x 1K synthetic, 255 bins, 127 leaves"
+WORKLOADS = {
+    "C3": dict(rows=10_000_000, cols=1024, leaves=127, seed=44),
+    "C2": dict(rows=1_000_000, cols=256, leaves=63, seed=42),
+}
+
+
+def gen_bins(rows, cols, seed, col_lo=0, col_hi=None, threads=None):
+    """Seeded synthetic bin matrix: one Philox stream per 64K-row chunk, so the matrix
+    (and any column slice of it) is identical whatever the thread count or the number of ranks."""
+    col_hi = cols if col_hi is None else col_hi
+    out = np.empty((rows, col_hi - col_lo), dtype=np.uint8)
+    chunk = 65536
+    starts = list(range(0, rows, chunk))
+
+    def work(s):
+        e = min(rows, s + chunk)
+        rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, 0, s // chunk]))
+        blk = rng.integers(0, 255, (e - s, cols), dtype=np.uint8)
+        out[s:e] = blk[:, col_lo:col_hi]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 8)) as ex:
+        list(ex.map(work, starts))
+    return out
+
+
+def gen_label(rows, cols, seed, bins_first32):
+    rng = np.random.Generator(np.random.Philox(key=seed + 1000))
+    w = rng.normal(size=32)
+    noise = rng.normal(size=rows).astype(np.float32)
+    return ((bins_first32.astype(np.float32) / 127.0 - 1.0) @ w.astype(np.float32) + 0.5 * noise).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.gpu = gpu_index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start(); return self
+
+    def __exit__(self, *a):
+        self._stop.set(); self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "hist_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_reference(args, wl, rank, world):
+    """The reference's own CPU learner (unmodified, built into oracle/_ref by oracle/Makefile.ref) on the
+    host cores, on a bounded row sample of the same workload; it/s is scaled by sample_rows/rows
+    (histogram work is linear in rows; this favours the CPU since per-split overheads do not scale)."""
+    if rank != 0:
+        return None
+    from oracle import refapi
+    rows = min(wl["rows"], args.ref_rows)
+    cores = os.cpu_count() or 1
+    bins = gen_bins(rows, wl["cols"], wl["seed"])
+    y = gen_label(rows, wl["cols"], wl["seed"], bins[:, :32])
+    X = bins.astype(np.float32)
+    dsp = dict(max_bin=255, min_data_in_bin=1, enable_bundle="false", feature_pre_filter="false", verbosity=-1,
+               num_threads=cores)
+    t0 = time.time()
+    ds = refapi.RefDataset(X, y, dsp)
+    t_ds = time.time() - t0
+    del X
+    bp = dict(dsp, objective="regression", num_leaves=wl["leaves"], learning_rate=0.1, min_data_in_leaf=20,
+              force_row_wise="true", device_type="cpu")
+    bst = refapi.RefBooster(ds, bp)
+    for _ in range(args.warmup):
+        bst.update()
+    t0 = time.time()
+    for _ in range(args.steps):
+        bst.update()
+    dt = (time.time() - t0) / args.steps
+    scale = rows / wl["rows"]
+    value = (1.0 / dt) * scale
+    sample = f"{rows} of {wl['rows']} rows x {wl['cols']} cols, {wl['leaves']} leaves; it/s scaled by {scale:g}; " \
+             f"dataset construction {t_ds:.1f}s excluded"
+    return dict(value=value, ms_per_step=dt * 1e3 / scale, cores=cores, sample=sample)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "C3"), choices=list(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override rows (debug only; makes the number INVALID)")
+    ap.add_argument("--ref-rows", type=int, default=500_000, help="row sample for the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    rank, world, local = dist_env()
+    wl = dict(WORKLOADS[args.workload])
+    if args.rows:
+        wl["rows"] = args.rows
+    config = {"workload": f"{args.workload}: {wl['rows']} rows x {wl['cols']} dense features, 255 bins, {wl['leaves']} leaves, "
+                          f"L2 regression, min_data_in_leaf=20, lr=0.1",
+              "parallelism": f"feature-shard x{world}" if world > 1 else "single GPU",
+              "l2_flush": "inputs larger than L2 (bin matrix 10.24 GB >> 126 MB)" if wl["rows"] * wl["cols"] > 2e9 else
+                          "bin matrix larger than L2 per GPU"}
+
+    if args.impl == "reference":
+        r = run_reference(args, wl, rank, world)
+        if rank == 0:
+            line = {"metric": METRIC, "impl": "reference", "value": r["value"], "unit": "iters/sec", "n_gpus": args.gpus,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f64 histograms (fp32 grad/hess)", "data": "synthetic",
+                    "config": config,
+                    "cpu_baseline": {"value": r["value"], "unit": "iters/sec", "cores": r["cores"], "kind": "reference",
+                                     "sample": r["sample"]},
+                    "e2e": {"value": r["value"], "unit": "iters/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------------------ this repo's arm
+    import lightgbm_b200 as lgb
+    from lightgbm_b200.tree_learner import PinnedArray
+    if world > 1:
+        raise SystemExit("multi-GPU feature-shard path: not wired into bench.py yet")
+    rows, cols, leaves = wl["rows"], wl["cols"], wl["leaves"]
+    bins = gen_bins(rows, cols, wl["seed"])
+    y = gen_label(rows, cols, wl["seed"], bins[:, :32])
+    lay = lgb.Layout.identity(bins)
+    cfg = lgb.Config(num_leaves=leaves, min_data_in_leaf=20, gpu_device_id=local, use_cuda_graph=True)
+    B = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=True)
+    L = B.learner
+
+    # --- value: device-resident boosting iterations
+    for _ in range(args.warmup):
+        B.update()
+    l0 = L.kernel_launches
+    with ClockSampler(local) as clk:
+        L.timer_start()
+        t0 = time.time()
+        for _ in range(args.steps):
+            B.update()
+        ms_total = L.timer_stop()
+        wall = time.time() - t0
+    launches = L.kernel_launches - l0
+    ms_per_step = ms_total / args.steps
+    value = 1e3 / ms_per_step
+    clocks = clk.summary()
+    final_l2 = B.l2()
+
+    # --- roofline of the dominant kernel (k_hist), measured live with CUDA events around every launch
+    L.set_profiling(True)
+    L.hist_stats(reset=True)
+    prof_steps = 3
+    for _ in range(prof_steps):
+        B.update()
+    hist_ms, hist_rows, hist_launches = L.hist_stats()
+    L.set_profiling(False)
+    # algorithmic bytes: per histogrammed row C bin bytes + 8 (grad,hess) + 4 (row index, not for the root),
+    # per launch the C*256*16 B of the int64 pool slot it fills
+    root_rows = rows * prof_steps
+    alg_bytes = hist_rows * (cols + 8) + (hist_rows - root_rows) * 4 + hist_launches * cols * 256 * 16
+    achieved = alg_bytes / (hist_ms * 1e-3) / 1e9
+    peak, peak_kind = peak_hbm()
+    tr = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "k_hist", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_kind": peak_kind,
+                "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                "hist_share_of_step": (hist_ms / prof_steps) / ms_per_step,
+                "alg_bytes_per_launch": alg_bytes / max(hist_launches, 1),
+                "avg_launch_ms": hist_ms / max(hist_launches, 1), "rows_built_factor_k": hist_rows / root_rows}
+
+    # --- e2e: host buffers through the C-ABI, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        H = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=False, learner=L, pinned=True)
+        for _ in range(args.warmup):
+            H.update()
+        t0 = time.time()
+        for _ in range(args.steps):
+            H.update()
+        dt = (time.time() - t0) / args.steps
+        e2e = {"value": 1.0 / dt, "unit": "iters/sec", "h2d_bytes_per_step": rows * 8, "d2h_bytes_per_step": rows * 4 + 4096,
+               "note": "host grad/hess (pinned) -> H2D inside Train; per-row leaf ids D2H inside AddPredictionToScore; "
+                       "host computes g = score - y and score += leaf_value[leaf_id]"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        a2 = argparse.Namespace(**vars(args)); a2.steps = 2; a2.warmup = 1
+        r = run_reference(a2, wl, rank, world)
+        cpu = {"value": r["value"], "unit": "iters/sec", "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
+
+    line = {"metric": METRIC, "value": value, "unit": "iters/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "fp32 partial sums -> int64 fixed-point histograms, f64 gain scan", "data": "synthetic",
+            "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "wall_ms_per_step": wall * 1e3 / args.steps, "final_train_l2": final_l2}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,19 @@ LGBMB200_EXPORT int LGBMB200_LearnerHistStats(LGBMB200_LearnerHandle h, int32_t 
                                               double* hist_rows, int64_t* hist_launches);
 LGBMB200_EXPORT int LGBMB200_LearnerSetProfiling(LGBMB200_LearnerHandle h, int32_t enable);
 
+/* Per-row leaf id of the last tree (host output, -1 for rows outside the bag): what the CPU learner's
+ * DataPartition encodes and the reference CUDA learner keeps in cuda_data_index_to_leaf_index_
+ * (reference src/treelearner/cuda/cuda_data_partition.cu:113). */
+LGBMB200_EXPORT int LGBMB200_LearnerGetLeafIndex(LGBMB200_LearnerHandle h, int32_t* leaf_index_host);
+
+/* CUDA-event stopwatch on the learner's stream (the stream every kernel of this library is launched on). */
+LGBMB200_EXPORT int LGBMB200_LearnerTimerStart(LGBMB200_LearnerHandle h);
+LGBMB200_EXPORT int LGBMB200_LearnerTimerStop(LGBMB200_LearnerHandle h, float* elapsed_ms);
+
+/* Pinned host memory for the host-buffer (e2e) path. */
+LGBMB200_EXPORT int LGBMB200_HostAllocPinned(void** ptr, int64_t bytes);
+LGBMB200_EXPORT int LGBMB200_HostFreePinned(void* ptr);
+
 /* Raw device pointer helpers so a host program without torch can keep grad/hess/score in HBM. */
 LGBMB200_EXPORT int LGBMB200_DeviceAlloc(void** ptr, int64_t bytes);
 LGBMB200_EXPORT int LGBMB200_DeviceFree(void* ptr);

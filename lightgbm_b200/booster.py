@@ -17,9 +17,12 @@ from .tree_learner import B200TreeLearner, Config, DeviceArray, Layout, Tree
 
 class B200Booster:
     def __init__(self, layout: Layout, label: np.ndarray, config: Config, learning_rate: float = 0.1,
-                 boost_from_average: bool = True, device_resident: bool = True):
-        self.learner = B200TreeLearner(config)
-        self.learner.init(layout, is_constant_hessian=True)
+                 boost_from_average: bool = True, device_resident: bool = True, learner: B200TreeLearner | None = None,
+                 pinned: bool = False):
+        if learner is None:
+            learner = B200TreeLearner(config)
+            learner.init(layout, is_constant_hessian=True)
+        self.learner = learner
         self.n = layout.num_data
         self.lr = float(learning_rate)
         self.device_resident = device_resident
@@ -35,8 +38,14 @@ class B200Booster:
             self.d_hess = DeviceArray(self.n * 4)
         else:
             self.score = score0
-            self.grad = np.empty(self.n, np.float32)
-            self.hess = np.ones(self.n, np.float32)
+            if pinned:
+                from .tree_learner import PinnedArray
+                self._pg, self._ph = PinnedArray(self.n, np.float32), PinnedArray(self.n, np.float32)
+                self.grad, self.hess = self._pg.array, self._ph.array
+                self.hess[:] = 1.0
+            else:
+                self.grad = np.empty(self.n, np.float32)
+                self.hess = np.ones(self.n, np.float32)
 
     def update(self) -> Tree:
         """One boosting iteration: gradients -> Train -> Shrinkage -> UpdateScore."""

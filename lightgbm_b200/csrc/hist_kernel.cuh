@@ -17,8 +17,11 @@
 //     processed four at a time with in-register forwarding, which keeps 4 independent LDS in flight
 //     and preserves the exact sequential fp32 summation order (=> bitwise run-to-run determinism).
 //   * Rows are gathered through the leaf's index list: 32-byte row segments and the (grad,hess) pairs
-//     are staged into a per-warp 6-deep shared-memory ring with cp.async (LDGSTS), no registers, no
-//     block barriers (warp-local __syncwarp only).
+//     are staged into a per-warp 6-deep shared-memory ring with cp.async (LDGSTS) by a PARTNER PRODUCER
+//     WARP; completion is tracked by mbarriers (cp.async.mbarrier.arrive), so the consumer warp never
+//     touches global memory and never waits on a global-load scoreboard (the first version, which issued
+//     its own loads, lost 37% of its cycles there — profiles/r01_hist_v1_stalls.txt).  No block barriers
+//     in the main loop.
 //   * Flush: fp32 partials -> int64 fixed point (power-of-two scale chosen per tree) added to the
 //     leaf's slot of the histogram pool with RED.ADD.64.  Integer adds are associative, so the global
 //     histogram does not depend on the order in which warps flush, and parent - child is exact.
@@ -27,15 +30,16 @@
 
 namespace b200 {
 
-constexpr int kHistWarps = 3;
-constexpr int kHistThreads = kHistWarps * 32;
+constexpr int kHistWarps = 3;                    // consumer warps (one per SMSP 0..2), each with a partner producer warp
+constexpr int kHistThreads = 2 * kHistWarps * 32; // warps 0..2 consume, warps 3..5 produce (warp 3 owns SMSP 3)
 constexpr int kStageRows = 32;
 constexpr int kStages = 6;                       // ring depth; kStages-1 stages in flight
 constexpr int kWarpHistBytes = kBinsPerColumn * 32 * 8;           // 65536
 constexpr int kStageBinBytes = kStageRows * kColGroup;            // 1024
 constexpr int kStageBytes = kStageBinBytes + kStageRows * 8;      // + (g,h) pairs = 1280
 constexpr int kWarpSmemBytes = kWarpHistBytes + kStages * kStageBytes;
-constexpr int kHistSmemBytes = kHistWarps * kWarpSmemBytes;       // 219648 B <= 227 KB
+constexpr int kHistBarBytes = kHistWarps * kStages * 2 * 8;        // full[] + empty[] mbarriers per consumer warp
+constexpr int kHistSmemBytes = kHistWarps * kWarpSmemBytes + kHistBarBytes;   // 219936 B <= 227 KB
 
 struct HistArgs {
   const uint8_t* bins;            // [num_data x pitch] row-major stored values
@@ -98,45 +102,117 @@ __device__ __forceinline__ void rmw4(unsigned hbase, uint32_t b0, uint32_t b1, u
   sts64(a3, make_float2(v3.x + s3.x, v3.y + s3.y));
 }
 
+// ---- mbarrier helpers (shared::cta) -----------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))) : "memory");
+}
+// all prior cp.async of this thread arrive on `bar` when they complete (count pre-accounted at init)
+__device__ __forceinline__ void mbar_arrive_on_cp_async(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  unsigned done = 0;
+  for (unsigned spin = 0; !done; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (spin > (1u << 28)) __trap();          // watchdog: turn a protocol bug into a launch error, not a hang
+  }
+}
+
+// Work decomposition shared by the producer and the consumer warp of a pair.
+struct HistWork {
+  int n, begin, slot;
+  const int32_t* idx;
+  int CG, per, items, total_warps, gw;
+};
+
+__device__ __forceinline__ bool hist_work_setup(const HistArgs& a, int pair, HistWork* w) {
+  if (a.explicit_n >= 0) {
+    w->n = a.explicit_n; w->begin = 0; w->slot = a.explicit_slot; w->idx = a.explicit_idx;
+  } else {
+    const Ctl* c = a.ctl;
+    if (!c->cur_valid || !c->do_find) return false;
+    const Leaf& L = a.leaves[c->smaller];
+    w->n = L.count; w->begin = L.begin; w->slot = L.slot;
+    // the root of an un-bagged tree is the identity list: skip the index load altogether
+    w->idx = (c->num_leaves == 1 && c->root_identity) ? nullptr : (L.buf ? a.idx1 : a.idx0);
+  }
+  if (w->n <= 0) return false;
+  w->total_warps = gridDim.x * kHistWarps;
+  w->gw = pair * gridDim.x + blockIdx.x;                       // spread the first items over all SMs
+  w->CG = a.num_colgroups;
+  const int max_splits = max(1, w->total_warps / w->CG);
+  const int splits = min(max_splits, max(1, (w->n + a.min_rows_per_item - 1) / a.min_rows_per_item));
+  w->per = (((w->n + splits - 1) / splits) + 31) & ~31;
+  w->items = w->CG * splits;
+  return true;
+}
+
 __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_producer = warp >= kHistWarps;
+  const int pair = is_producer ? warp - kHistWarps : warp;
 
-  int n, begin, slot;
-  const int32_t* idx;
-  if (a.explicit_n >= 0) {
-    n = a.explicit_n; begin = 0; slot = a.explicit_slot; idx = a.explicit_idx;
-  } else {
-    const Ctl* c = a.ctl;
-    if (!c->cur_valid || !c->do_find) return;
-    const Leaf& L = a.leaves[c->smaller];
-    n = L.count; begin = L.begin; slot = L.slot;
-    // the root of an un-bagged tree is the identity list: skip the index load altogether
-    idx = (c->num_leaves == 1 && c->root_identity) ? nullptr : (L.buf ? a.idx1 : a.idx0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kHistWarps * kWarpSmemBytes);
+  uint64_t* full = bars + pair * (2 * kStages);       // producer -> consumer: stage landed
+  uint64_t* empty = full + kStages;                   // consumer -> producer: stage consumed
+  if (!is_producer && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, 1); }
   }
-  if (n <= 0) return;
+  __syncthreads();
 
-  unsigned char* wbase = smem + warp * kWarpSmemBytes;
-  float2* H = reinterpret_cast<float2*>(wbase) + lane;            // lane's column of the [bin][lane] table
+  HistWork w;
+  if (!hist_work_setup(a, pair, &w)) return;
+  unsigned char* wbase = smem + pair * kWarpSmemBytes;
   unsigned char* ring = wbase + kWarpHistBytes;
+
+  if (is_producer) {
+    // ------------------------------------------------------------------ producer warp: stage rows
+    int slot = 0; unsigned phase = 0;
+    for (int item = w.gw; item < w.items; item += w.total_warps) {
+      const int cg = item % w.CG, part = item / w.CG;
+      const int r0 = part * w.per;
+      const int r1 = min(w.n, r0 + w.per);
+      if (r0 >= r1) continue;
+      const uint8_t* colbase = a.bins + static_cast<int64_t>(cg) * kColGroup;
+      const int half = (lane & 1) * 16;
+      const int32_t* ip = w.idx ? w.idx + w.begin : nullptr;
+      for (int p0 = r0; p0 < r1; p0 += kStageRows) {
+        // row ids: lane -> (g,h) of row p0+lane; lane pair -> 32-byte bin segment of rows p0+lane/2 and +16
+        const int pa = p0 + (lane >> 1), pb = pa + 16, pg = p0 + lane;
+        int ra = -1, rb = -1, rg = -1;
+        if (pa < r1) ra = ip ? __ldg(ip + pa) : pa;
+        if (pb < r1) rb = ip ? __ldg(ip + pb) : pb;
+        if (pg < r1) rg = ip ? __ldg(ip + pg) : pg;
+        mbar_wait(empty + slot, phase ^ 1);           // the consumer released this ring slot
+        unsigned char* sb = ring + slot * kStageBytes;
+        if (ra >= 0) cp_async16(sb + (lane >> 1) * kColGroup + half, colbase + static_cast<int64_t>(ra) * a.pitch + half);
+        if (rb >= 0) cp_async16(sb + (16 + (lane >> 1)) * kColGroup + half, colbase + static_cast<int64_t>(rb) * a.pitch + half);
+        if (rg >= 0) cp_async8(sb + kStageBinBytes + lane * 8, a.gh + rg);
+        mbar_arrive_on_cp_async(full + slot);
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer warp: accumulate
+  float2* H = reinterpret_cast<float2*>(wbase) + lane;            // lane's column of the [bin][lane] table
   const unsigned hbase = static_cast<unsigned>(__cvta_generic_to_shared(H));   // + bin*256 = the lane's cell
-
-  const int total_warps = gridDim.x * kHistWarps;
-  const int gw = warp * gridDim.x + blockIdx.x;                  // spread the first items over all SMs
-  const int CG = a.num_colgroups;
-  const int max_splits = max(1, total_warps / CG);
-  const int splits = min(max_splits, max(1, (n + a.min_rows_per_item - 1) / a.min_rows_per_item));
-  const int per = (((n + splits - 1) / splits) + 31) & ~31;
-  const int items = CG * splits;
   const double gs = a.ctl->g_scale, hs = a.ctl->h_scale;
-
-  for (int item = gw; item < items; item += total_warps) {
-    const int cg = item % CG, part = item / CG;
-    const int r0 = part * per;
-    const int r1 = min(n, r0 + per);
+  int slot = 0; unsigned phase = 0;
+  for (int item = w.gw; item < w.items; item += w.total_warps) {
+    const int cg = item % w.CG, part = item / w.CG;
+    const int r0 = part * w.per;
+    const int r1 = min(w.n, r0 + w.per);
     if (r0 >= r1) continue;
 
-    // zero the warp-private histogram
+    // zero the warp-private histogram (the producer is already filling the ring meanwhile)
     {
       float4* z = reinterpret_cast<float4*>(wbase);
 #pragma unroll 8
@@ -144,76 +220,49 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a) {
     }
     __syncwarp();
 
-    const uint8_t* colbase = a.bins + static_cast<int64_t>(cg) * kColGroup;
-    const int nst = (r1 - r0 + kStageRows - 1) / kStageRows;
-    constexpr int D = kStages - 1;
-    int row_next;
-    {
-      const int p = r0 + lane;
-      row_next = (p < r1) ? (idx ? __ldg(idx + begin + p) : p) : -1;
-    }
-    int wslot = 0, rslot = 0;
-    for (int s = 0; s < nst + D; ++s) {
-      if (s < nst) {
-        const int row = row_next;
-        const int p = r0 + (s + 1) * kStageRows + lane;
-        row_next = (p < r1) ? (idx ? __ldg(idx + begin + p) : p) : -1;
-        unsigned char* sb = ring + wslot * kStageBytes;
-        const int ra = __shfl_sync(0xffffffffu, row, lane >> 1);
-        const int rb = __shfl_sync(0xffffffffu, row, 16 + (lane >> 1));
-        const int half = (lane & 1) * 16;
-        if (ra >= 0) cp_async16(sb + (lane >> 1) * kColGroup + half, colbase + static_cast<int64_t>(ra) * a.pitch + half);
-        if (rb >= 0) cp_async16(sb + (16 + (lane >> 1)) * kColGroup + half, colbase + static_cast<int64_t>(rb) * a.pitch + half);
-        if (row >= 0) cp_async8(sb + kStageBinBytes + lane * 8, a.gh + row);
-        wslot = (wslot + 1 == kStages) ? 0 : wslot + 1;
-      }
-      cp_async_commit();
-      if (s >= D) {
-        cp_async_wait<D>();
-        __syncwarp();
-        const int st = s - D;
-        const int cnt = min(kStageRows, r1 - r0 - st * kStageRows);
-        const unsigned char* sb = ring + rslot * kStageBytes;
-        const unsigned char* sbin = sb + lane;
-        const float2* sgh = reinterpret_cast<const float2*>(sb + kStageBinBytes);
-        if (cnt == kStageRows) {
-          uint32_t b0 = sbin[0], b1 = sbin[32], b2 = sbin[64], b3 = sbin[96];
-          float4 q01 = *reinterpret_cast<const float4*>(sgh), q23 = *reinterpret_cast<const float4*>(sgh + 2);
+    for (int p0 = r0; p0 < r1; p0 += kStageRows) {
+      mbar_wait(full + slot, phase);
+      const int cnt = min(kStageRows, r1 - p0);
+      const unsigned char* sb = ring + slot * kStageBytes;
+      const unsigned char* sbin = sb + lane;
+      const float2* sgh = reinterpret_cast<const float2*>(sb + kStageBinBytes);
+      if (cnt == kStageRows) {
+        uint32_t b0 = sbin[0], b1 = sbin[32], b2 = sbin[64], b3 = sbin[96];
+        float4 q01 = *reinterpret_cast<const float4*>(sgh), q23 = *reinterpret_cast<const float4*>(sgh + 2);
 #pragma unroll
-          for (int r = 0; r < kStageRows; r += 4) {
-            // software pipeline: fetch the next batch from the stage before this batch's stores
-            uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-            float4 t01 = q01, t23 = q23;
-            if (r + 4 < kStageRows) {
-              c0 = sbin[(r + 4) * 32]; c1 = sbin[(r + 5) * 32]; c2 = sbin[(r + 6) * 32]; c3 = sbin[(r + 7) * 32];
-              t01 = *reinterpret_cast<const float4*>(sgh + r + 4);
-              t23 = *reinterpret_cast<const float4*>(sgh + r + 6);
-            }
-            rmw4(hbase, b0, b1, b2, b3, q01, q23);
-            b0 = c0; b1 = c1; b2 = c2; b3 = c3; q01 = t01; q23 = t23;
+        for (int r = 0; r < kStageRows; r += 4) {
+          // software pipeline: fetch the next batch from the stage before this batch's stores
+          uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+          float4 t01 = q01, t23 = q23;
+          if (r + 4 < kStageRows) {
+            c0 = sbin[(r + 4) * 32]; c1 = sbin[(r + 5) * 32]; c2 = sbin[(r + 6) * 32]; c3 = sbin[(r + 7) * 32];
+            t01 = *reinterpret_cast<const float4*>(sgh + r + 4);
+            t23 = *reinterpret_cast<const float4*>(sgh + r + 6);
           }
-        } else {
-          for (int r = 0; r < cnt; ++r) {
-            const uint32_t b = sbin[r * 32];
-            const float2 q = sgh[r];
-            float2 v = H[b * 32];
-            v.x += q.x; v.y += q.y;
-            H[b * 32] = v;
-          }
+          rmw4(hbase, b0, b1, b2, b3, q01, q23);
+          b0 = c0; b1 = c1; b2 = c2; b3 = c3; q01 = t01; q23 = t23;
         }
-        __syncwarp();
-        rslot = (rslot + 1 == kStages) ? 0 : rslot + 1;
+      } else {
+        for (int r = 0; r < cnt; ++r) {
+          const uint32_t b = sbin[r * 32];
+          const float2 q = sgh[r];
+          const unsigned addr = hbase + (b << 8);
+          float2 v = lds64(addr);
+          v.x += q.x; v.y += q.y;
+          sts64(addr, v);
+        }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + slot);
+      if (++slot == kStages) { slot = 0; phase ^= 1; }
     }
-    cp_async_wait<0>();
-    __syncwarp();
 
     // flush: fp32 partial -> int64 fixed point, RED.ADD.64 into the leaf's pool slot
-    unsigned long long* dst = a.pool + static_cast<int64_t>(slot) * a.slot_stride +
+    unsigned long long* dst = a.pool + static_cast<int64_t>(w.slot) * a.slot_stride +
                               (static_cast<int64_t>(cg) * kColGroup + lane) * (kBinsPerColumn * 2);
 #pragma unroll 4
     for (int b = 0; b < kBinsPerColumn; ++b) {
-      const float2 v = H[b * 32];
+      const float2 v = lds64(hbase + (b << 8));
       if (v.x != 0.f || v.y != 0.f) {
         atomicAdd(dst + 2 * b, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v.x) * gs)));
         atomicAdd(dst + 2 * b + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v.y) * hs)));

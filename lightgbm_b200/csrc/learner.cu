@@ -14,6 +14,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lgbm_b200.h"
@@ -210,20 +211,56 @@ class Learner {
   void AddPredictionToScore(const double* leaf_value, int num_leaves, double* score, int on_device) {
     REQUIRE(inited_ && last_num_leaves_ > 0, "Train first");
     REQUIRE(num_leaves == last_num_leaves_, "num_leaves does not match the last trained tree");
-    CUDA_CHECK(cudaMemcpyAsync(leaf_value_dev_.p, leaf_value, sizeof(double) * num_leaves, cudaMemcpyHostToDevice, stream_));
-    double* sc = score;
-    if (!on_device) {
-      if (score_stage_.n < static_cast<size_t>(N_)) score_stage_.alloc(N_);
-      CUDA_CHECK(cudaMemcpyAsync(score_stage_.p, score, sizeof(double) * N_, cudaMemcpyHostToDevice, stream_));
-      sc = score_stage_.p;
+    if (on_device) {
+      CUDA_CHECK(cudaMemcpyAsync(leaf_value_dev_.p, leaf_value, sizeof(double) * num_leaves, cudaMemcpyHostToDevice, stream_));
+      ScoreArgs sa{leaves_.p, idx0_.p, idx1_.p, leaf_value_dev_.p, score};
+      dim3 grid(std::max(1, std::min(num_sms_ * 4, (N_ + 255) / 256)), num_leaves);
+      k_add_score<<<grid, 256, 0, stream_>>>(sa);
+      ++launches_;
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaStreamSynchronize(stream_));
+      return;
     }
-    ScoreArgs sa{leaves_.p, idx0_.p, idx1_.p, leaf_value_dev_.p, sc};
-    dim3 grid(std::max(1, std::min(num_sms_ * 4, (N_ + 255) / 256)), num_leaves);
-    k_add_score<<<grid, 256, 0, stream_>>>(sa);
+    // host score (the link-seam path, boosting_on_gpu_ == false): ship 4 B/row of leaf ids, add on the host
+    FetchLeafIndex();
+    const int32_t* rl = h_row_leaf_;
+    const int nt = std::max(1, std::min(8, static_cast<int>(std::thread::hardware_concurrency())));
+    std::vector<std::thread> th;
+    const int64_t per = (static_cast<int64_t>(N_) + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+      th.emplace_back([=]() {
+        const int64_t lo = t * per, hi = std::min<int64_t>(N_, lo + per);
+        for (int64_t i = lo; i < hi; ++i) { const int l = rl[i]; if (l >= 0) score[i] += leaf_value[l]; }
+      });
+    }
+    for (auto& t : th) t.join();
+  }
+
+  void FetchLeafIndex() {
+    REQUIRE(inited_ && last_num_leaves_ > 0, "Train first");
+    if (row_leaf_.n < static_cast<size_t>(N_)) { row_leaf_.alloc(N_); CUDA_CHECK(cudaMallocHost(&h_row_leaf_, sizeof(int32_t) * N_)); }
+    if (bag_count_ >= 0) CUDA_CHECK(cudaMemsetAsync(row_leaf_.p, 0xFF, sizeof(int32_t) * N_, stream_));
+    dim3 grid(std::max(1, std::min(num_sms_ * 4, (N_ + 255) / 256)), last_num_leaves_);
+    k_leaf_index<<<grid, 256, 0, stream_>>>(leaves_.p, idx0_.p, idx1_.p, row_leaf_.p);
     ++launches_;
     CUDA_CHECK(cudaGetLastError());
-    if (!on_device) CUDA_CHECK(cudaMemcpyAsync(score, sc, sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(h_row_leaf_, row_leaf_.p, sizeof(int32_t) * N_, cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
+  }
+  void GetLeafIndex(int32_t* out) { FetchLeafIndex(); std::memcpy(out, h_row_leaf_, sizeof(int32_t) * N_); }
+
+  void TimerStart() {
+    if (!t0_) { CUDA_CHECK(cudaEventCreate(&t0_)); CUDA_CHECK(cudaEventCreate(&t1_)); }
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    CUDA_CHECK(cudaEventRecord(t0_, stream_));
+  }
+  float TimerStop() {
+    REQUIRE(t0_ != nullptr, "TimerStart first");
+    CUDA_CHECK(cudaEventRecord(t1_, stream_));
+    CUDA_CHECK(cudaEventSynchronize(t1_));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, t0_, t1_));
+    return ms;
   }
 
   void GetPartition(int32_t* leaf_begin, int32_t* leaf_count, int32_t* indices) {
@@ -435,6 +472,8 @@ class Learner {
     for (auto& e : hist_events_) cudaEventDestroy(e);
     hist_events_.clear();
     if (h_splits_) { cudaFreeHost(h_splits_); cudaFreeHost(h_leaves_); cudaFreeHost(h_ctl_); h_splits_ = nullptr; }
+    if (h_row_leaf_) { cudaFreeHost(h_row_leaf_); h_row_leaf_ = nullptr; }
+    if (t0_) { cudaEventDestroy(t0_); cudaEventDestroy(t1_); t0_ = nullptr; }
     if (stream_) { cudaStreamDestroy(stream_); stream_ = nullptr; }
   }
 
@@ -450,8 +489,10 @@ class Learner {
   DevBuf<uint8_t> bins_, flags_, feature_used_, splittable_;
   DevBuf<float2> gh_;
   DevBuf<float> grad_stage_, hess_stage_;
-  DevBuf<double> score_stage_, leaf_value_dev_;
-  DevBuf<int32_t> idx0_, idx1_, block_left_, bag_;
+  DevBuf<double> leaf_value_dev_;
+  DevBuf<int32_t> idx0_, idx1_, block_left_, bag_, row_leaf_;
+  int32_t* h_row_leaf_ = nullptr;
+  cudaEvent_t t0_ = nullptr, t1_ = nullptr;
   DevBuf<PartialSum> partials_;
   DevBuf<Ctl> ctl_;
   DevBuf<Leaf> leaves_;
@@ -572,6 +613,35 @@ int LGBMB200_LearnerSetProfiling(LGBMB200_LearnerHandle h, int32_t enable) {
   API_BEGIN();
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->SetProfiling(enable);
+  API_END();
+}
+int LGBMB200_LearnerGetLeafIndex(LGBMB200_LearnerHandle h, int32_t* leaf_index_host) {
+  API_BEGIN();
+  if (!h || !leaf_index_host) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->GetLeafIndex(leaf_index_host);
+  API_END();
+}
+int LGBMB200_LearnerTimerStart(LGBMB200_LearnerHandle h) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->TimerStart();
+  API_END();
+}
+int LGBMB200_LearnerTimerStop(LGBMB200_LearnerHandle h, float* elapsed_ms) {
+  API_BEGIN();
+  if (!h || !elapsed_ms) throw CudaError{"null argument"};
+  *elapsed_ms = static_cast<Learner*>(h)->TimerStop();
+  API_END();
+}
+int LGBMB200_HostAllocPinned(void** ptr, int64_t bytes) {
+  API_BEGIN();
+  if (!ptr) throw CudaError{"null argument"};
+  CUDA_CHECK(cudaMallocHost(ptr, static_cast<size_t>(bytes > 0 ? bytes : 1)));
+  API_END();
+}
+int LGBMB200_HostFreePinned(void* ptr) {
+  API_BEGIN();
+  CUDA_CHECK(cudaFreeHost(ptr));
   API_END();
 }
 int LGBMB200_DeviceAlloc(void** ptr, int64_t bytes) {

@@ -292,6 +292,13 @@ __global__ void __launch_bounds__(256) k_add_score(const ScoreArgs a) {
   for (int i = blockIdx.x * 256 + threadIdx.x; i < L.count; i += gridDim.x * 256) a.score[idx[i]] += v;
 }
 
+// row -> leaf id of the final partition (one grid row per leaf)
+__global__ void __launch_bounds__(256) k_leaf_index(const Leaf* leaves, const int32_t* idx0, const int32_t* idx1, int32_t* row_leaf) {
+  const Leaf& L = leaves[blockIdx.y];
+  const int32_t* idx = (L.buf ? idx1 : idx0) + L.begin;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < L.count; i += gridDim.x * 256) row_leaf[idx[i]] = blockIdx.y;
+}
+
 // L2 objective gradients (regression_objective.hpp:127-142, unweighted): g = score - label, h = 1
 __global__ void k_l2_gradients(const double* score, const float* label, float* grad, float* hess, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

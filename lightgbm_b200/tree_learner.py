@@ -180,6 +180,25 @@ class DeviceArray:
             pass
 
 
+class PinnedArray:
+    """numpy view over cudaMallocHost memory (for the host-buffer e2e path)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = (shape,) if np.isscalar(shape) else tuple(shape)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = C.c_void_p()
+        check(lib().LGBMB200_HostAllocPinned(C.byref(self.ptr), C.c_int64(n)))
+        buf = (C.c_byte * n).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().LGBMB200_HostFreePinned(self.ptr)
+            self.ptr = C.c_void_p()
+
+
 def _ptr_of(x):
     """host numpy array -> (pointer, on_device=0); DeviceArray / int / torch cuda tensor -> (pointer, 1)."""
     if isinstance(x, DeviceArray):
@@ -292,6 +311,19 @@ class B200TreeLearner:
                                                        C.c_int32(0 if idx is None else len(idx)),
                                                        None if out is None else _p(out), C.byref(ms)))
         return out, ms.value
+
+    def get_leaf_index(self) -> np.ndarray:
+        out = np.empty(self.layout.num_data, np.int32)
+        check(lib().LGBMB200_LearnerGetLeafIndex(self.handle, _p(out)))
+        return out
+
+    def timer_start(self) -> None:
+        check(lib().LGBMB200_LearnerTimerStart(self.handle))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        check(lib().LGBMB200_LearnerTimerStop(self.handle, C.byref(ms)))
+        return ms.value
 
     def l2_gradients(self, score_dev, label_dev, grad_dev, hess_dev, n: int) -> None:
         check(lib().LGBMB200_L2Gradients(self.handle, _ptr_of(score_dev)[0], _ptr_of(label_dev)[0],
