@@ -18,7 +18,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(_HERE, "_ref")
-REF_LIB = os.path.join(REF_DIR, "lib_lightgbm.so")
+# LGBM_REF_LIB lets the drop-in test point the very same harness at integration/_build/lib_lightgbm.so
+REF_LIB = os.environ.get("LGBM_REF_LIB", os.path.join(REF_DIR, "lib_lightgbm.so"))
 PROBE_LIB = os.path.join(REF_DIR, "libref_probe.so")
 
 C_API_DTYPE_FLOAT32, C_API_DTYPE_FLOAT64, C_API_DTYPE_INT32 = 0, 1, 2
@@ -37,7 +38,7 @@ def lib():
     if _lib is None:
         if not available():
             raise RuntimeError(f"reference library not built: run `make -C oracle -f Makefile.ref` ({REF_LIB})")
-        _lib = C.CDLL(REF_LIB, mode=C.RTLD_GLOBAL)
+        _lib = C.CDLL(REF_LIB)
         _lib.LGBM_GetLastError.restype = C.c_char_p
         _probe = C.CDLL(PROBE_LIB)
     return _lib
