@@ -39,21 +39,25 @@ WORKLOADS = {
 
 
 def gen_bins(rows, cols, seed, col_lo=0, col_hi=None, threads=None):
-    """Seeded synthetic bin matrix: one Philox stream per 64K-row chunk, so the matrix
-    (and any column slice of it) is identical whatever the thread count or the number of ranks."""
+    """Seeded synthetic bin matrix: one Philox stream per (64K-row chunk, 128-column block), so the
+    matrix — and any column slice of it — is identical whatever the thread count or the number of ranks, and a rank
+    only generates the column blocks it owns."""
     col_hi = cols if col_hi is None else col_hi
     out = np.empty((rows, col_hi - col_lo), dtype=np.uint8)
-    chunk = 65536
-    starts = list(range(0, rows, chunk))
+    chunk, cblock = 65536, 128
+    jobs = [(s, b) for s in range(0, rows, chunk) for b in range(col_lo // cblock, (col_hi + cblock - 1) // cblock)]
 
-    def work(s):
+    def work(job):
+        s, b = job
         e = min(rows, s + chunk)
-        rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, 0, s // chunk]))
-        blk = rng.integers(0, 255, (e - s, cols), dtype=np.uint8)
-        out[s:e] = blk[:, col_lo:col_hi]
+        c0, c1 = b * cblock, min(cols, (b + 1) * cblock)
+        rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, b, s // chunk]))
+        blk = rng.integers(0, 255, (e - s, c1 - c0), dtype=np.uint8)
+        lo, hi = max(c0, col_lo), min(c1, col_hi)
+        out[s:e, lo - col_lo:hi - col_lo] = blk[:, lo - c0:hi - c0]
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 8)) as ex:
-        list(ex.map(work, starts))
+        list(ex.map(work, jobs))
     return out
 
 
@@ -201,28 +205,53 @@ def main():
 
     # ------------------------------------------------------------------------------ this repo's arm
     import lightgbm_b200 as lgb
-    from lightgbm_b200.tree_learner import PinnedArray
-    if world > 1:
-        raise SystemExit("multi-GPU feature-shard path: not wired into bench.py yet")
+    from lightgbm_b200 import distributed as D
     rows, cols, leaves = wl["rows"], wl["cols"], wl["leaves"]
-    bins = gen_bins(rows, cols, wl["seed"])
-    y = gen_label(rows, cols, wl["seed"], bins[:, :32])
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world)
+    # feature-shard: every rank holds ALL rows x its column slice
+    lo, hi = D.shard_columns(cols, world)[rank]
+    host_threads = max(4, (os.cpu_count() or 8) // max(world, 1))
+    bins = gen_bins(rows, cols, wl["seed"], lo, hi, threads=min(32, host_threads))
+    first32 = bins[:, :32] if lo == 0 and hi >= 32 else gen_bins(rows, cols, wl["seed"], 0, 32, threads=min(32, host_threads))
+    y = gen_label(rows, cols, wl["seed"], first32)
     lay = lgb.Layout.identity(bins)
+    lay.feat_real_index = np.arange(lo, hi, dtype=np.int32)
     cfg = lgb.Config(num_leaves=leaves, min_data_in_leaf=20, gpu_device_id=local, use_cuda_graph=True)
-    B = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=True)
-    L = B.learner
+    L = D.make_sharded_learner(lay, cfg, rank, world)
+    B = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=True, learner=L)
+    my_cols = hi - lo
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
 
     # --- value: device-resident boosting iterations
     for _ in range(args.warmup):
         B.update()
     l0 = L.kernel_launches
+    barrier()
     with ClockSampler(local) as clk:
         L.timer_start()
         t0 = time.time()
         for _ in range(args.steps):
             B.update()
         ms_total = L.timer_stop()
+        barrier()
         wall = time.time() - t0
+    ms_total = max_over_ranks(ms_total)
     launches = L.kernel_launches - l0
     ms_per_step = ms_total / args.steps
     value = 1e3 / ms_per_step
@@ -240,7 +269,7 @@ def main():
     # algorithmic bytes: per histogrammed row C bin bytes + 8 (grad,hess) + 4 (row index, not for the root),
     # per launch the C*256*16 B of the int64 pool slot it fills
     root_rows = rows * prof_steps
-    alg_bytes = hist_rows * (cols + 8) + (hist_rows - root_rows) * 4 + hist_launches * cols * 256 * 16
+    alg_bytes = hist_rows * (my_cols + 8) + (hist_rows - root_rows) * 4 + hist_launches * my_cols * 256 * 16
     achieved = alg_bytes / (hist_ms * 1e-3) / 1e9
     peak, peak_kind = peak_hbm()
     tr = ncu_traffic()
@@ -257,16 +286,22 @@ def main():
         H = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=False, learner=L, pinned=True)
         for _ in range(args.warmup):
             H.update()
+        barrier()
         t0 = time.time()
         for _ in range(args.steps):
             H.update()
-        dt = (time.time() - t0) / args.steps
+        barrier()
+        dt = max_over_ranks((time.time() - t0) / args.steps)
         e2e = {"value": 1.0 / dt, "unit": "iters/sec", "h2d_bytes_per_step": rows * 8, "d2h_bytes_per_step": rows * 4 + 4096,
                "note": "host grad/hess (pinned) -> H2D inside Train; per-row leaf ids D2H inside AddPredictionToScore; "
                        "host computes g = score - y and score += leaf_value[leaf_id]"}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
+    if not args.no_cpu_baseline and world == 1:
         a2 = argparse.Namespace(**vars(args)); a2.steps = 2; a2.warmup = 1
         r = run_reference(a2, wl, rank, world)
         cpu = {"value": r["value"], "unit": "iters/sec", "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
@@ -277,6 +312,8 @@ def main():
             "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "wall_ms_per_step": wall * 1e3 / args.steps, "final_train_l2": final_l2}
     print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
 
 
 if __name__ == "__main__":

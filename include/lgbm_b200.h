@@ -165,6 +165,18 @@ LGBMB200_EXPORT int LGBMB200_LearnerHistStats(LGBMB200_LearnerHandle h, int32_t 
                                               double* hist_rows, int64_t* hist_launches);
 LGBMB200_EXPORT int LGBMB200_LearnerSetProfiling(LGBMB200_LearnerHandle h, int32_t enable);
 
+/* ---- Multi-GPU, feature-shard (semantic model: FeatureParallelTreeLearner, reference
+ * src/treelearner/feature_parallel_tree_learner.cpp:37-78 + SyncUpGlobalBestSplit, parallel_tree_learner.h:207-232).
+ * One learner per GPU (one process per GPU, or several learners in one process); every learner is Init-ed with ALL
+ * rows and ITS column slice (feat_real_index stays global).  Per split the ranks exchange their two per-leaf best
+ * candidates and the split's owner pushes the go-left flags — both through NVLink peer memory inside the kernels
+ * (no NCCL call, no host round trip).  Bootstrap: every rank exports a 64-byte CUDA-IPC handle of its exchange
+ * block; the caller all-gathers the handles (any transport: torch.distributed, MPI, a file) and hands each rank the
+ * full list plus feature_offsets[world+1] (first global inner-feature id of every rank's slice). */
+LGBMB200_EXPORT int LGBMB200_LearnerCommExport(LGBMB200_LearnerHandle h, uint8_t* handle_out_64);
+LGBMB200_EXPORT int LGBMB200_LearnerCommConnect(LGBMB200_LearnerHandle h, int32_t rank, int32_t world,
+                                                const uint8_t* all_handles, const int32_t* feature_offsets);
+
 /* Per-row leaf id of the last tree (host output, -1 for rows outside the bag): what the CPU learner's
  * DataPartition encodes and the reference CUDA learner keeps in cuda_data_index_to_leaf_index_
  * (reference src/treelearner/cuda/cuda_data_partition.cu:113). */

@@ -121,6 +121,9 @@ class Learner {
     prep_blocks_ = num_sms_ * 2;
     partials_.alloc(prep_blocks_);
     ctl_.alloc(1);
+    CUDA_CHECK(cudaMemset(ctl_.p, 0, sizeof(Ctl)));      // exchange sequence numbers start at 0 on every rank
+    peers_ = CommPeers{};
+    peers_.rank = 0; peers_.world = 1; peers_.flags_stride = 0;
     feature_used_.alloc(F_);
     have_feature_mask_ = false;
     bag_count_ = -1;
@@ -175,6 +178,7 @@ class Learner {
     CUDA_CHECK(cudaStreamSynchronize(stream_));     // the one host sync per tree
     if (profiling_) CollectHistTimes();
 
+    if (h_ctl_->error) throw CudaError{"feature-shard exchange timed out: a peer rank did not arrive (see LGBMB200_LearnerCommConnect)"};
     const int n_leaves = h_ctl_->num_leaves;
     out->num_leaves = n_leaves;
     out->root_sum_gradient = h_ctl_->root_sum_g; out->root_sum_hessian = h_ctl_->root_sum_h;
@@ -193,7 +197,7 @@ class Learner {
     for (int i = 0; i < n_leaves - 1; ++i) {
       const SplitRec& r = h_splits_[i];
       LGBMB200_Split& s = out->splits[i];
-      s.leaf = r.leaf; s.feature = r.feature; s.threshold = r.threshold; s.default_left = r.default_left;
+      s.leaf = r.leaf; s.feature = r.feature + (peers_.world > 1 ? feature_offsets_[r.owner] : 0); s.threshold = r.threshold; s.default_left = r.default_left;
       s.left_count = r.left_count; s.right_count = r.right_count; s.gain = r.gain;
       s.left_sum_gradient = r.lsg; s.left_sum_hessian = r.lsh; s.left_output = r.lout;
       s.right_sum_gradient = r.rsg; s.right_sum_hessian = r.rsh; s.right_output = r.rout;
@@ -323,6 +327,39 @@ class Learner {
     last_num_leaves_ = 0;
   }
 
+  // ---- feature-shard bootstrap: export this rank's CommBlock, then map every peer's
+  void CommExport(uint8_t* handle_out) {
+    REQUIRE(inited_, "Init first");
+    const int64_t stride = (static_cast<int64_t>(N_) + 255) / 256 * 256;
+    const size_t bytes = sizeof(CommBlock) + 2 * static_cast<size_t>(stride);
+    if (!comm_local_) {
+      CUDA_CHECK(cudaMalloc(&comm_local_, bytes));
+      CUDA_CHECK(cudaMemset(comm_local_, 0, bytes));
+    }
+    comm_stride_ = stride;
+    cudaIpcMemHandle_t hnd;
+    CUDA_CHECK(cudaIpcGetMemHandle(&hnd, comm_local_));
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle_out, &hnd, 64);
+  }
+  void CommConnect(int rank, int world, const uint8_t* handles, const int32_t* feature_offsets) {
+    REQUIRE(comm_local_ != nullptr, "CommExport first");
+    REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "bad rank/world");
+    peers_ = CommPeers{};
+    peers_.rank = rank; peers_.world = world; peers_.flags_stride = comm_stride_;
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) { peers_.block[r] = reinterpret_cast<CommBlock*>(comm_local_); continue; }
+      cudaIpcMemHandle_t hnd;
+      std::memcpy(&hnd, handles + 64 * r, 64);
+      void* p = nullptr;
+      CUDA_CHECK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+      peers_.block[r] = reinterpret_cast<CommBlock*>(p);
+      comm_opened_.push_back(p);
+    }
+    feature_offsets_.assign(feature_offsets, feature_offsets + world + 1);
+    InvalidateGraph();
+  }
+
   void L2Gradients(const double* score, const float* label, float* grad, float* hess, int n) {
     k_l2_gradients<<<num_sms_ * 4, 256, 0, stream_>>>(score, label, grad, hess, n);
     ++launches_;
@@ -389,10 +426,11 @@ class Learner {
     sa.feat = feat_.p; sa.feature_used = have_feature_mask_ ? feature_used_.p : nullptr; sa.num_features = F_;
     sa.params = params_; sa.leaves = leaves_.p; sa.ctl = ctl_.p; sa.pool = pool_.p; sa.slot_stride = slot_stride_;
     sa.splittable = splittable_.p; sa.cand = cand_.p;
-    SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p};
+    SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p, peers_};
     PartArgs pt;
     pt.bins = bins_.p; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flags = flags_.p;
     pt.block_left = block_left_.p; pt.leaves = leaves_.p; pt.ctl = ctl_.p; pt.splits = splits_.p; pt.params = params_;
+    pt.peers = peers_;
     const int scan_blocks = (F_ + kScanWarps - 1) / kScanWarps;
     int hist_ev = 0;
 
@@ -404,6 +442,7 @@ class Learner {
       // it == 0: root pass; it >= 1: apply split it-1, then find splits for its two children
       if (it > 0) {
         k_part_flags<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
+        if (peers_.world > 1) { k_part_count<<<part_blocks_, kPartThreads, 0, stream_>>>(pt); ++launches_; }
         k_part_scatter<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
         launches_ += 2;
         if (it == NL - 1) break;   // the tree is full: no need to look for further splits
@@ -472,6 +511,9 @@ class Learner {
     for (auto& e : hist_events_) cudaEventDestroy(e);
     hist_events_.clear();
     if (h_splits_) { cudaFreeHost(h_splits_); cudaFreeHost(h_leaves_); cudaFreeHost(h_ctl_); h_splits_ = nullptr; }
+    for (void* p : comm_opened_) cudaIpcCloseMemHandle(p);
+    comm_opened_.clear();
+    if (comm_local_) { cudaFree(comm_local_); comm_local_ = nullptr; }
     if (h_row_leaf_) { cudaFreeHost(h_row_leaf_); h_row_leaf_ = nullptr; }
     if (t0_) { cudaEventDestroy(t0_); cudaEventDestroy(t1_); t0_ = nullptr; }
     if (stream_) { cudaStreamDestroy(stream_); stream_ = nullptr; }
@@ -494,6 +536,11 @@ class Learner {
   int32_t* h_row_leaf_ = nullptr;
   cudaEvent_t t0_ = nullptr, t1_ = nullptr;
   DevBuf<PartialSum> partials_;
+  CommPeers peers_{};
+  void* comm_local_ = nullptr;
+  int64_t comm_stride_ = 0;
+  std::vector<void*> comm_opened_;
+  std::vector<int32_t> feature_offsets_;
   DevBuf<Ctl> ctl_;
   DevBuf<Leaf> leaves_;
   DevBuf<SplitRec> splits_;
@@ -613,6 +660,19 @@ int LGBMB200_LearnerSetProfiling(LGBMB200_LearnerHandle h, int32_t enable) {
   API_BEGIN();
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->SetProfiling(enable);
+  API_END();
+}
+int LGBMB200_LearnerCommExport(LGBMB200_LearnerHandle h, uint8_t* handle_out_64) {
+  API_BEGIN();
+  if (!h || !handle_out_64) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->CommExport(handle_out_64);
+  API_END();
+}
+int LGBMB200_LearnerCommConnect(LGBMB200_LearnerHandle h, int32_t rank, int32_t world, const uint8_t* all_handles,
+                                const int32_t* feature_offsets) {
+  API_BEGIN();
+  if (!h || !all_handles || !feature_offsets) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->CommConnect(rank, world, all_handles, feature_offsets);
   API_END();
 }
 int LGBMB200_LearnerGetLeafIndex(LGBMB200_LearnerHandle h, int32_t* leaf_index_host) {

@@ -25,8 +25,9 @@ struct PartArgs {
   int64_t pitch;
   int32_t* idx0;
   int32_t* idx1;
-  uint8_t* flags;          // [num_data] scratch
+  uint8_t* flags;          // [num_data] scratch (single GPU); feature-shard mode uses the CommBlock flag buffers
   int32_t* block_left;     // [gridDim.x]
+  CommPeers peers;         // world == 1: plain local partition
   Leaf* leaves;
   Ctl* ctl;
   SplitRec* splits;        // [num_leaves-1] output records
@@ -51,13 +52,31 @@ __device__ __forceinline__ void part_block_range(int n, int nblocks, int b, int*
   *hi = min(n, *lo + per);
 }
 
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
-  const Ctl* c = a.ctl;
+  Ctl* c = a.ctl;
   if (!c->cur_valid) return;
+  const int W = a.peers.world, me = a.peers.rank;
+  if (W > 1 && c->cur_owner != me) return;        // only the rank that holds the split column computes flags
   const int n = c->cur_count, begin = c->cur_begin;
   const int32_t* src = (c->cur_buf ? a.idx1 : a.idx0) + begin;
   const FeatMeta m = c->cur_meta;
   const int threshold = c->cur_threshold, default_left = c->cur_default_left;
+  const unsigned long long fseq = c->flag_seq;      // bumped by k_select when it chose this split
+  const int par = static_cast<int>(fseq & 1);
+  uint8_t* fl[kMaxRanks];
+  if (W > 1) {
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r) fl[r] = r < W ? comm_flags(a.peers.block[r], par, a.peers.flags_stride) + begin : nullptr;
+  }
   int lo, hi;
   part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
   int cnt = 0;
@@ -65,9 +84,61 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
     const int row = __ldg(src + i);
     const uint32_t v = __ldg(a.bins + static_cast<int64_t>(row) * a.pitch + m.col);
     const bool left = goes_left(v, m, threshold, default_left);
-    a.flags[begin + i] = left ? 1 : 0;
+    if (W > 1) {
+      // push the go-left byte into every rank's flag buffer over NVLink (peer stores), own copy included
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r) if (r < W) fl[r][i] = left ? 1 : 0;
+    } else {
+      a.flags[begin + i] = left ? 1 : 0;
+    }
     cnt += left ? 1 : 0;
   }
+  __shared__ int s_cnt[kPartThreads / 32];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kPartThreads / 32; ++w) t += s_cnt[w];
+    a.block_left[blockIdx.x] = t;
+    if (W > 1) {
+      // last block publishes "flags of push #fseq are complete" to every rank
+      __threadfence_system();
+      const unsigned done = atomicAdd(&c->part_blocks_done, 1u);
+      if (done == gridDim.x - 1) {
+        __threadfence_system();
+        for (int r = 0; r < W; ++r) st_release_sys_u64(&a.peers.block[r]->flags_seq[par], fseq);
+      }
+    }
+  }
+}
+
+// feature-shard mode: every rank (owner included) waits for the pushed flags, then counts lefts per block
+__global__ void __launch_bounds__(kPartThreads) k_part_count(const PartArgs a) {
+  Ctl* c = a.ctl;
+  if (!c->cur_valid) return;
+  const unsigned long long fseq = c->flag_seq;
+  const int par = static_cast<int>(fseq & 1);
+  CommBlock* mine = a.peers.block[a.peers.rank];
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    int ok = 1;
+    while (ld_acquire_sys_u64(&mine->flags_seq[par]) != fseq) {
+      if (clock64() - t0 > 20000000000ll) { ok = 0; c->error = 1; break; }
+    }
+    s_ok = ok;
+  }
+  __syncthreads();
+  if (!s_ok) { a.block_left[blockIdx.x] = 0; return; }
+  const int n = c->cur_count, begin = c->cur_begin;
+  const uint8_t* fl = comm_flags(mine, par, a.peers.flags_stride) + begin;
+  int lo, hi;
+  part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
+  int cnt = 0;
+  for (int i = lo + threadIdx.x; i < hi; i += kPartThreads) cnt += __ldcv(fl + i) ? 1 : 0;
   __shared__ int s_cnt[kPartThreads / 32];
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
@@ -88,6 +159,11 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
   const int32_t* src = (c->cur_buf ? a.idx1 : a.idx0) + begin;
   int32_t* dst = (c->cur_buf ? a.idx0 : a.idx1) + begin;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint8_t* flags = a.flags;
+  if (a.peers.world > 1) {
+    if (c->error) return;
+    flags = comm_flags(a.peers.block[a.peers.rank], static_cast<int>(c->flag_seq & 1), a.peers.flags_stride);
+  }
 
   // offsets from the per-block counts (gridDim.x <= 1024)
   __shared__ int s_red[kPartThreads / 32];
@@ -118,7 +194,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
   for (int base = lo; base < hi; base += kPartThreads) {
     const int i = base + tid;
     const bool valid = i < hi;
-    const int flag = valid ? a.flags[begin + i] : 0;
+    const int flag = valid ? __ldcv(flags + begin + i) : 0;
     const unsigned bal = __ballot_sync(0xffffffffu, flag);
     const int wcnt = __popc(bal);
     const int rank_in_warp = __popc(bal & ((1u << lane) - 1u));
@@ -147,16 +223,16 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
     const int left_count = total_left, right_count = n - total_left;
     SplitRec& rec = a.splits[right - 1];
     rec.leaf = leaf; rec.feature = s.feature; rec.threshold = s.threshold; rec.default_left = s.default_left;
-    rec.left_count = left_count; rec.right_count = right_count;
+    rec.left_count = left_count; rec.right_count = right_count; rec.owner = s.owner; rec.pad = 0;
     rec.gain = s.gain; rec.lsg = s.lsg; rec.lsh = s.lsh; rec.lout = s.lout; rec.rsg = s.rsg; rec.rsh = s.rsh; rec.rout = s.rout;
 
     const int parent_slot = L.slot, parent_depth = L.depth, child_buf = 1 - L.buf;
     R.begin = begin + left_count; R.count = right_count; R.buf = child_buf; R.depth = parent_depth + 1;
     R.sum_g = s.rsg; R.sum_h = s.rsh; R.output = s.rout;
-    R.best.gain = -INFINITY; R.best.feature = -1;
+    R.best.gain = -INFINITY; R.best.feature = -1; R.best.real = 0x7fffffff; R.best.owner = 0;
     L.count = left_count; L.buf = child_buf; L.depth = parent_depth + 1;
     L.sum_g = s.lsg; L.sum_h = s.lsh; L.output = s.lout;
-    L.best.gain = -INFINITY; L.best.feature = -1;
+    L.best.gain = -INFINITY; L.best.feature = -1; L.best.real = 0x7fffffff; L.best.owner = 0;
     // smaller / larger (serial_tree_learner.cpp:858): the parent's pool slot becomes the larger child's,
     // the smaller child gets the fresh slot `right` (one new slot per split, zeroed by the host sequence)
     int smaller, larger;
@@ -253,7 +329,7 @@ __global__ void k_root_init(const PrepArgs a) {
     Leaf& L = a.leaves[i];
     L.begin = 0; L.count = 0; L.buf = 0; L.depth = 0; L.slot = 0; L.pad = 0;
     L.sum_g = 0; L.sum_h = 0; L.output = 0;
-    L.best.gain = -INFINITY; L.best.feature = -1;
+    L.best.gain = -INFINITY; L.best.feature = -1; L.best.real = 0x7fffffff; L.best.owner = 0;
   }
   Leaf& R = a.leaves[0];
   R.count = n_root; R.sum_g = sg; R.sum_h = sh;
@@ -266,7 +342,7 @@ __global__ void k_root_init(const PrepArgs a) {
     R.output = ret;
   }
   Ctl* c = a.ctl;
-  c->cur_valid = 1; c->cur_leaf = 0; c->cur_begin = 0; c->cur_count = n_root; c->cur_buf = 0;
+  c->cur_valid = 1; c->error = 0; c->cur_owner = 0; c->part_blocks_done = 0; c->cur_leaf = 0; c->cur_begin = 0; c->cur_count = n_root; c->cur_buf = 0;
   c->smaller = 0; c->larger = -1; c->do_find = 1; c->num_leaves = 1;
   // BeforeFindBestSplit at the root: too few rows to ever split
   if (n_root < a.params.min_data_in_leaf * 2) c->do_find = 0;

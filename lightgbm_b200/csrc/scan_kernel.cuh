@@ -208,6 +208,7 @@ __device__ __forceinline__ Cand find_best_threshold(const double (&g)[8], const 
   Cand out;
   out.gain = -INFINITY; out.feature = f; out.threshold = 0; out.default_left = 1;
   out.lsg = out.lsh = out.lout = out.rsg = out.rsh = out.rout = 0.0; out.left_count = out.right_count = 0; out.pad = 0;
+  out.real = m.real_index; out.owner = 0;
   const double sum_h = sum_h_in + 2 * B200_KEPS;
   const double min_gain_shift = leaf_gain(gc, sum_g, sum_h, num_data, parent_output) + P.min_gain_to_split;
   int splittable = 0;
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) k_scan(const ScanArgs a) {
   const Leaf& LS = a.leaves[smaller];
   Cand none; none.gain = -INFINITY; none.feature = -1; none.threshold = 0; none.default_left = 1;
   none.lsg = none.lsh = none.lout = none.rsg = none.rsh = none.rout = 0.0; none.left_count = none.right_count = 0; none.pad = 0;
+  none.real = 0x7fffffff; none.owner = 0;
 
   bool used = (a.feature_used == nullptr) || a.feature_used[f];
   uint8_t* sp_small = a.splittable + static_cast<int64_t>(LS.slot) * F;
@@ -360,7 +362,28 @@ struct SelectArgs {
   Leaf* leaves;
   Ctl* ctl;
   const Cand* cand;
+  CommPeers peers;            // world == 1: no exchange
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// payload written by a peer GPU: read it around L1 (the acquire on the sequence word orders it)
+__device__ __forceinline__ Cand load_cand_sys(const Cand* p) {
+  static_assert(sizeof(Cand) % 8 == 0, "Cand must be a multiple of 8 bytes");
+  Cand out;
+  const unsigned long long* s = reinterpret_cast<const unsigned long long*>(p);
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(&out);
+#pragma unroll
+  for (int i = 0; i < static_cast<int>(sizeof(Cand) / 8); ++i) d[i] = __ldcv(s + i);
+  return out;
+}
+constexpr long long kWatchdogCycles = 20000000000ll;   // ~10 s: a missing peer becomes an error, not a hang
 
 __device__ __forceinline__ bool cand_better(double ga, int fa_real, double gb, int fb_real) {
   if (ga != gb) return ga > gb;
@@ -401,18 +424,61 @@ __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
     }
     if (tid == 0) {
       Leaf& L = a.leaves[leaf];
-      if (s_idx[0] >= 0) L.best = a.cand[which * F + s_idx[0]];
-      else { L.best.gain = -INFINITY; L.best.feature = -1; }
+      if (s_idx[0] >= 0) { L.best = a.cand[which * F + s_idx[0]]; L.best.owner = a.peers.rank; }
+      else { L.best.gain = -INFINITY; L.best.feature = -1; L.best.real = 0x7fffffff; L.best.owner = a.peers.rank; }
     }
     __syncthreads();
   }
 
+  // ---- feature-shard: exchange the two per-leaf winners with every peer over NVLink peer memory and keep
+  // the global best (SyncUpGlobalBestSplit, reference src/treelearner/parallel_tree_learner.h:207-232).
+  // Every rank applies the same deterministic reduction => identical decisions everywhere.
+  if (a.peers.world > 1) {
+    const int W = a.peers.world, me = a.peers.rank;
+    const unsigned long long seq = c->xchg_seq + 1;
+    const int par = static_cast<int>(seq & 1);
+    if (tid < W) {
+      CommBlock* dst = a.peers.block[tid];
+      Cand* slot = &dst->mail[par][me][0];
+      slot[0] = a.leaves[smaller].best;
+      if (larger >= 0) slot[1] = a.leaves[larger].best;
+      __threadfence_system();
+      st_release_sys(&dst->mail_seq[par][me], seq);
+    }
+    __syncthreads();
+    if (tid < W) {
+      CommBlock* mine = a.peers.block[me];
+      const long long t0 = clock64();
+      while (ld_acquire_sys(&mine->mail_seq[par][tid]) != seq) {
+        if (clock64() - t0 > kWatchdogCycles) { c->error = 1; break; }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      CommBlock* mine = a.peers.block[me];
+      for (int which = 0; which < 2; ++which) {
+        const int leaf = which == 0 ? smaller : larger;
+        if (leaf < 0) continue;
+        Cand best = load_cand_sys(&mine->mail[par][0][which]);
+        for (int r = 1; r < W; ++r) {
+          const Cand o = load_cand_sys(&mine->mail[par][r][which]);
+          if (cand_better(o.gain, o.feature < 0 ? 0x7fffffff : o.real, best.gain, best.feature < 0 ? 0x7fffffff : best.real)) best = o;
+        }
+        a.leaves[leaf].best = best;
+      }
+      c->xchg_seq = seq;
+      if (c->error) c->cur_valid = 0;
+    }
+    __syncthreads();
+    if (c->error) return;
+  }
+  {
   // arg-max over all leaf slots (ungrown leaves hold gain = -inf, feature = -1)
   {
     double bg = -INFINITY; int br = 0x7fffffff, bi = 0x7fffffff;
     for (int i = tid; i < a.max_leaves; i += 256) {
       const Cand& cd = a.leaves[i].best;
-      const int real = cd.feature < 0 ? 0x7fffffff : a.feat[cd.feature].real_index;
+      const int real = cd.feature < 0 ? 0x7fffffff : cd.real;
       // first maximum in leaf order: strict operator> (array_args.h:52-58)
       if (cand_better(cd.gain, real, bg, br) || (bi == 0x7fffffff)) { bg = cd.gain; br = real; bi = i; }
     }
@@ -441,9 +507,13 @@ __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
       } else {
         c->cur_leaf = best_leaf; c->cur_begin = L.begin; c->cur_count = L.count; c->cur_buf = L.buf;
         c->cur_feature = L.best.feature; c->cur_threshold = L.best.threshold; c->cur_default_left = L.best.default_left;
-        c->cur_meta = a.feat[L.best.feature];
+        c->cur_owner = L.best.owner;
+        if (L.best.owner == a.peers.rank) c->cur_meta = a.feat[L.best.feature];   // only the owner holds the column
+        c->part_blocks_done = 0;
+        c->flag_seq += 1;          // sequence number of the flag push that applies this split
       }
     }
+  }
   }
 }
 

@@ -39,6 +39,8 @@ struct Cand {
   int32_t threshold;
   int32_t default_left;
   int32_t left_count, right_count;   // estimated (RoundInt(hess*cnt_factor)) until the partition ran
+  int32_t real;                // real (global) feature index: the cross-feature / cross-rank tie-break key
+  int32_t owner;               // rank that owns `feature` (feature-shard mode); 0 on a single GPU
   int32_t pad;
 };
 
@@ -70,14 +72,40 @@ struct Ctl {
   double root_sum_g, root_sum_h;
   int32_t root_count;          // rows in the root (bag size or num_data)
   int32_t root_identity;       // 1: root index list is 0..N-1 (no bagging) => histogram skips the index load
+  // ---- multi-GPU (feature-shard) state; persistent across trees
+  int32_t cur_owner;           // rank owning the feature of the split to apply
+  int32_t error;               // set by a watchdog when a peer never showed up
+  unsigned long long xchg_seq; // number of candidate exchanges done so far (mailbox sequence)
+  unsigned long long flag_seq; // number of flag pushes done so far
+  uint32_t part_blocks_done;   // last-block detection in k_part_flags
+  uint32_t pad2;
 };
 
 // One applied split, copied back to the host once per tree (mirrors LGBMB200_Split)
 struct SplitRec {
   int32_t leaf, feature, threshold, default_left, left_count, right_count;
+  int32_t owner, pad;
   double gain, lsg, lsh, lout, rsg, rsh, rout;
 };
 
 struct PartialSum { double g, h; float gmax, hmax; };
+
+// ---- feature-shard exchange over NVLink peer memory (one CommBlock per rank, IPC-mapped by every peer)
+constexpr int kMaxRanks = 16;
+struct CommBlock {
+  Cand mail[2][kMaxRanks][2];                 // [parity][source rank][smaller, larger] best candidates
+  unsigned long long mail_seq[2][kMaxRanks];  // written by the source rank after its payload
+  unsigned long long flags_seq[2];            // written by the split's owner after pushing the go-left flags
+  unsigned long long pad[6];
+  // followed by: uint8_t flags[2][num_data]
+};
+struct CommPeers {
+  CommBlock* block[kMaxRanks];                // block[r] = rank r's CommBlock (own entry = local pointer)
+  int32_t rank, world;
+  int64_t flags_stride;                       // bytes between the two flag buffers (= num_data rounded up)
+};
+__host__ __device__ inline uint8_t* comm_flags(CommBlock* b, int parity, int64_t stride) {
+  return reinterpret_cast<uint8_t*>(b + 1) + parity * stride;
+}
 
 }  // namespace b200

@@ -312,6 +312,19 @@ class B200TreeLearner:
                                                        None if out is None else _p(out), C.byref(ms)))
         return out, ms.value
 
+    # ---- feature-shard bootstrap (see lightgbm_b200/distributed.py)
+    def comm_export(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        check(lib().LGBMB200_LearnerCommExport(self.handle, buf))
+        return bytes(buf)
+
+    def comm_connect(self, rank: int, world: int, all_handles: bytes, feature_offsets) -> None:
+        assert len(all_handles) == 64 * world
+        off = np.ascontiguousarray(feature_offsets, dtype=np.int32)
+        assert len(off) == world + 1
+        hb = (C.c_uint8 * len(all_handles)).from_buffer_copy(all_handles)
+        check(lib().LGBMB200_LearnerCommConnect(self.handle, C.c_int32(rank), C.c_int32(world), hb, _p(off)))
+
     def get_leaf_index(self) -> np.ndarray:
         out = np.empty(self.layout.num_data, np.int32)
         check(lib().LGBMB200_LearnerGetLeafIndex(self.handle, _p(out)))
