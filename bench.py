@@ -265,6 +265,7 @@ def main():
     for _ in range(prof_steps):
         B.update()
     hist_ms, hist_rows, hist_launches = L.hist_stats()
+    by_kind = {k: v / prof_steps for k, v in L.profile_by_kind().items()}
     L.set_profiling(False)
     # algorithmic bytes: per histogrammed row C bin bytes + 8 (grad,hess) + 4 (row index, not for the root),
     # per launch the C*256*16 B of the int64 pool slot it fills
@@ -278,7 +279,8 @@ def main():
                 "traffic": tr["dram_bytes_per_launch"] if tr else None,
                 "hist_share_of_step": (hist_ms / prof_steps) / ms_per_step,
                 "alg_bytes_per_launch": alg_bytes / max(hist_launches, 1),
-                "avg_launch_ms": hist_ms / max(hist_launches, 1), "rows_built_factor_k": hist_rows / root_rows}
+                "avg_launch_ms": hist_ms / max(hist_launches, 1), "rows_built_factor_k": hist_rows / root_rows,
+                "ms_per_step_by_kernel": by_kind}
 
     # --- e2e: host buffers through the C-ABI, copies inside the timed region
     e2e = None

@@ -164,6 +164,10 @@ LGBMB200_EXPORT int64_t LGBMB200_LearnerKernelLaunches(LGBMB200_LearnerHandle h)
 LGBMB200_EXPORT int LGBMB200_LearnerHistStats(LGBMB200_LearnerHandle h, int32_t reset, double* hist_ms,
                                               double* hist_rows, int64_t* hist_launches);
 LGBMB200_EXPORT int LGBMB200_LearnerSetProfiling(LGBMB200_LearnerHandle h, int32_t enable);
+/* CUDA-event time (ms, accumulated since the last HistStats reset) per launch kind, profiling mode only:
+ * [0] unused, [1] prep+root_init, [2] part_flags, [3] part_count, [4] part_scatter, [5] pool memset, [6] hist,
+ * [7] scan, [8] select. */
+LGBMB200_EXPORT int LGBMB200_LearnerProfileByKind(LGBMB200_LearnerHandle h, double* ms_out_9);
 
 /* ---- Multi-GPU, feature-shard (semantic model: FeatureParallelTreeLearner, reference
  * src/treelearner/feature_parallel_tree_learner.cpp:37-78 + SyncUpGlobalBestSplit, parallel_tree_learner.h:207-232).

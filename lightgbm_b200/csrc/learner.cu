@@ -369,7 +369,8 @@ class Learner {
   void SetProfiling(int enable) {
     profiling_ = enable != 0;
     if (profiling_ && hist_events_.empty()) {
-      hist_events_.resize(2 * static_cast<size_t>(params_.num_leaves));
+      hist_events_.resize(8 * static_cast<size_t>(params_.num_leaves) + 8);
+      prof_kind_.assign(hist_events_.size(), 0);
       for (auto& e : hist_events_) CUDA_CHECK(cudaEventCreate(&e));
     }
   }
@@ -377,8 +378,9 @@ class Learner {
     if (ms) *ms = hist_ms_;
     if (rows) *rows = hist_rows_;
     if (launches) *launches = hist_launches_;
-    if (reset) { hist_ms_ = 0; hist_rows_ = 0; hist_launches_ = 0; }
+    if (reset) { hist_ms_ = 0; hist_rows_ = 0; hist_launches_ = 0; for (double& v : prof_ms_) v = 0; }
   }
+  void ProfileByKind(double* out9) { for (int i = 0; i < kProfKinds; ++i) out9[i] = prof_ms_[i]; }
   int64_t launches() const { return launches_; }
   cudaStream_t stream() const { return stream_; }
 
@@ -432,31 +434,36 @@ class Learner {
     pt.block_left = block_left_.p; pt.leaves = leaves_.p; pt.ctl = ctl_.p; pt.splits = splits_.p; pt.params = params_;
     pt.peers = peers_;
     const int scan_blocks = (F_ + kScanWarps - 1) / kScanWarps;
-    int hist_ev = 0;
+    prof_n_ = 0;
+    Stamp(kProfStart);
 
     k_prep<<<prep_blocks_, kPrepThreads, 0, stream_>>>(pa);
     k_root_init<<<1, 32, 0, stream_>>>(pa);
     CUDA_CHECK(cudaMemsetAsync(splittable_.p, 1, static_cast<size_t>(NL) * F_, stream_));
     launches_ += 2;
+    Stamp(kProfPrep);
     for (int it = 0; it < NL - 1 + 1; ++it) {
       // it == 0: root pass; it >= 1: apply split it-1, then find splits for its two children
       if (it > 0) {
         k_part_flags<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
-        if (peers_.world > 1) { k_part_count<<<part_blocks_, kPartThreads, 0, stream_>>>(pt); ++launches_; }
+        Stamp(kProfPartFlags);
+        if (peers_.world > 1) { k_part_count<<<part_blocks_, kPartThreads, 0, stream_>>>(pt); ++launches_; Stamp(kProfPartCount); }
         k_part_scatter<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
+        Stamp(kProfPartScatter);
         launches_ += 2;
         if (it == NL - 1) break;   // the tree is full: no need to look for further splits
       }
       const int slot = it;         // fresh pool slot of the leaf histogrammed in this iteration
       CUDA_CHECK(cudaMemsetAsync(pool_.p + static_cast<size_t>(slot) * slot_stride_, 0, sizeof(long long) * slot_stride_, stream_));
-      if (profiling_) CUDA_CHECK(cudaEventRecord(hist_events_[2 * hist_ev], stream_));
+      Stamp(kProfMemset);
       k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha);
-      if (profiling_) { CUDA_CHECK(cudaEventRecord(hist_events_[2 * hist_ev + 1], stream_)); ++hist_ev; }
+      Stamp(kProfHist);
       k_scan<<<scan_blocks, kScanWarps * 32, 0, stream_>>>(sa);
+      Stamp(kProfScan);
       k_select<<<1, 256, 0, stream_>>>(se);
+      Stamp(kProfSelect);
       launches_ += 3;
     }
-    hist_events_used_ = hist_ev;
     CUDA_CHECK(cudaGetLastError());
   }
 
@@ -484,12 +491,25 @@ class Learner {
     if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
   }
 
+  enum ProfKind { kProfStart = 0, kProfPrep, kProfPartFlags, kProfPartCount, kProfPartScatter, kProfMemset, kProfHist, kProfScan, kProfSelect, kProfKinds };
+  // profiling mode: an event after every launch; the segment since the previous event is charged to `kind`
+  void Stamp(int kind) {
+    if (!profiling_) return;
+    if (prof_n_ >= static_cast<int>(hist_events_.size())) return;
+    CUDA_CHECK(cudaEventRecord(hist_events_[prof_n_], stream_));
+    prof_kind_[prof_n_] = kind;
+    ++prof_n_;
+  }
   void CollectHistTimes() {
     // smaller-leaf row counts of every histogram pass are recoverable from the split records
-    for (int i = 0; i < hist_events_used_; ++i) {
+    int hist_launches = 0;
+    for (int i = 1; i < prof_n_; ++i) {
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, hist_events_[2 * i], hist_events_[2 * i + 1]) == cudaSuccess) hist_ms_ += ms;
+      if (cudaEventElapsedTime(&ms, hist_events_[i - 1], hist_events_[i]) != cudaSuccess) continue;
+      prof_ms_[prof_kind_[i]] += ms;
+      if (prof_kind_[i] == kProfHist) { hist_ms_ += ms; ++hist_launches; }
     }
+    hist_events_used_ = hist_launches;
     const int n_leaves = h_ctl_->num_leaves;
     double rows = h_ctl_->root_count;
     for (int i = 0; i < n_leaves - 1; ++i) {
@@ -560,6 +580,9 @@ class Learner {
   bool profiling_ = false;
   std::vector<cudaEvent_t> hist_events_;
   int hist_events_used_ = 0;
+  int prof_n_ = 0;
+  std::vector<int> prof_kind_;
+  double prof_ms_[16] = {0};
   double hist_ms_ = 0, hist_rows_ = 0;
   int64_t hist_launches_ = 0;
 };
@@ -654,6 +677,12 @@ int LGBMB200_LearnerHistStats(LGBMB200_LearnerHandle h, int32_t reset, double* h
   API_BEGIN();
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->HistStats(reset, hist_ms, hist_rows, hist_launches);
+  API_END();
+}
+int LGBMB200_LearnerProfileByKind(LGBMB200_LearnerHandle h, double* ms_out_9) {
+  API_BEGIN();
+  if (!h || !ms_out_9) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->ProfileByKind(ms_out_9);
   API_END();
 }
 int LGBMB200_LearnerSetProfiling(LGBMB200_LearnerHandle h, int32_t enable) {

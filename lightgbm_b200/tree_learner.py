@@ -350,6 +350,12 @@ class B200TreeLearner:
         check(lib().LGBMB200_LearnerHistStats(self.handle, C.c_int32(1 if reset else 0), C.byref(ms), C.byref(rows), C.byref(n)))
         return ms.value, rows.value, n.value
 
+    def profile_by_kind(self) -> dict:
+        out = np.zeros(9)
+        check(lib().LGBMB200_LearnerProfileByKind(self.handle, _p(out)))
+        names = ("_", "prep", "part_flags", "part_count", "part_scatter", "memset", "hist", "scan", "select")
+        return {n: float(v) for n, v in zip(names, out) if n != "_"}
+
     @property
     def kernel_launches(self) -> int:
         return int(lib().LGBMB200_LearnerKernelLaunches(self.handle))
