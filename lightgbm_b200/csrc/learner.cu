@@ -113,7 +113,7 @@ class Learner {
     if (pitch_ != C_) CUDA_CHECK(cudaMemset(bins_.p, 0, static_cast<size_t>(N_) * pitch_));
     CUDA_CHECK(cudaMemcpy2D(bins_.p, pitch_, bins_host, C_, C_, N_, cudaMemcpyHostToDevice));
 
-    gh_.alloc(N_); idx0_.alloc(N_); idx1_.alloc(N_); flags_.alloc(N_);
+    gh_.alloc(N_); idx0_.alloc(N_); idx1_.alloc(N_); flags_.alloc((static_cast<size_t>(N_) + 31) / 32 * 4 + 256);
     grad_stage_.alloc(N_); hess_stage_.alloc(N_);
     part_blocks_ = num_sms_ * 2;
     if (part_blocks_ > 1024) part_blocks_ = 1024;
@@ -330,7 +330,7 @@ class Learner {
   // ---- feature-shard bootstrap: export this rank's CommBlock, then map every peer's
   void CommExport(uint8_t* handle_out) {
     REQUIRE(inited_, "Init first");
-    const int64_t stride = (static_cast<int64_t>(N_) + 255) / 256 * 256;
+    const int64_t stride = ((static_cast<int64_t>(N_) + 31) / 32 * 4 + 255) / 256 * 256;
     const size_t bytes = sizeof(CommBlock) + 2 * static_cast<size_t>(stride);
     if (!comm_local_) {
       CUDA_CHECK(cudaMalloc(&comm_local_, bytes));
@@ -391,6 +391,8 @@ class Learner {
     pool_.alloc(static_cast<size_t>(slot_stride_) * NL);
     leaves_.alloc(NL); splits_.alloc(NL); cand_.alloc(2 * static_cast<size_t>(F_));
     splittable_.alloc(static_cast<size_t>(NL) * F_);
+    splittable_new_.alloc(2 * static_cast<size_t>(F_));
+    block_best_.alloc(2 * static_cast<size_t>((F_ + kScanWarps - 1) / kScanWarps));
     leaf_value_dev_.alloc(NL);
     if (h_splits_) { cudaFreeHost(h_splits_); cudaFreeHost(h_leaves_); cudaFreeHost(h_ctl_); }
     CUDA_CHECK(cudaMallocHost(&h_splits_, sizeof(SplitRec) * NL));
@@ -427,13 +429,13 @@ class Learner {
     ScanArgs sa;
     sa.feat = feat_.p; sa.feature_used = have_feature_mask_ ? feature_used_.p : nullptr; sa.num_features = F_;
     sa.params = params_; sa.leaves = leaves_.p; sa.ctl = ctl_.p; sa.pool = pool_.p; sa.slot_stride = slot_stride_;
-    sa.splittable = splittable_.p; sa.cand = cand_.p;
-    SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p, peers_};
+    sa.splittable = splittable_.p; sa.splittable_new = splittable_new_.p; sa.cand = cand_.p; sa.block_best = block_best_.p;
+    const int scan_blocks = (F_ + kScanWarps - 1) / kScanWarps;
+    SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p, block_best_.p, scan_blocks, splittable_.p, splittable_new_.p, peers_};
     PartArgs pt;
-    pt.bins = bins_.p; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flags = flags_.p;
+    pt.bins = bins_.p; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flag_words = reinterpret_cast<uint32_t*>(flags_.p);
     pt.block_left = block_left_.p; pt.leaves = leaves_.p; pt.ctl = ctl_.p; pt.splits = splits_.p; pt.params = params_;
     pt.peers = peers_;
-    const int scan_blocks = (F_ + kScanWarps - 1) / kScanWarps;
     prof_n_ = 0;
     Stamp(kProfStart);
 
@@ -442,6 +444,9 @@ class Learner {
     CUDA_CHECK(cudaMemsetAsync(splittable_.p, 1, static_cast<size_t>(NL) * F_, stream_));
     launches_ += 2;
     Stamp(kProfPrep);
+    // one memset for every histogram slot this tree can use (slot i is filled by iteration i)
+    CUDA_CHECK(cudaMemsetAsync(pool_.p, 0, sizeof(long long) * slot_stride_ * static_cast<size_t>(NL - 1), stream_));
+    Stamp(kProfMemset);
     for (int it = 0; it < NL - 1 + 1; ++it) {
       // it == 0: root pass; it >= 1: apply split it-1, then find splits for its two children
       if (it > 0) {
@@ -453,12 +458,9 @@ class Learner {
         launches_ += 2;
         if (it == NL - 1) break;   // the tree is full: no need to look for further splits
       }
-      const int slot = it;         // fresh pool slot of the leaf histogrammed in this iteration
-      CUDA_CHECK(cudaMemsetAsync(pool_.p + static_cast<size_t>(slot) * slot_stride_, 0, sizeof(long long) * slot_stride_, stream_));
-      Stamp(kProfMemset);
       k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha);
       Stamp(kProfHist);
-      k_scan<<<scan_blocks, kScanWarps * 32, 0, stream_>>>(sa);
+      k_scan<<<dim3(scan_blocks, 2), kScanWarps * 32, 0, stream_>>>(sa);
       Stamp(kProfScan);
       k_select<<<1, 256, 0, stream_>>>(se);
       Stamp(kProfSelect);
@@ -548,7 +550,8 @@ class Learner {
   int64_t pitch_ = 0, slot_stride_ = 0;
   int part_blocks_ = 296, prep_blocks_ = 296;
   DevBuf<FeatMeta> feat_;
-  DevBuf<uint8_t> bins_, flags_, feature_used_, splittable_;
+  DevBuf<uint8_t> bins_, flags_, feature_used_, splittable_, splittable_new_;
+  DevBuf<BlockBest> block_best_;
   DevBuf<float2> gh_;
   DevBuf<float> grad_stage_, hess_stage_;
   DevBuf<double> leaf_value_dev_;

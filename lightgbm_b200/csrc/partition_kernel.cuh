@@ -25,7 +25,8 @@ struct PartArgs {
   int64_t pitch;
   int32_t* idx0;
   int32_t* idx1;
-  uint8_t* flags;          // [num_data] scratch (single GPU); feature-shard mode uses the CommBlock flag buffers
+  uint32_t* flag_words;    // [ceil(num_data/32)] bit-packed go-left flags (single GPU); feature-shard mode uses
+                           // the CommBlock flag buffers instead
   int32_t* block_left;     // [gridDim.x]
   CommPeers peers;         // world == 1: plain local partition
   Leaf* leaves;
@@ -61,6 +62,13 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
   return v;
 }
 
+// Go-left flags are BIT-packed, one 32-bit ballot word per 32 consecutive rows of the leaf (leaf-relative
+// index i -> word i>>5, bit i&31).  Block ranges are multiples of 256 rows, so every warp owns whole words.
+// Single GPU: words go to the local scratch.  Feature-shard: only the split's owner computes them and
+// pushes each word into every rank's flag buffer over NVLink (n/8 bytes per peer), then publishes a
+// sequence number; k_part_count on every rank waits for it.
+constexpr int kPartUnroll = 4;
+
 __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
@@ -72,31 +80,40 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
   const int threshold = c->cur_threshold, default_left = c->cur_default_left;
   const unsigned long long fseq = c->flag_seq;      // bumped by k_select when it chose this split
   const int par = static_cast<int>(fseq & 1);
-  uint8_t* fl[kMaxRanks];
-  if (W > 1) {
-#pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r) fl[r] = r < W ? comm_flags(a.peers.block[r], par, a.peers.flags_stride) + begin : nullptr;
-  }
+  const int lane = threadIdx.x & 31;
+  const uint8_t* colp = a.bins + m.col;
   int lo, hi;
   part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
   int cnt = 0;
-  for (int i = lo + threadIdx.x; i < hi; i += kPartThreads) {
-    const int row = __ldg(src + i);
-    const uint32_t v = __ldg(a.bins + static_cast<int64_t>(row) * a.pitch + m.col);
-    const bool left = goes_left(v, m, threshold, default_left);
-    if (W > 1) {
-      // push the go-left byte into every rank's flag buffer over NVLink (peer stores), own copy included
+  for (int base = lo; base < hi; base += kPartThreads * kPartUnroll) {
+    // kPartUnroll independent (index -> bin byte) load chains per thread
+    int row[kPartUnroll]; uint32_t v[kPartUnroll];
 #pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r) if (r < W) fl[r][i] = left ? 1 : 0;
-    } else {
-      a.flags[begin + i] = left ? 1 : 0;
+    for (int k = 0; k < kPartUnroll; ++k) {
+      const int i = base + k * kPartThreads + threadIdx.x;
+      row[k] = i < hi ? __ldg(src + i) : -1;
     }
-    cnt += left ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < kPartUnroll; ++k) v[k] = row[k] >= 0 ? __ldg(colp + static_cast<int64_t>(row[k]) * a.pitch) : 0u;
+#pragma unroll
+    for (int k = 0; k < kPartUnroll; ++k) {
+      const int i = base + k * kPartThreads + threadIdx.x;
+      const bool left = row[k] >= 0 && goes_left(v[k], m, threshold, default_left);
+      const unsigned word = __ballot_sync(0xffffffffu, left);
+      if (lane == 0 && (i - lane) < hi) {
+        const int wi = (i - lane) >> 5;
+        if (W > 1) {
+#pragma unroll
+          for (int r = 0; r < kMaxRanks; ++r) if (r < W) comm_flag_words(a.peers.block[r], par, a.peers.flags_stride)[wi] = word;
+        } else {
+          a.flag_words[wi] = word;
+        }
+        cnt += __popc(word);
+      }
+    }
   }
   __shared__ int s_cnt[kPartThreads / 32];
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  if (lane == 0) s_cnt[threadIdx.x >> 5] = cnt;
   __syncthreads();
   if (threadIdx.x == 0) {
     int t = 0;
@@ -115,7 +132,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
   }
 }
 
-// feature-shard mode: every rank (owner included) waits for the pushed flags, then counts lefts per block
+// feature-shard mode: every rank (owner included) waits for the pushed flag words, then counts lefts per block
 __global__ void __launch_bounds__(kPartThreads) k_part_count(const PartArgs a) {
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
@@ -133,12 +150,12 @@ __global__ void __launch_bounds__(kPartThreads) k_part_count(const PartArgs a) {
   }
   __syncthreads();
   if (!s_ok) { a.block_left[blockIdx.x] = 0; return; }
-  const int n = c->cur_count, begin = c->cur_begin;
-  const uint8_t* fl = comm_flags(mine, par, a.peers.flags_stride) + begin;
+  const int n = c->cur_count;
+  const uint32_t* fw = comm_flag_words(mine, par, a.peers.flags_stride);
   int lo, hi;
   part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
   int cnt = 0;
-  for (int i = lo + threadIdx.x; i < hi; i += kPartThreads) cnt += __ldcv(fl + i) ? 1 : 0;
+  for (int wi = (lo >> 5) + threadIdx.x; wi < ((hi + 31) >> 5); wi += kPartThreads) cnt += __popc(__ldcv(fw + wi));
   __shared__ int s_cnt[kPartThreads / 32];
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
@@ -159,14 +176,14 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
   const int32_t* src = (c->cur_buf ? a.idx1 : a.idx0) + begin;
   int32_t* dst = (c->cur_buf ? a.idx0 : a.idx1) + begin;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint8_t* flags = a.flags;
+  const uint32_t* fw = a.flag_words;
   if (a.peers.world > 1) {
     if (c->error) return;
-    flags = comm_flags(a.peers.block[a.peers.rank], static_cast<int>(c->flag_seq & 1), a.peers.flags_stride);
+    fw = comm_flag_words(a.peers.block[a.peers.rank], static_cast<int>(c->flag_seq & 1), a.peers.flags_stride);
   }
 
   // offsets from the per-block counts (gridDim.x <= 1024)
-  __shared__ int s_red[kPartThreads / 32];
+  __shared__ int s_red[kPartUnroll][kPartThreads / 32];
   __shared__ int s_before, s_total;
   int before = 0, total = 0;
   for (int j = tid; j < static_cast<int>(gridDim.x); j += kPartThreads) {
@@ -191,25 +208,32 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
 
   int lo, hi;
   part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
-  for (int base = lo; base < hi; base += kPartThreads) {
-    const int i = base + tid;
-    const bool valid = i < hi;
-    const int flag = valid ? __ldcv(flags + begin + i) : 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, flag);
-    const int wcnt = __popc(bal);
-    const int rank_in_warp = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) s_red[warp] = wcnt;
-    __syncthreads();
-    int wbefore = 0, tile_left = 0;
+  for (int base = lo; base < hi; base += kPartThreads * kPartUnroll) {
+    unsigned word[kPartUnroll]; int row[kPartUnroll];
 #pragma unroll
-    for (int w = 0; w < kPartThreads / 32; ++w) { const int v = s_red[w]; if (w < warp) wbefore += v; tile_left += v; }
-    if (valid) {
-      const int lefts_before_me = left_run + wbefore + rank_in_warp;
-      const int row = src[i];
-      if (flag) dst[lefts_before_me] = row;
-      else dst[total_left + (i - lefts_before_me)] = row;
+    for (int k = 0; k < kPartUnroll; ++k) {
+      const int i = base + k * kPartThreads + tid;
+      const int w0 = i - lane;                       // first row of this warp's word
+      word[k] = (w0 < hi) ? __ldcv(fw + (w0 >> 5)) : 0u;
+      row[k] = (i < hi) ? src[i] : -1;
+      if (lane == 0) s_red[k][warp] = __popc(word[k]);
     }
-    left_run += tile_left;
+    __syncthreads();
+    int run = left_run;
+#pragma unroll
+    for (int k = 0; k < kPartUnroll; ++k) {
+      int wbefore = 0, tile_left = 0;
+#pragma unroll
+      for (int w = 0; w < kPartThreads / 32; ++w) { const int v = s_red[k][w]; if (w < warp) wbefore += v; tile_left += v; }
+      const int i = base + k * kPartThreads + tid;
+      if (i < hi) {
+        const int lefts_before_me = run + wbefore + __popc(word[k] & ((1u << lane) - 1u));
+        if ((word[k] >> lane) & 1u) dst[lefts_before_me] = row[k];
+        else dst[total_left + (i - lefts_before_me)] = row[k];
+      }
+      run += tile_left;
+    }
+    left_run = run;
     __syncthreads();
   }
 

@@ -246,6 +246,8 @@ __device__ __forceinline__ Cand find_best_threshold(const double (&g)[8], const 
   return out;
 }
 
+struct BlockBest { double gain; int32_t real; int32_t feature; };   // per k_scan block: its best candidate
+
 struct ScanArgs {
   const FeatMeta* feat;
   const uint8_t* feature_used;      // by-tree mask or nullptr
@@ -255,101 +257,121 @@ struct ScanArgs {
   const Ctl* ctl;
   long long* pool;
   int64_t slot_stride;
-  uint8_t* splittable;              // [slot][num_features] FeatureHistogram::is_splittable_
+  const uint8_t* splittable;        // [slot][num_features] FeatureHistogram::is_splittable_ (read-only here)
+  uint8_t* splittable_new;          // [2][num_features]: 0/1 = new flag of (smaller, larger), 2 = leave unchanged
   Cand* cand;                       // [2][num_features]: smaller, larger
+  BlockBest* block_best;            // [2][gridDim.x]
 };
 
 constexpr int kScanWarps = 8;
 
+// grid = (ceil(F/8), 2): blockIdx.y = 0 scans the smaller child, 1 the larger child (= parent - smaller).
+// One warp per (feature, child); the two warps of a feature are independent: the larger-child warp re-derives
+// the smaller child's fixed slice itself, so nothing is exchanged between them.
 __global__ void __launch_bounds__(kScanWarps * 32, 1) k_scan(const ScanArgs a) {
   const Ctl* c = a.ctl;
   if (!c->cur_valid || !c->do_find) return;
-  const int lane = threadIdx.x & 31;
-  const int f = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
-  if (f >= a.num_features) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int which = blockIdx.y;
+  const int f = blockIdx.x * kScanWarps + warp;
   const int F = a.num_features;
   const int smaller = c->smaller, larger = c->larger;
-  const Leaf& LS = a.leaves[smaller];
-  Cand none; none.gain = -INFINITY; none.feature = -1; none.threshold = 0; none.default_left = 1;
-  none.lsg = none.lsh = none.lout = none.rsg = none.rsh = none.rout = 0.0; none.left_count = none.right_count = 0; none.pad = 0;
-  none.real = 0x7fffffff; none.owner = 0;
+  __shared__ double s_gain[kScanWarps];
+  __shared__ int s_real[kScanWarps], s_feat[kScanWarps];
 
-  bool used = (a.feature_used == nullptr) || a.feature_used[f];
-  uint8_t* sp_small = a.splittable + static_cast<int64_t>(LS.slot) * F;
-  uint8_t* sp_large = larger >= 0 ? a.splittable + static_cast<int64_t>(a.leaves[larger].slot) * F : nullptr;
-  if (used && sp_large != nullptr && !sp_large[f]) {
-    // parent was not splittable on this feature (serial_tree_learner.cpp:397-402)
-    if (lane == 0) sp_small[f] = 0;
-    used = false;
-  }
-  if (!used) {
-    if (lane == 0) { a.cand[f] = none; a.cand[F + f] = none; }
-    return;
-  }
+  Cand out;                       // this warp's candidate (lane-uniform)
+  out.gain = -INFINITY; out.feature = -1; out.threshold = 0; out.default_left = 1;
+  out.lsg = out.lsh = out.lout = out.rsg = out.rsh = out.rout = 0.0; out.left_count = out.right_count = 0; out.pad = 0;
+  out.real = 0x7fffffff; out.owner = 0;
+  int new_flag = 2;
 
-  const FeatMeta m = a.feat[f];
-  const GainCfg gc = make_gain_cfg(a.params);
-  const double g_inv = c->g_inv, h_inv = c->h_inv;
-  const int64_t slice = (static_cast<int64_t>(m.col) * kBinsPerColumn + m.lo) * 2;
-  long long* hs = a.pool + static_cast<int64_t>(LS.slot) * a.slot_stride + slice;
+  const bool active = f < F && !(which == 1 && larger < 0);
+  if (active) {
+    const Leaf& LS = a.leaves[smaller];
+    bool used = (a.feature_used == nullptr) || a.feature_used[f];
+    if (used && larger >= 0 && !a.splittable[static_cast<int64_t>(a.leaves[larger].slot) * F + f]) {
+      // parent was not splittable on this feature (serial_tree_learner.cpp:397-402): both children inherit it
+      used = false; new_flag = (which == 0) ? 0 : 2;
+    }
+    if (used) {
+      const FeatMeta m = a.feat[f];
+      const GainCfg gc = make_gain_cfg(a.params);
+      const double g_inv = c->g_inv, h_inv = c->h_inv;
+      const int64_t slice = (static_cast<int64_t>(m.col) * kBinsPerColumn + m.lo) * 2;
+      long long* hs = a.pool + static_cast<int64_t>(LS.slot) * a.slot_stride + slice;
 
-  // ---- smaller child: load slice, FixHistogram, scan
-  long long ig[8], ih[8];
+      // smaller child's slice + FixHistogram (exact integer arithmetic)
+      long long ig[8], ih[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int e = lane * 8 + k;
-    if (e < m.nslice) {
-      const longlong2 v = *reinterpret_cast<const longlong2*>(hs + 2 * e);
-      ig[k] = v.x; ih[k] = v.y;
-    } else { ig[k] = 0; ih[k] = 0; }
-  }
-  if (m.mfb > 0) {
-    // Dataset::FixHistogram: entry[mfb] = leaf total - sum(other entries), exact in fixed point
-    long long og = 0, oh = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { if (lane * 8 + k != m.mfb) { og += ig[k]; oh += ih[k]; } }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) { og += __shfl_xor_sync(0xffffffffu, og, d); oh += __shfl_xor_sync(0xffffffffu, oh, d); }
-    const long long tg = __double2ll_rn(LS.sum_g * c->g_scale) - og;
-    const long long th = __double2ll_rn(LS.sum_h * c->h_scale) - oh;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (lane * 8 + k == m.mfb) {
-        ig[k] = tg; ih[k] = th;
-        *reinterpret_cast<longlong2*>(hs + 2 * m.mfb) = make_longlong2(tg, th);
+      for (int k = 0; k < 8; ++k) {
+        const int e = lane * 8 + k;
+        if (e < m.nslice) {
+          const longlong2 v = *reinterpret_cast<const longlong2*>(hs + 2 * e);
+          ig[k] = v.x; ih[k] = v.y;
+        } else { ig[k] = 0; ih[k] = 0; }
       }
+      if (m.mfb > 0) {
+        // Dataset::FixHistogram: entry[mfb] = leaf total - sum(other entries); the stored mfb entry is ignored,
+        // so it does not matter whether the smaller-child warp has already written it back
+        long long og = 0, oh = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { if (lane * 8 + k != m.mfb) { og += ig[k]; oh += ih[k]; } }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) { og += __shfl_xor_sync(0xffffffffu, og, d); oh += __shfl_xor_sync(0xffffffffu, oh, d); }
+        const long long tg = __double2ll_rn(LS.sum_g * c->g_scale) - og;
+        const long long th = __double2ll_rn(LS.sum_h * c->h_scale) - oh;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (lane * 8 + k == m.mfb) {
+            ig[k] = tg; ih[k] = th;
+            if (which == 0) *reinterpret_cast<longlong2*>(hs + 2 * m.mfb) = make_longlong2(tg, th);
+          }
+        }
+      }
+      double g[8], h[8];
+      int splittable = 0;
+      if (which == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { h[k] = static_cast<double>(ih[k]) * h_inv; g[k] = (ih[k] == 0) ? 0.0 : static_cast<double>(ig[k]) * g_inv; }
+        const double po = (c->num_leaves == 1)
+            ? leaf_output(GainCfg{1, 1, 0, a.params.l1, a.params.l2, a.params.max_delta_step, a.params.path_smooth}, LS.sum_g, LS.sum_h, LS.count, 0.0)
+            : LS.output;
+        out = find_best_threshold(g, h, lane, f, m, a.params, gc, LS.sum_g, LS.sum_h, LS.count, po, &splittable);
+      } else {
+        // larger child = parent - smaller (exact), written in place into the parent's slot
+        const Leaf& LL = a.leaves[larger];
+        long long* hl = a.pool + static_cast<int64_t>(LL.slot) * a.slot_stride + slice;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = lane * 8 + k;
+          if (e < m.nslice) {
+            longlong2 v = *reinterpret_cast<const longlong2*>(hl + 2 * e);
+            v.x -= ig[k]; v.y -= ih[k];
+            *reinterpret_cast<longlong2*>(hl + 2 * e) = v;
+            h[k] = static_cast<double>(v.y) * h_inv;
+            g[k] = (v.y == 0) ? 0.0 : static_cast<double>(v.x) * g_inv;
+          } else { g[k] = 0.0; h[k] = 0.0; }
+        }
+        out = find_best_threshold(g, h, lane, f, m, a.params, gc, LL.sum_g, LL.sum_h, LL.count, LL.output, &splittable);
+      }
+      new_flag = splittable;
+    }
+    if (lane == 0) {
+      a.cand[which * F + f] = out;
+      a.splittable_new[which * F + f] = static_cast<uint8_t>(new_flag);
     }
   }
-  double g[8], h[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { h[k] = static_cast<double>(ih[k]) * h_inv; g[k] = (ih[k] == 0) ? 0.0 : static_cast<double>(ig[k]) * g_inv; }
-
-  const double po_small = (c->num_leaves == 1)
-      ? leaf_output(GainCfg{1, 1, 0, a.params.l1, a.params.l2, a.params.max_delta_step, a.params.path_smooth}, LS.sum_g, LS.sum_h, LS.count, 0.0)
-      : LS.output;
-  int splittable = 0;
-  Cand cs = find_best_threshold(g, h, lane, f, m, a.params, gc, LS.sum_g, LS.sum_h, LS.count, po_small, &splittable);
-  if (lane == 0) { a.cand[f] = cs; sp_small[f] = static_cast<uint8_t>(splittable); }
-
-  if (larger < 0) { if (lane == 0) a.cand[F + f] = none; return; }
-
-  // ---- larger child = parent - smaller (exact), in place in the parent's slot
-  const Leaf& LL = a.leaves[larger];
-  long long* hl = a.pool + static_cast<int64_t>(LL.slot) * a.slot_stride + slice;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int e = lane * 8 + k;
-    if (e < m.nslice) {
-      longlong2 v = *reinterpret_cast<const longlong2*>(hl + 2 * e);
-      v.x -= ig[k]; v.y -= ih[k];
-      *reinterpret_cast<longlong2*>(hl + 2 * e) = v;
-      h[k] = static_cast<double>(v.y) * h_inv;
-      g[k] = (v.y == 0) ? 0.0 : static_cast<double>(v.x) * g_inv;
-    } else { g[k] = 0.0; h[k] = 0.0; }
+  // block-level arg-max (gain, then smaller real feature index) so that k_select scans F/8 entries only
+  if (lane == 0) { s_gain[warp] = out.gain; s_real[warp] = out.feature < 0 ? 0x7fffffff : out.real; s_feat[warp] = out.feature; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    BlockBest bb; bb.gain = -INFINITY; bb.real = 0x7fffffff; bb.feature = -1;
+    for (int w = 0; w < kScanWarps; ++w) {
+      if (s_feat[w] < 0) continue;
+      if (s_gain[w] > bb.gain || (s_gain[w] == bb.gain && s_real[w] < bb.real)) { bb.gain = s_gain[w]; bb.real = s_real[w]; bb.feature = s_feat[w]; }
+    }
+    a.block_best[which * gridDim.x + blockIdx.x] = bb;
   }
-  splittable = 0;
-  Cand cl = find_best_threshold(g, h, lane, f, m, a.params, gc, LL.sum_g, LL.sum_h, LL.count, LL.output, &splittable);
-  if (lane == 0) { a.cand[F + f] = cl; sp_large[f] = static_cast<uint8_t>(splittable); }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -362,7 +384,11 @@ struct SelectArgs {
   Leaf* leaves;
   Ctl* ctl;
   const Cand* cand;
-  CommPeers peers;            // world == 1: no exchange
+  const BlockBest* block_best;  // [2][scan_blocks]
+  int32_t scan_blocks;
+  uint8_t* splittable;          // [slot][num_features]
+  const uint8_t* splittable_new;  // [2][num_features] written by k_scan
+  CommPeers peers;              // world == 1: no exchange
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -400,16 +426,25 @@ __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
   const int F = a.num_features;
   const int smaller = c->smaller, larger = c->larger;
 
+  // hand the children's is_splittable_ flags over (k_scan wrote them to a staging array so that the parent's
+  // flags stayed immutable while both children were being scanned)
+  if (c->do_find) {
+    for (int which = 0; which < 2; ++which) {
+      const int leaf = which == 0 ? smaller : larger;
+      if (leaf < 0) continue;
+      uint8_t* dst = a.splittable + static_cast<int64_t>(a.leaves[leaf].slot) * F;
+      for (int f = tid; f < F; f += 256) { const uint8_t v = a.splittable_new[which * F + f]; if (v != 2) dst[f] = v; }
+    }
+  }
   for (int which = 0; which < 2; ++which) {
     const int leaf = which == 0 ? smaller : larger;
     if (leaf < 0) continue;
     double bg = -INFINITY; int br = 0x7fffffff, bi = -1;
     if (c->do_find) {
-      for (int f = tid; f < F; f += 256) {
-        const Cand& cd = a.cand[which * F + f];
-        if (cd.feature < 0) continue;
-        const int real = a.feat[f].real_index;
-        if (cand_better(cd.gain, real, bg, br)) { bg = cd.gain; br = real; bi = f; }
+      for (int b = tid; b < a.scan_blocks; b += 256) {
+        const BlockBest bb = a.block_best[which * a.scan_blocks + b];
+        if (bb.feature < 0) continue;
+        if (cand_better(bb.gain, bb.real, bg, br)) { bg = bb.gain; br = bb.real; bi = bb.feature; }
       }
     }
     s_gain[tid] = bg; s_real[tid] = br; s_idx[tid] = bi;

@@ -97,15 +97,15 @@ struct CommBlock {
   unsigned long long mail_seq[2][kMaxRanks];  // written by the source rank after its payload
   unsigned long long flags_seq[2];            // written by the split's owner after pushing the go-left flags
   unsigned long long pad[6];
-  // followed by: uint8_t flags[2][num_data]
+  // followed by: uint32_t flag_words[2][ceil(num_data/32)] (bit-packed go-left flags)
 };
 struct CommPeers {
   CommBlock* block[kMaxRanks];                // block[r] = rank r's CommBlock (own entry = local pointer)
   int32_t rank, world;
-  int64_t flags_stride;                       // bytes between the two flag buffers (= num_data rounded up)
+  int64_t flags_stride;                       // bytes between the two flag-word buffers
 };
-__host__ __device__ inline uint8_t* comm_flags(CommBlock* b, int parity, int64_t stride) {
-  return reinterpret_cast<uint8_t*>(b + 1) + parity * stride;
+__host__ __device__ inline uint32_t* comm_flag_words(CommBlock* b, int parity, int64_t stride) {
+  return reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(b + 1) + parity * stride);
 }
 
 }  // namespace b200
