@@ -51,7 +51,8 @@ typedef struct {
   double  max_delta_step;
   double  path_smooth;
   int32_t use_cuda_graph;           /* 1: replay the whole per-tree launch sequence as one CUDA graph */
-  int32_t reserved;
+  int32_t reserved;                 /* bit 0: do NOT keep the column-major copy of the bin matrix used by the
+                                       partition kernels (saves num_data*num_columns bytes of HBM) */
 } LGBMB200_Config;
 
 /*

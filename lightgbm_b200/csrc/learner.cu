@@ -113,6 +113,15 @@ class Learner {
     if (pitch_ != C_) CUDA_CHECK(cudaMemset(bins_.p, 0, static_cast<size_t>(N_) * pitch_));
     CUDA_CHECK(cudaMemcpy2D(bins_.p, pitch_, bins_host, C_, C_, N_, cudaMemcpyHostToDevice));
 
+    // column-major copy for the partition kernels (+C*N bytes; LGBMB200_Config.reserved bit 0 disables it)
+    if (!(cfg_.reserved & 1)) {
+      binsT_.alloc(static_cast<size_t>(N_) * C_);
+      dim3 tg(static_cast<unsigned>((N_ + 31) / 32), static_cast<unsigned>((C_ + 31) / 32));
+      k_transpose_bins<<<tg, 256, 0, stream_>>>(bins_.p, pitch_, N_, C_, binsT_.p);
+      CUDA_CHECK(cudaGetLastError());
+    } else {
+      binsT_.release();
+    }
     gh_.alloc(N_); idx0_.alloc(N_); idx1_.alloc(N_); flags_.alloc((static_cast<size_t>(N_) + 31) / 32 * 4 + 256);
     grad_stage_.alloc(N_); hess_stage_.alloc(N_);
     part_blocks_ = num_sms_ * 2;
@@ -433,7 +442,7 @@ class Learner {
     const int scan_blocks = (F_ + kScanWarps - 1) / kScanWarps;
     SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p, block_best_.p, scan_blocks, splittable_.p, splittable_new_.p, peers_};
     PartArgs pt;
-    pt.bins = bins_.p; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flag_words = reinterpret_cast<uint32_t*>(flags_.p);
+    pt.bins = bins_.p; pt.binsT = binsT_.p; pt.num_data = N_; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flag_words = reinterpret_cast<uint32_t*>(flags_.p);
     pt.block_left = block_left_.p; pt.leaves = leaves_.p; pt.ctl = ctl_.p; pt.splits = splits_.p; pt.params = params_;
     pt.peers = peers_;
     prof_n_ = 0;
@@ -550,7 +559,7 @@ class Learner {
   int64_t pitch_ = 0, slot_stride_ = 0;
   int part_blocks_ = 296, prep_blocks_ = 296;
   DevBuf<FeatMeta> feat_;
-  DevBuf<uint8_t> bins_, flags_, feature_used_, splittable_, splittable_new_;
+  DevBuf<uint8_t> bins_, binsT_, flags_, feature_used_, splittable_, splittable_new_;
   DevBuf<BlockBest> block_best_;
   DevBuf<float2> gh_;
   DevBuf<float> grad_stage_, hess_stage_;

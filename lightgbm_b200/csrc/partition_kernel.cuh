@@ -21,7 +21,9 @@ namespace b200 {
 constexpr int kPartThreads = 256;
 
 struct PartArgs {
-  const uint8_t* bins;
+  const uint8_t* bins;     // row-major [N x pitch] (used when no column-major copy exists)
+  const uint8_t* binsT;    // column-major copy [Cpad x N] for the partition, or nullptr
+  int64_t num_data;
   int64_t pitch;
   int32_t* idx0;
   int32_t* idx1;
@@ -81,7 +83,11 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
   const unsigned long long fseq = c->flag_seq;      // bumped by k_select when it chose this split
   const int par = static_cast<int>(fseq & 1);
   const int lane = threadIdx.x & 31;
-  const uint8_t* colp = a.bins + m.col;
+  // the column-major copy turns the per-row 32-byte sector gather of the row-major matrix (1 useful byte per
+  // sector, ~8x below DRAM peak at the root) into a near-sequential byte stream: rows of a leaf are ascending
+  const bool use_t = a.binsT != nullptr;
+  const uint8_t* colp = use_t ? a.binsT + static_cast<int64_t>(m.col) * a.num_data : a.bins + m.col;
+  const int64_t rstride = use_t ? 1 : a.pitch;
   int lo, hi;
   part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
   int cnt = 0;
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
       row[k] = i < hi ? __ldg(src + i) : -1;
     }
 #pragma unroll
-    for (int k = 0; k < kPartUnroll; ++k) v[k] = row[k] >= 0 ? __ldg(colp + static_cast<int64_t>(row[k]) * a.pitch) : 0u;
+    for (int k = 0; k < kPartUnroll; ++k) v[k] = row[k] >= 0 ? __ldg(colp + static_cast<int64_t>(row[k]) * rstride) : 0u;
 #pragma unroll
     for (int k = 0; k < kPartUnroll; ++k) {
       const int i = base + k * kPartThreads + threadIdx.x;
@@ -270,6 +276,25 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
     if (a.params.max_depth > 0 && parent_depth + 1 >= a.params.max_depth) do_find = 0;
     if (right_count < a.params.min_data_in_leaf * 2 && left_count < a.params.min_data_in_leaf * 2) do_find = 0;
     c->do_find = do_find;
+  }
+}
+
+// One-off at Init: column-major copy of the bin matrix (32x32 byte tiles through shared memory)
+__global__ void __launch_bounds__(256) k_transpose_bins(const uint8_t* __restrict__ bins, int64_t pitch, int64_t N, int C,
+                                                        uint8_t* __restrict__ binsT) {
+  __shared__ uint8_t tile[32][33];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t r = r0 + j;
+    tile[j][tx] = (r < N && c0 + tx < C) ? bins[r * pitch + c0 + tx] : 0;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const int64_t r = r0 + tx;
+    if (c < C && r < N) binsT[static_cast<int64_t>(c) * N + r] = tile[tx][j];
   }
 }
 

@@ -419,53 +419,46 @@ __device__ __forceinline__ bool cand_better(double ga, int fa_real, double gb, i
 __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
-  __shared__ double s_gain[256];
-  __shared__ int s_real[256];
-  __shared__ int s_idx[256];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int F = a.num_features;
-  const int smaller = c->smaller, larger = c->larger;
+  const int smaller = c->smaller, larger = c->larger, do_find = c->do_find;
 
-  // hand the children's is_splittable_ flags over (k_scan wrote them to a staging array so that the parent's
-  // flags stayed immutable while both children were being scanned)
-  if (c->do_find) {
+  // (1) warps 0/1: per-leaf arg-max over the k_scan block winners (SplitInfo::operator>) -> leaves[].best
+  //     warps 2..7: hand the children's is_splittable_ flags over from the staging array
+  if (warp < 2) {
+    const int which = warp;
+    const int leaf = which == 0 ? smaller : larger;
+    if (leaf >= 0) {
+      double bg = -INFINITY; int br = 0x7fffffff, bi = -1;
+      if (do_find) {
+        for (int b = lane; b < a.scan_blocks; b += 32) {
+          const BlockBest bb = a.block_best[which * a.scan_blocks + b];
+          if (bb.feature >= 0 && cand_better(bb.gain, bb.real, bg, br)) { bg = bb.gain; br = bb.real; bi = bb.feature; }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+          const double og = __shfl_xor_sync(0xffffffffu, bg, d);
+          const int orl = __shfl_xor_sync(0xffffffffu, br, d), oi = __shfl_xor_sync(0xffffffffu, bi, d);
+          if (oi >= 0 && cand_better(og, orl, bg, br)) { bg = og; br = orl; bi = oi; }
+        }
+      }
+      if (lane == 0) {
+        Leaf& L = a.leaves[leaf];
+        if (bi >= 0) { L.best = a.cand[which * F + bi]; L.best.owner = a.peers.rank; }
+        else { L.best.gain = -INFINITY; L.best.feature = -1; L.best.real = 0x7fffffff; L.best.owner = a.peers.rank; }
+      }
+    }
+  } else if (do_find) {
     for (int which = 0; which < 2; ++which) {
       const int leaf = which == 0 ? smaller : larger;
       if (leaf < 0) continue;
       uint8_t* dst = a.splittable + static_cast<int64_t>(a.leaves[leaf].slot) * F;
-      for (int f = tid; f < F; f += 256) { const uint8_t v = a.splittable_new[which * F + f]; if (v != 2) dst[f] = v; }
+      for (int f = tid - 64; f < F; f += 192) { const uint8_t v = a.splittable_new[which * F + f]; if (v != 2) dst[f] = v; }
     }
   }
-  for (int which = 0; which < 2; ++which) {
-    const int leaf = which == 0 ? smaller : larger;
-    if (leaf < 0) continue;
-    double bg = -INFINITY; int br = 0x7fffffff, bi = -1;
-    if (c->do_find) {
-      for (int b = tid; b < a.scan_blocks; b += 256) {
-        const BlockBest bb = a.block_best[which * a.scan_blocks + b];
-        if (bb.feature < 0) continue;
-        if (cand_better(bb.gain, bb.real, bg, br)) { bg = bb.gain; br = bb.real; bi = bb.feature; }
-      }
-    }
-    s_gain[tid] = bg; s_real[tid] = br; s_idx[tid] = bi;
-    __syncthreads();
-    for (int st = 128; st >= 1; st >>= 1) {
-      if (tid < st) {
-        if (cand_better(s_gain[tid + st], s_real[tid + st], s_gain[tid], s_real[tid])) {
-          s_gain[tid] = s_gain[tid + st]; s_real[tid] = s_real[tid + st]; s_idx[tid] = s_idx[tid + st];
-        }
-      }
-      __syncthreads();
-    }
-    if (tid == 0) {
-      Leaf& L = a.leaves[leaf];
-      if (s_idx[0] >= 0) { L.best = a.cand[which * F + s_idx[0]]; L.best.owner = a.peers.rank; }
-      else { L.best.gain = -INFINITY; L.best.feature = -1; L.best.real = 0x7fffffff; L.best.owner = a.peers.rank; }
-    }
-    __syncthreads();
-  }
+  __syncthreads();
 
-  // ---- feature-shard: exchange the two per-leaf winners with every peer over NVLink peer memory and keep
+  // (2) feature-shard: exchange the two per-leaf winners with every peer over NVLink peer memory and keep
   // the global best (SyncUpGlobalBestSplit, reference src/treelearner/parallel_tree_learner.h:207-232).
   // Every rank applies the same deterministic reduction => identical decisions everywhere.
   if (a.peers.world > 1) {
@@ -489,11 +482,11 @@ __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      CommBlock* mine = a.peers.block[me];
-      for (int which = 0; which < 2; ++which) {
-        const int leaf = which == 0 ? smaller : larger;
-        if (leaf < 0) continue;
+    if (tid < 2) {
+      const int which = tid;
+      const int leaf = which == 0 ? smaller : larger;
+      if (leaf >= 0) {
+        CommBlock* mine = a.peers.block[me];
         Cand best = load_cand_sys(&mine->mail[par][0][which]);
         for (int r = 1; r < W; ++r) {
           const Cand o = load_cand_sys(&mine->mail[par][r][which]);
@@ -501,40 +494,31 @@ __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
         }
         a.leaves[leaf].best = best;
       }
-      c->xchg_seq = seq;
-      if (c->error) c->cur_valid = 0;
     }
+    __syncthreads();
+    if (tid == 0) { c->xchg_seq = seq; if (c->error) c->cur_valid = 0; }
     __syncthreads();
     if (c->error) return;
   }
-  {
-  // arg-max over all leaf slots (ungrown leaves hold gain = -inf, feature = -1)
-  {
+
+  // (3) warp 0: arg-max over all leaf slots (array_args.h:45-60: first maximum in leaf order under
+  //     operator>; ungrown leaves hold gain = -inf, feature = -1), stop rule, snapshot of the split to apply
+  if (warp == 0) {
     double bg = -INFINITY; int br = 0x7fffffff, bi = 0x7fffffff;
-    for (int i = tid; i < a.max_leaves; i += 256) {
+    for (int i = lane; i < a.max_leaves; i += 32) {
       const Cand& cd = a.leaves[i].best;
-      const int real = cd.feature < 0 ? 0x7fffffff : cd.real;
-      // first maximum in leaf order: strict operator> (array_args.h:52-58)
-      if (cand_better(cd.gain, real, bg, br) || (bi == 0x7fffffff)) { bg = cd.gain; br = real; bi = i; }
+      const double g = cd.gain; const int real = cd.feature < 0 ? 0x7fffffff : cd.real;
+      if (bi == 0x7fffffff || cand_better(g, real, bg, br)) { bg = g; br = real; bi = i; }
     }
-    s_gain[tid] = bg; s_real[tid] = br; s_idx[tid] = bi;
-    __syncthreads();
-    for (int st = 128; st >= 1; st >>= 1) {
-      if (tid < st) {
-        const bool other_valid = s_idx[tid + st] != 0x7fffffff;
-        const bool mine_valid = s_idx[tid] != 0x7fffffff;
-        bool take = false;
-        if (other_valid && !mine_valid) take = true;
-        else if (other_valid && mine_valid) {
-          if (cand_better(s_gain[tid + st], s_real[tid + st], s_gain[tid], s_real[tid])) take = true;
-          else if (!cand_better(s_gain[tid], s_real[tid], s_gain[tid + st], s_real[tid + st]) && s_idx[tid + st] < s_idx[tid]) take = true;
-        }
-        if (take) { s_gain[tid] = s_gain[tid + st]; s_real[tid] = s_real[tid + st]; s_idx[tid] = s_idx[tid + st]; }
-      }
-      __syncthreads();
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const double og = __shfl_xor_sync(0xffffffffu, bg, d);
+      const int orl = __shfl_xor_sync(0xffffffffu, br, d), oi = __shfl_xor_sync(0xffffffffu, bi, d);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || cand_better(og, orl, bg, br) ||
+                               (!cand_better(bg, br, og, orl) && oi < bi))) { bg = og; br = orl; bi = oi; }
     }
-    if (tid == 0) {
-      const int best_leaf = s_idx[0];
+    if (lane == 0) {
+      const int best_leaf = bi;
       const Leaf& L = a.leaves[best_leaf];
       // serial_tree_learner.cpp:232: stop when the best gain is <= 0; also when the tree is full
       if (L.best.gain <= 0.0 || L.best.feature < 0 || c->num_leaves >= a.max_leaves) {
@@ -548,7 +532,6 @@ __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
         c->flag_seq += 1;          // sequence number of the flag push that applies this split
       }
     }
-  }
   }
 }
 
