@@ -33,6 +33,7 @@ namespace b200 {
 constexpr int kHistWarps = 3;                    // consumer warps (one per SMSP 0..2), each with a partner producer warp
 constexpr int kHistThreads = 2 * kHistWarps * 32; // warps 0..2 consume, warps 3..5 produce (warp 3 owns SMSP 3)
 constexpr int kStageRows = 32;
+constexpr int kHistBatch = 4;                    // rows per in-register RMW batch (independent LDS.64 in flight per warp)
 constexpr int kStages = 6;                       // ring depth; kStages-1 stages in flight
 constexpr int kWarpHistBytes = kBinsPerColumn * 32 * 8;           // 65536
 constexpr int kStageBinBytes = kStageRows * kColGroup;            // 1024
@@ -80,26 +81,26 @@ __device__ __forceinline__ void sts64(unsigned addr, float2 v) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y));
 }
 
-// Four rows of the lane's column.  All four cells are loaded BEFORE any store, so rows that hit the same
-// bin see the same old value v; the new value of row j is v + (sum of the q_i, i <= j, with b_i == b_j).
-// Those partial sums do not depend on the loads and are formed while the LDS are in flight, so the
-// critical path per batch is LDS -> FADD -> STS.  Stores are issued in row order: the last store to a
-// cell carries the complete sum.  Fixed evaluation order => bitwise run-to-run determinism.
-__device__ __forceinline__ void rmw4(unsigned hbase, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3,
-                                     float4 q01, float4 q23) {
-  const unsigned a0 = hbase + (b0 << 8), a1 = hbase + (b1 << 8), a2 = hbase + (b2 << 8), a3 = hbase + (b3 << 8);
-  const float2 v0 = lds64(a0), v1 = lds64(a1), v2 = lds64(a2), v3 = lds64(a3);
-  float2 s1 = make_float2(q01.z, q01.w), s2 = make_float2(q23.x, q23.y), s3 = make_float2(q23.z, q23.w);
-  if (b1 == b0) { s1.x += q01.x; s1.y += q01.y; }
-  if (b2 == b0) { s2.x += q01.x; s2.y += q01.y; }
-  if (b2 == b1) { s2.x += q01.z; s2.y += q01.w; }
-  if (b3 == b0) { s3.x += q01.x; s3.y += q01.y; }
-  if (b3 == b1) { s3.x += q01.z; s3.y += q01.w; }
-  if (b3 == b2) { s3.x += q23.x; s3.y += q23.y; }
-  sts64(a0, make_float2(v0.x + q01.x, v0.y + q01.y));
-  sts64(a1, make_float2(v1.x + s1.x, v1.y + s1.y));
-  sts64(a2, make_float2(v2.x + s2.x, v2.y + s2.y));
-  sts64(a3, make_float2(v3.x + s3.x, v3.y + s3.y));
+// K rows of the lane's column.  All K cells are loaded BEFORE any store, so rows that hit the same bin see the
+// same old value v; the new value of row i is v + (q_i + sum of the q_j, j < i, with b_j == b_i).  Those
+// partial sums do not depend on the loads and are formed while the LDS are in flight, so the critical path
+// per batch is LDS -> FADD -> STS and K independent LDS.64 are in flight per warp (with 3 warps per SM the
+// shared-memory pipe is latency-bound, so K is the lever).  Stores are issued in row order: the last store
+// to a cell carries the complete sum.  Fixed evaluation order => bitwise run-to-run determinism.
+template <int K>
+__device__ __forceinline__ void rmw_batch(unsigned hbase, const uint32_t (&b)[K], const float2 (&q)[K]) {
+  unsigned addr[K];
+  float2 v[K], s[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) { addr[i] = hbase + (b[i] << 8); v[i] = lds64(addr[i]); }
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    s[i] = q[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) if (b[j] == b[i]) { s[i].x += q[j].x; s[i].y += q[j].y; }
+  }
+#pragma unroll
+  for (int i = 0; i < K; ++i) sts64(addr[i], make_float2(v[i].x + s[i].x, v[i].y + s[i].y));
 }
 
 // ---- mbarrier helpers (shared::cta) -----------------------------------------------------------------
@@ -227,20 +228,20 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a) {
       const unsigned char* sbin = sb + lane;
       const float2* sgh = reinterpret_cast<const float2*>(sb + kStageBinBytes);
       if (cnt == kStageRows) {
-        uint32_t b0 = sbin[0], b1 = sbin[32], b2 = sbin[64], b3 = sbin[96];
-        float4 q01 = *reinterpret_cast<const float4*>(sgh), q23 = *reinterpret_cast<const float4*>(sgh + 2);
+        constexpr int K = kHistBatch;
+        // fully unrolled: the stage reads are plain loads (free to be hoisted above the previous batch's
+        // histogram stores, which are asm volatile and ordered among themselves)
 #pragma unroll
-        for (int r = 0; r < kStageRows; r += 4) {
-          // software pipeline: fetch the next batch from the stage before this batch's stores
-          uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-          float4 t01 = q01, t23 = q23;
-          if (r + 4 < kStageRows) {
-            c0 = sbin[(r + 4) * 32]; c1 = sbin[(r + 5) * 32]; c2 = sbin[(r + 6) * 32]; c3 = sbin[(r + 7) * 32];
-            t01 = *reinterpret_cast<const float4*>(sgh + r + 4);
-            t23 = *reinterpret_cast<const float4*>(sgh + r + 6);
+        for (int r = 0; r < kStageRows; r += K) {
+          uint32_t cb[K]; float2 cq[K];
+#pragma unroll
+          for (int i = 0; i < K; ++i) cb[i] = sbin[(r + i) * 32];
+#pragma unroll
+          for (int i = 0; i < K; i += 2) {
+            const float4 t = *reinterpret_cast<const float4*>(sgh + r + i);
+            cq[i] = make_float2(t.x, t.y); cq[i + 1] = make_float2(t.z, t.w);
           }
-          rmw4(hbase, b0, b1, b2, b3, q01, q23);
-          b0 = c0; b1 = c1; b2 = c2; b3 = c3; q01 = t01; q23 = t23;
+          rmw_batch<K>(hbase, cb, cq);
         }
       } else {
         for (int r = 0; r < cnt; ++r) {

@@ -115,6 +115,9 @@ class Learner {
 
     // column-major copy for the partition kernels (+C*N bytes; LGBMB200_Config.reserved bit 0 disables it)
     if (!(cfg_.reserved & 1)) {
+      // a pageable H2D cudaMemcpy may return before its DMA has landed, and stream_ is a non-blocking stream:
+      // make the matrix resident before the first kernel reads it
+      CUDA_CHECK(cudaDeviceSynchronize());
       binsT_.alloc(static_cast<size_t>(N_) * C_);
       dim3 tg(static_cast<unsigned>((N_ + 31) / 32), static_cast<unsigned>((C_ + 31) / 32));
       k_transpose_bins<<<tg, 256, 0, stream_>>>(bins_.p, pitch_, N_, C_, binsT_.p);

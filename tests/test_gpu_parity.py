@@ -161,3 +161,55 @@ def test_booster_device_resident_equals_host_mode(mods):
     np.testing.assert_allclose(a.scores(), b.scores(), rtol=1e-6, atol=1e-9)
     assert a.l2() < l0 * 0.8
     assert a.learner.kernel_launches > 0
+
+
+def test_leaf_index_bagging_host_score_and_profiling(mods):
+    lgb, orc = mods
+    n, f = 20000, 9
+    bins, y, g, h = synth_identity(n, f, seed=31)
+    lay = lgb.Layout.identity(bins)
+    L = _learner(lgb, lay, num_leaves=15)
+    bag = np.sort(np.random.default_rng(4).choice(n, n // 3, replace=False)).astype(np.int32)
+    L.set_bagging_data(bag)
+    t = L.train(g, h)
+    li = L.get_leaf_index()
+    assert (li[bag] >= 0).all() and (np.delete(li, bag) == -1).all()       # rows outside the bag are in no leaf
+    lb, lc, idx = L.get_partition(t.num_leaves)
+    for leaf in range(t.num_leaves):
+        assert (li[idx[lb[leaf]:lb[leaf] + lc[leaf]]] == leaf).all()
+    score = np.zeros(n)
+    L.add_prediction_to_score(t, score)                                     # host path: leaf ids D2H + host add
+    want = np.where(li >= 0, t.leaf_value[np.maximum(li, 0)], 0.0)
+    np.testing.assert_array_equal(score, want)
+    # profiling mode (no CUDA graph) grows the identical tree and reports per-kernel times
+    L.set_bagging_data(None)
+    t_graph = L.train(g, h)
+    L.set_profiling(True); L.hist_stats(reset=True)
+    t_prof = L.train(g, h)
+    L.set_profiling(False)
+    assert np.array_equal(t_graph.splits, t_prof.splits) and np.array_equal(t_graph.leaf_value, t_prof.leaf_value)
+    ms, rows, nl = L.hist_stats()
+    kinds = L.profile_by_kind()
+    assert ms > 0 and rows >= n and nl >= 1 and kinds["hist"] > 0 and kinds["scan"] > 0 and kinds["part_flags"] > 0
+    L.timer_start(); L.train(g, h); assert L.timer_stop() > 0
+
+
+def test_row_major_partition_path_matches_column_major(mods):
+    """LGBMB200_Config.reserved bit 0 drops the column-major copy; both partition paths must agree."""
+    lgb, _ = mods
+    import ctypes as C
+    from lightgbm_b200 import tree_learner as TL
+    n, f = 30000, 20
+    bins, y, g, h = synth_identity(n, f, seed=77)
+    lay = lgb.Layout.identity(bins)
+    a = _learner(lgb, lay, num_leaves=31)
+    ta = a.train(g, h)
+    cfg = lgb.Config(num_leaves=31)
+    orig = cfg.to_c
+
+    def to_c_no_t():
+        c = orig(); c.reserved = 1; return c
+    cfg.to_c = to_c_no_t
+    b = lgb.B200TreeLearner(cfg); b.init(lay)
+    tb = b.train(g, h)
+    assert np.array_equal(ta.splits, tb.splits) and np.array_equal(ta.leaf_count, tb.leaf_count)
