@@ -182,6 +182,18 @@ LGBMB200_EXPORT int LGBMB200_LearnerCommExport(LGBMB200_LearnerHandle h, uint8_t
 LGBMB200_EXPORT int LGBMB200_LearnerCommConnect(LGBMB200_LearnerHandle h, int32_t rank, int32_t world,
                                                 const uint8_t* all_handles, const int32_t* feature_offsets);
 
+/* ---- Multi-GPU, row-shard (semantic model: DataParallelTreeLearner, reference
+ * src/treelearner/data_parallel_tree_learner.cpp, and the reference's own num_gpu>1 mode,
+ * src/boosting/cuda/nccl_gbdt_component.hpp:30-57).  Every learner is Init-ed with ITS row slice and ALL columns;
+ * Train takes the gradients of those rows.  Per split: local histogram of the smaller child -> the owning rank
+ * of each feature slice sums the peers' histogram slots straight out of their HBM over NVLink inside the scan
+ * kernel (exact int64) -> candidate exchange as in feature-shard mode -> local partition + an all-gather of the
+ * left/right counts.  Root sums and counts are global.  Bootstrap: CommExport + CommExportPool handles of every
+ * rank, then CommConnectRows. */
+LGBMB200_EXPORT int LGBMB200_LearnerCommExportPool(LGBMB200_LearnerHandle h, uint8_t* handle_out_64);
+LGBMB200_EXPORT int LGBMB200_LearnerCommConnectRows(LGBMB200_LearnerHandle h, int32_t rank, int32_t world,
+                                                    const uint8_t* comm_handles, const uint8_t* pool_handles);
+
 /* Per-row leaf id of the last tree (host output, -1 for rows outside the bag): what the CPU learner's
  * DataPartition encodes and the reference CUDA learner keeps in cuda_data_index_to_leaf_index_
  * (reference src/treelearner/cuda/cuda_data_partition.cu:113). */

@@ -138,7 +138,7 @@ __device__ __forceinline__ bool hist_work_setup(const HistArgs& a, int pair, His
     const Ctl* c = a.ctl;
     if (!c->cur_valid || !c->do_find) return false;
     const Leaf& L = a.leaves[c->smaller];
-    w->n = L.count; w->begin = L.begin; w->slot = L.slot;
+    w->n = L.lcount; w->begin = L.begin; w->slot = L.slot;
     // the root of an un-bagged tree is the identity list: skip the index load altogether
     w->idx = (c->num_leaves == 1 && c->root_identity) ? nullptr : (L.buf ? a.idx1 : a.idx0);
   }

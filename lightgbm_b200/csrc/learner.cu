@@ -209,7 +209,7 @@ class Learner {
     for (int i = 0; i < n_leaves - 1; ++i) {
       const SplitRec& r = h_splits_[i];
       LGBMB200_Split& s = out->splits[i];
-      s.leaf = r.leaf; s.feature = r.feature + (peers_.world > 1 ? feature_offsets_[r.owner] : 0); s.threshold = r.threshold; s.default_left = r.default_left;
+      s.leaf = r.leaf; s.feature = r.feature + ((peers_.world > 1 && peers_.mode == 0) ? feature_offsets_[r.owner] : 0); s.threshold = r.threshold; s.default_left = r.default_left;
       s.left_count = r.left_count; s.right_count = r.right_count; s.gain = r.gain;
       s.left_sum_gradient = r.lsg; s.left_sum_hessian = r.lsh; s.left_output = r.lout;
       s.right_sum_gradient = r.rsg; s.right_sum_hessian = r.rsh; s.right_output = r.rout;
@@ -286,9 +286,9 @@ class Learner {
     CUDA_CHECK(cudaMemcpy(b1.data(), idx1_.p, sizeof(int32_t) * N_, cudaMemcpyDeviceToHost));
     for (int l = 0; l < last_num_leaves_; ++l) {
       const Leaf& L = h_leaves_[l];
-      leaf_begin[l] = L.begin; leaf_count[l] = L.count;
+      leaf_begin[l] = L.begin; leaf_count[l] = L.lcount;      // rows of the leaf held by this rank
       const std::vector<int32_t>& src = L.buf ? b1 : b0;
-      std::memcpy(indices + L.begin, src.data() + L.begin, sizeof(int32_t) * L.count);
+      std::memcpy(indices + L.begin, src.data() + L.begin, sizeof(int32_t) * L.lcount);
     }
   }
 
@@ -310,6 +310,7 @@ class Learner {
     // prep with "no bagging" semantics over all rows: packs gh and sets the fixed-point scales
     PrepArgs pa = MakePrepArgs(g, h);
     pa.bag = nullptr; pa.bag_count = 0;
+    pa.peers.world = 1;            // stand-alone hook: local histogram only, no exchange
     k_prep<<<prep_blocks_, kPrepThreads, 0, stream_>>>(pa);
     k_root_init<<<1, 32, 0, stream_>>>(pa);
     const int32_t* didx = nullptr;
@@ -372,6 +373,33 @@ class Learner {
     InvalidateGraph();
   }
 
+  // row-shard bootstrap: additionally export the histogram pool, whose peer copies k_scan sums over NVLink
+  void CommExportPool(uint8_t* handle_out) {
+    REQUIRE(inited_, "Init first");
+    cudaIpcMemHandle_t hnd;
+    CUDA_CHECK(cudaIpcGetMemHandle(&hnd, pool_.p));
+    std::memcpy(handle_out, &hnd, 64);
+  }
+  void CommConnectRows(int rank, int world, const uint8_t* comm_handles, const uint8_t* pool_handles) {
+    const std::vector<int32_t> dummy(world + 1, 0);
+    CommConnect(rank, world, comm_handles, dummy.data());
+    peers_.mode = 1;
+    // feature slice reduced + scanned by this rank: contiguous, balanced by count
+    const int base = F_ / world, extra = F_ % world;
+    peers_.f_lo = rank * base + std::min(rank, extra);
+    peers_.f_cnt = base + (rank < extra ? 1 : 0);
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) { peers_.pool[r] = pool_.p; continue; }
+      cudaIpcMemHandle_t hnd;
+      std::memcpy(&hnd, pool_handles + 64 * r, 64);
+      void* p = nullptr;
+      CUDA_CHECK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+      peers_.pool[r] = reinterpret_cast<long long*>(p);
+      comm_opened_.push_back(p);
+    }
+    InvalidateGraph();
+  }
+
   void L2Gradients(const double* score, const float* label, float* grad, float* hess, int n) {
     k_l2_gradients<<<num_sms_ * 4, 256, 0, stream_>>>(score, label, grad, hess, n);
     ++launches_;
@@ -421,7 +449,7 @@ class Learner {
     pa.grad = g; pa.hess = h; pa.gh = gh_.p; pa.idx0 = idx0_.p;
     pa.bag = bag_count_ >= 0 ? bag_.p : nullptr; pa.bag_count = bag_count_ >= 0 ? bag_count_ : 0;
     pa.num_data = N_; pa.partials = partials_.p; pa.leaves = leaves_.p; pa.ctl = ctl_.p; pa.params = params_;
-    pa.max_leaves = params_.num_leaves; pa.num_partials = prep_blocks_;
+    pa.max_leaves = params_.num_leaves; pa.num_partials = prep_blocks_; pa.peers = peers_;
     return pa;
   }
   HistArgs MakeHistArgs() {
@@ -442,7 +470,9 @@ class Learner {
     sa.feat = feat_.p; sa.feature_used = have_feature_mask_ ? feature_used_.p : nullptr; sa.num_features = F_;
     sa.params = params_; sa.leaves = leaves_.p; sa.ctl = ctl_.p; sa.pool = pool_.p; sa.slot_stride = slot_stride_;
     sa.splittable = splittable_.p; sa.splittable_new = splittable_new_.p; sa.cand = cand_.p; sa.block_best = block_best_.p;
-    const int scan_blocks = (F_ + kScanWarps - 1) / kScanWarps;
+    sa.peers = peers_;
+    const bool row_mode = peers_.world > 1 && peers_.mode == 1;
+    const int scan_blocks = ((row_mode ? peers_.f_cnt : F_) + kScanWarps - 1) / kScanWarps;
     SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p, block_best_.p, scan_blocks, splittable_.p, splittable_new_.p, peers_};
     PartArgs pt;
     pt.bins = bins_.p; pt.binsT = binsT_.p; pt.num_data = N_; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flag_words = reinterpret_cast<uint32_t*>(flags_.p);
@@ -464,7 +494,7 @@ class Learner {
       if (it > 0) {
         k_part_flags<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
         Stamp(kProfPartFlags);
-        if (peers_.world > 1) { k_part_count<<<part_blocks_, kPartThreads, 0, stream_>>>(pt); ++launches_; Stamp(kProfPartCount); }
+        if (peers_.world > 1 && peers_.mode == 0) { k_part_count<<<part_blocks_, kPartThreads, 0, stream_>>>(pt); ++launches_; Stamp(kProfPartCount); }
         k_part_scatter<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
         Stamp(kProfPartScatter);
         launches_ += 2;
@@ -472,7 +502,8 @@ class Learner {
       }
       k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha);
       Stamp(kProfHist);
-      k_scan<<<dim3(scan_blocks, 2), kScanWarps * 32, 0, stream_>>>(sa);
+      if (row_mode) { k_hist_signal<<<1, 32, 0, stream_>>>(peers_, ctl_.p); ++launches_; }
+      k_scan<<<dim3(std::max(scan_blocks, 1), row_mode ? 1 : 2), kScanWarps * 32, 0, stream_>>>(sa);
       Stamp(kProfScan);
       k_select<<<1, 256, 0, stream_>>>(se);
       Stamp(kProfSelect);
@@ -717,6 +748,19 @@ int LGBMB200_LearnerCommConnect(LGBMB200_LearnerHandle h, int32_t rank, int32_t 
   API_BEGIN();
   if (!h || !all_handles || !feature_offsets) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->CommConnect(rank, world, all_handles, feature_offsets);
+  API_END();
+}
+int LGBMB200_LearnerCommExportPool(LGBMB200_LearnerHandle h, uint8_t* handle_out_64) {
+  API_BEGIN();
+  if (!h || !handle_out_64) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->CommExportPool(handle_out_64);
+  API_END();
+}
+int LGBMB200_LearnerCommConnectRows(LGBMB200_LearnerHandle h, int32_t rank, int32_t world, const uint8_t* comm_handles,
+                                    const uint8_t* pool_handles) {
+  API_BEGIN();
+  if (!h || !comm_handles || !pool_handles) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->CommConnectRows(rank, world, comm_handles, pool_handles);
   API_END();
 }
 int LGBMB200_LearnerGetLeafIndex(LGBMB200_LearnerHandle h, int32_t* leaf_index_host) {

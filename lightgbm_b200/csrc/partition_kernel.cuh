@@ -14,6 +14,7 @@
 //                    Thread 0 of block 0 then plays SplitInner: child leaf records, smaller/larger
 //                    choice, histogram-slot hand-over, BeforeFindBestSplit gates, the split record.
 #pragma once
+#include "comm.cuh"
 #include "types.cuh"
 
 namespace b200 {
@@ -55,15 +56,6 @@ __device__ __forceinline__ void part_block_range(int n, int nblocks, int b, int*
   *hi = min(n, *lo + per);
 }
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
 // Go-left flags are BIT-packed, one 32-bit ballot word per 32 consecutive rows of the leaf (leaf-relative
 // index i -> word i>>5, bit i&31).  Block ranges are multiples of 256 rows, so every warp owns whole words.
 // Single GPU: words go to the local scratch.  Feature-shard: only the split's owner computes them and
@@ -74,8 +66,9 @@ constexpr int kPartUnroll = 4;
 __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
-  const int W = a.peers.world, me = a.peers.rank;
-  if (W > 1 && c->cur_owner != me) return;        // only the rank that holds the split column computes flags
+  const int me = a.peers.rank;
+  const int W = a.peers.mode == 1 ? 1 : a.peers.world;   // row-shard: every rank flags its own rows, no push
+  if (W > 1 && c->cur_owner != me) return;        // feature-shard: only the rank that holds the split column computes flags
   const int n = c->cur_count, begin = c->cur_begin;
   const int32_t* src = (c->cur_buf ? a.idx1 : a.idx0) + begin;
   const FeatMeta m = c->cur_meta;
@@ -132,7 +125,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
       const unsigned done = atomicAdd(&c->part_blocks_done, 1u);
       if (done == gridDim.x - 1) {
         __threadfence_system();
-        for (int r = 0; r < W; ++r) st_release_sys_u64(&a.peers.block[r]->flags_seq[par], fseq);
+        for (int r = 0; r < W; ++r) st_release_sys(&a.peers.block[r]->flags_seq[par], fseq);
       }
     }
   }
@@ -147,11 +140,8 @@ __global__ void __launch_bounds__(kPartThreads) k_part_count(const PartArgs a) {
   CommBlock* mine = a.peers.block[a.peers.rank];
   __shared__ int s_ok;
   if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    int ok = 1;
-    while (ld_acquire_sys_u64(&mine->flags_seq[par]) != fseq) {
-      if (clock64() - t0 > 20000000000ll) { ok = 0; c->error = 1; break; }
-    }
+    const int ok = wait_seq(&mine->flags_seq[par], fseq) ? 1 : 0;
+    if (!ok) c->error = 1;
     s_ok = ok;
   }
   __syncthreads();
@@ -183,7 +173,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
   int32_t* dst = (c->cur_buf ? a.idx0 : a.idx1) + begin;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* fw = a.flag_words;
-  if (a.peers.world > 1) {
+  if (a.peers.world > 1 && a.peers.mode == 0) {
     if (c->error) return;
     fw = comm_flag_words(a.peers.block[a.peers.rank], static_cast<int>(c->flag_seq & 1), a.peers.flags_stride);
   }
@@ -243,28 +233,43 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
     __syncthreads();
   }
 
-  // ---- SplitInner bookkeeping (one thread): serial_tree_learner.cpp:769-925, tree.h:543-585
-  if (blockIdx.x == 0 && tid == 0) {
+  // ---- SplitInner bookkeeping: serial_tree_learner.cpp:769-925, tree.h:543-585
+  // row-shard: the children's GLOBAL row counts decide smaller/larger and the min-data gates; block 0 all-gathers
+  // the local left/right counts first (DataParallelTreeLearner keeps global_data_count_in_leaf_ the same way,
+  // reference src/treelearner/data_parallel_tree_learner.cpp:254-262)
+  if (blockIdx.x != 0) return;
+  __shared__ double s_in[8];
+  __shared__ double s_out[kMaxRanks][8];
+  int g_left = total_left, g_right = n - total_left;
+  if (a.peers.world > 1 && a.peers.mode == 1) {
+    if (tid == 0) { s_in[0] = total_left; s_in[1] = n - total_left; for (int k = 2; k < 8; ++k) s_in[k] = 0; }
+    __syncthreads();
+    exchange_misc(a.peers, c, s_in, s_out);
+    g_left = 0; g_right = 0;
+    for (int r = 0; r < a.peers.world; ++r) { g_left += static_cast<int>(s_out[r][0]); g_right += static_cast<int>(s_out[r][1]); }
+  }
+  if (tid == 0) {
     const int leaf = c->cur_leaf;
     const int right = c->num_leaves;          // next_leaf_id
     Leaf& L = a.leaves[leaf];
     Leaf& R = a.leaves[right];
     const Cand s = L.best;
-    const int left_count = total_left, right_count = n - total_left;
+    const int left_count = g_left, right_count = g_right;          // global
+    const int lleft = total_left, lright = n - total_left;         // this rank's rows
     SplitRec& rec = a.splits[right - 1];
     rec.leaf = leaf; rec.feature = s.feature; rec.threshold = s.threshold; rec.default_left = s.default_left;
     rec.left_count = left_count; rec.right_count = right_count; rec.owner = s.owner; rec.pad = 0;
     rec.gain = s.gain; rec.lsg = s.lsg; rec.lsh = s.lsh; rec.lout = s.lout; rec.rsg = s.rsg; rec.rsh = s.rsh; rec.rout = s.rout;
 
     const int parent_slot = L.slot, parent_depth = L.depth, child_buf = 1 - L.buf;
-    R.begin = begin + left_count; R.count = right_count; R.buf = child_buf; R.depth = parent_depth + 1;
+    R.begin = begin + lleft; R.count = right_count; R.lcount = lright; R.buf = child_buf; R.depth = parent_depth + 1;
     R.sum_g = s.rsg; R.sum_h = s.rsh; R.output = s.rout;
     R.best.gain = -INFINITY; R.best.feature = -1; R.best.real = 0x7fffffff; R.best.owner = 0;
-    L.count = left_count; L.buf = child_buf; L.depth = parent_depth + 1;
+    L.count = left_count; L.lcount = lleft; L.buf = child_buf; L.depth = parent_depth + 1;
     L.sum_g = s.lsg; L.sum_h = s.lsh; L.output = s.lout;
     L.best.gain = -INFINITY; L.best.feature = -1; L.best.real = 0x7fffffff; L.best.owner = 0;
     // smaller / larger (serial_tree_learner.cpp:858): the parent's pool slot becomes the larger child's,
-    // the smaller child gets the fresh slot `right` (one new slot per split, zeroed by the host sequence)
+    // the smaller child gets the fresh slot `right` (one new slot per split, zeroed at the start of the tree)
     int smaller, larger;
     if (left_count < right_count) { smaller = leaf; larger = right; } else { smaller = right; larger = leaf; }
     a.leaves[larger].slot = parent_slot;
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
     if (a.params.max_depth > 0 && parent_depth + 1 >= a.params.max_depth) do_find = 0;
     if (right_count < a.params.min_data_in_leaf * 2 && left_count < a.params.min_data_in_leaf * 2) do_find = 0;
     c->do_find = do_find;
+    if (c->error) c->cur_valid = 0;
   }
 }
 
@@ -314,6 +320,7 @@ struct PrepArgs {
   Params params;
   int32_t max_leaves;
   int32_t num_partials;
+  CommPeers peers;
 };
 
 constexpr int kPrepThreads = 256;
@@ -369,19 +376,43 @@ __device__ __forceinline__ double pow2_scale(double bound) {
   return ldexp(1.0, k);
 }
 
-__global__ void k_root_init(const PrepArgs a) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double sg = 0.0, sh = 0.0; float mg = 0.f, mh = 0.f;
-  for (int b = 0; b < a.num_partials; ++b) { sg += a.partials[b].g; sh += a.partials[b].h; mg = fmaxf(mg, a.partials[b].gmax); mh = fmaxf(mh, a.partials[b].hmax); }
-  const int n_root = a.bag ? a.bag_count : a.num_data;
+__global__ void __launch_bounds__(32) k_root_init(const PrepArgs a) {
+  __shared__ double s_in[8];
+  __shared__ double s_out[kMaxRanks][8];
+  const int tid = threadIdx.x;
+  const bool rows = a.peers.world > 1 && a.peers.mode == 1;
+  if (tid == 0) {
+    double sg = 0.0, sh = 0.0; float mg = 0.f, mh = 0.f;
+    for (int b = 0; b < a.num_partials; ++b) { sg += a.partials[b].g; sh += a.partials[b].h; mg = fmaxf(mg, a.partials[b].gmax); mh = fmaxf(mh, a.partials[b].hmax); }
+    s_in[0] = sg; s_in[1] = sh; s_in[2] = mg; s_in[3] = mh; s_in[4] = a.bag ? a.bag_count : a.num_data;
+    s_in[5] = s_in[6] = s_in[7] = 0;
+  }
+  __syncthreads();
+  if (rows) {
+    // row-shard: LeafSplits::Init sums are global (cuda_leaf_splits.cu:337-340 all-reduces them with NCCL;
+    // here: all-gather over peer memory + a fixed-order sum => bitwise identical on every rank)
+    exchange_misc(a.peers, a.ctl, s_in, s_out);
+  }
+  if (tid != 0) return;
+  double sg = s_in[0], sh = s_in[1]; float mg = static_cast<float>(s_in[2]), mh = static_cast<float>(s_in[3]);
+  const int n_local = static_cast<int>(s_in[4]);
+  int n_root = n_local;
+  if (rows) {
+    sg = 0; sh = 0; mg = 0; mh = 0; n_root = 0;
+    for (int r = 0; r < a.peers.world; ++r) {
+      sg += s_out[r][0]; sh += s_out[r][1];
+      mg = fmaxf(mg, static_cast<float>(s_out[r][2])); mh = fmaxf(mh, static_cast<float>(s_out[r][3]));
+      n_root += static_cast<int>(s_out[r][4]);
+    }
+  }
   for (int i = 0; i < a.max_leaves; ++i) {
     Leaf& L = a.leaves[i];
-    L.begin = 0; L.count = 0; L.buf = 0; L.depth = 0; L.slot = 0; L.pad = 0;
+    L.begin = 0; L.count = 0; L.buf = 0; L.depth = 0; L.slot = 0; L.lcount = 0;
     L.sum_g = 0; L.sum_h = 0; L.output = 0;
     L.best.gain = -INFINITY; L.best.feature = -1; L.best.real = 0x7fffffff; L.best.owner = 0;
   }
   Leaf& R = a.leaves[0];
-  R.count = n_root; R.sum_g = sg; R.sum_h = sh;
+  R.count = n_root; R.lcount = n_local; R.sum_g = sg; R.sum_h = sh;
   // root output (serial_tree_learner.cpp:207-211): L1 + max_delta_step, no smoothing
   {
     double ret = -sg;
@@ -391,7 +422,7 @@ __global__ void k_root_init(const PrepArgs a) {
     R.output = ret;
   }
   Ctl* c = a.ctl;
-  c->cur_valid = 1; c->error = 0; c->cur_owner = 0; c->part_blocks_done = 0; c->cur_leaf = 0; c->cur_begin = 0; c->cur_count = n_root; c->cur_buf = 0;
+  c->cur_valid = c->error ? 0 : 1; c->cur_owner = 0; c->part_blocks_done = 0; c->cur_leaf = 0; c->cur_begin = 0; c->cur_count = n_local; c->cur_buf = 0;
   c->smaller = 0; c->larger = -1; c->do_find = 1; c->num_leaves = 1;
   // BeforeFindBestSplit at the root: too few rows to ever split
   if (n_root < a.params.min_data_in_leaf * 2) c->do_find = 0;
@@ -399,6 +430,19 @@ __global__ void k_root_init(const PrepArgs a) {
   c->h_scale = pow2_scale(static_cast<double>(n_root) * mh);
   c->g_inv = 1.0 / c->g_scale; c->h_inv = 1.0 / c->h_scale;
   c->root_sum_g = sg; c->root_sum_h = sh; c->root_count = n_root; c->root_identity = a.bag ? 0 : 1;
+}
+
+// row-shard: tell every peer that this rank's local histogram for the current iteration is complete
+// (launched right after k_hist: stream order guarantees the REDs have been performed)
+__global__ void __launch_bounds__(32) k_hist_signal(const CommPeers peers, Ctl* c) {
+  if (!c->cur_valid || !c->do_find) return;
+  const unsigned long long seq = c->hist_seq + 1;
+  if (threadIdx.x < peers.world) {
+    __threadfence_system();
+    st_release_sys(&peers.block[threadIdx.x]->hist_seq[peers.rank], seq);
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) c->hist_seq = seq;
 }
 
 // AddPredictionToScore (serial_tree_learner.h:100-115): one grid row per leaf
@@ -414,14 +458,14 @@ __global__ void __launch_bounds__(256) k_add_score(const ScoreArgs a) {
   const Leaf& L = a.leaves[blockIdx.y];
   const int32_t* idx = (L.buf ? a.idx1 : a.idx0) + L.begin;
   const double v = a.leaf_value[blockIdx.y];
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < L.count; i += gridDim.x * 256) a.score[idx[i]] += v;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < L.lcount; i += gridDim.x * 256) a.score[idx[i]] += v;
 }
 
 // row -> leaf id of the final partition (one grid row per leaf)
 __global__ void __launch_bounds__(256) k_leaf_index(const Leaf* leaves, const int32_t* idx0, const int32_t* idx1, int32_t* row_leaf) {
   const Leaf& L = leaves[blockIdx.y];
   const int32_t* idx = (L.buf ? idx1 : idx0) + L.begin;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < L.count; i += gridDim.x * 256) row_leaf[idx[i]] = blockIdx.y;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < L.lcount; i += gridDim.x * 256) row_leaf[idx[i]] = blockIdx.y;
 }
 
 // L2 objective gradients (regression_objective.hpp:127-142, unweighted): g = score - label, h = 1

@@ -18,6 +18,7 @@
 // rule is applied explicitly: a candidate whose just-accumulated bin is empty is a duplicate of the
 // previous candidate and is skipped.  With the int64 pool an empty bin is exactly (0,0).
 #pragma once
+#include "comm.cuh"
 #include "types.cuh"
 
 namespace b200 {
@@ -254,61 +255,96 @@ struct ScanArgs {
   int32_t num_features;
   Params params;
   const Leaf* leaves;
-  const Ctl* ctl;
+  Ctl* ctl;
   long long* pool;
   int64_t slot_stride;
   const uint8_t* splittable;        // [slot][num_features] FeatureHistogram::is_splittable_ (read-only here)
   uint8_t* splittable_new;          // [2][num_features]: 0/1 = new flag of (smaller, larger), 2 = leave unchanged
   Cand* cand;                       // [2][num_features]: smaller, larger
-  BlockBest* block_best;            // [2][gridDim.x]
+  BlockBest* block_best;            // [2][scan_blocks]
+  CommPeers peers;                  // row-shard: whose pools to sum, which feature slice is mine
 };
 
 constexpr int kScanWarps = 8;
 
-// grid = (ceil(F/8), 2): blockIdx.y = 0 scans the smaller child, 1 the larger child (= parent - smaller).
-// One warp per (feature, child); the two warps of a feature are independent: the larger-child warp re-derives
-// the smaller child's fixed slice itself, so nothing is exchanged between them.
-__global__ void __launch_bounds__(kScanWarps * 32, 1) k_scan(const ScanArgs a) {
-  const Ctl* c = a.ctl;
-  if (!c->cur_valid || !c->do_find) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int which = blockIdx.y;
-  const int f = blockIdx.x * kScanWarps + warp;
-  const int F = a.num_features;
-  const int smaller = c->smaller, larger = c->larger;
-  __shared__ double s_gain[kScanWarps];
-  __shared__ int s_real[kScanWarps], s_feat[kScanWarps];
-
-  Cand out;                       // this warp's candidate (lane-uniform)
+__device__ __forceinline__ Cand cand_none() {
+  Cand out;
   out.gain = -INFINITY; out.feature = -1; out.threshold = 0; out.default_left = 1;
   out.lsg = out.lsh = out.lout = out.rsg = out.rsh = out.rout = 0.0; out.left_count = out.right_count = 0; out.pad = 0;
   out.real = 0x7fffffff; out.owner = 0;
-  int new_flag = 2;
+  return out;
+}
 
-  const bool active = f < F && !(which == 1 && larger < 0);
-  if (active) {
+// Single GPU / feature-shard: grid = (ceil(F/8), 2); blockIdx.y = 0 scans the smaller child, 1 the larger child
+// (= parent - smaller).  One warp per (feature, child); the larger-child warp re-derives the smaller child's
+// fixed slice itself, so the two warps of a feature exchange nothing.
+// Row-shard: grid = (ceil(f_cnt/8), 1) over this rank's feature slice; one warp handles BOTH children, and the
+// smaller child's slice is first REDUCED over all ranks by reading every peer's pool slot through NVLink
+// (the reduce-scatter of DataParallelTreeLearner, data_parallel_tree_learner.cpp:283+, fused into the scan's
+// load phase; int64 fixed point => the sum is exact and order-independent).  The global slice is written back
+// into this rank's own pool so that later subtractions (parent - smaller) stay local.
+__global__ void __launch_bounds__(kScanWarps * 32, 1) k_scan(const ScanArgs a) {
+  Ctl* c = a.ctl;
+  if (!c->cur_valid || !c->do_find) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool rows = a.peers.world > 1 && a.peers.mode == 1;
+  const int f = (rows ? a.peers.f_lo : 0) + blockIdx.x * kScanWarps + warp;
+  const int f_end = rows ? a.peers.f_lo + a.peers.f_cnt : a.num_features;
+  const int F = a.num_features;
+  const int smaller = c->smaller, larger = c->larger;
+  __shared__ double s_gain[2][kScanWarps];
+  __shared__ int s_real[2][kScanWarps], s_feat[2][kScanWarps];
+  __shared__ int s_ok;
+
+  if (rows) {
+    // every peer's local histogram of this iteration must be complete before anyone sums it
+    if (threadIdx.x < a.peers.world) {
+      if (!wait_seq(&a.peers.block[a.peers.rank]->hist_seq[threadIdx.x], c->hist_seq)) c->error = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_ok = c->error ? 0 : 1;
+    __syncthreads();
+    if (!s_ok) return;
+  }
+
+  Cand out[2] = {cand_none(), cand_none()};
+  int new_flag[2] = {2, 2};
+  const int w_lo = rows ? 0 : blockIdx.y, w_hi = rows ? 2 : blockIdx.y + 1;     // which children this warp handles
+
+  if (f < f_end) {
     const Leaf& LS = a.leaves[smaller];
     bool used = (a.feature_used == nullptr) || a.feature_used[f];
     if (used && larger >= 0 && !a.splittable[static_cast<int64_t>(a.leaves[larger].slot) * F + f]) {
       // parent was not splittable on this feature (serial_tree_learner.cpp:397-402): both children inherit it
-      used = false; new_flag = (which == 0) ? 0 : 2;
+      used = false; new_flag[0] = 0;
     }
     if (used) {
       const FeatMeta m = a.feat[f];
       const GainCfg gc = make_gain_cfg(a.params);
       const double g_inv = c->g_inv, h_inv = c->h_inv;
       const int64_t slice = (static_cast<int64_t>(m.col) * kBinsPerColumn + m.lo) * 2;
-      long long* hs = a.pool + static_cast<int64_t>(LS.slot) * a.slot_stride + slice;
+      const int64_t soff = static_cast<int64_t>(LS.slot) * a.slot_stride + slice;
+      long long* hs = a.pool + soff;
 
-      // smaller child's slice + FixHistogram (exact integer arithmetic)
+      // smaller child's slice (row-shard: summed over every rank's local histogram)
       long long ig[8], ih[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int e = lane * 8 + k;
-        if (e < m.nslice) {
-          const longlong2 v = *reinterpret_cast<const longlong2*>(hs + 2 * e);
-          ig[k] = v.x; ih[k] = v.y;
-        } else { ig[k] = 0; ih[k] = 0; }
+      for (int k = 0; k < 8; ++k) { ig[k] = 0; ih[k] = 0; }
+      if (rows) {
+        for (int r = 0; r < a.peers.world; ++r) {
+          const long long* hp = a.peers.pool[r] + soff;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int e = lane * 8 + k;
+            if (e < m.nslice) { const longlong2 v = __ldcv(reinterpret_cast<const longlong2*>(hp + 2 * e)); ig[k] += v.x; ih[k] += v.y; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = lane * 8 + k;
+          if (e < m.nslice) { const longlong2 v = *reinterpret_cast<const longlong2*>(hs + 2 * e); ig[k] = v.x; ih[k] = v.y; }
+        }
       }
       if (m.mfb > 0) {
         // Dataset::FixHistogram: entry[mfb] = leaf total - sum(other entries); the stored mfb entry is ignored,
@@ -321,54 +357,70 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) k_scan(const ScanArgs a) {
         const long long tg = __double2ll_rn(LS.sum_g * c->g_scale) - og;
         const long long th = __double2ll_rn(LS.sum_h * c->h_scale) - oh;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (lane * 8 + k == m.mfb) {
-            ig[k] = tg; ih[k] = th;
-            if (which == 0) *reinterpret_cast<longlong2*>(hs + 2 * m.mfb) = make_longlong2(tg, th);
-          }
+        for (int k = 0; k < 8; ++k) { if (lane * 8 + k == m.mfb) { ig[k] = tg; ih[k] = th; } }
+      }
+      if (w_lo == 0) {
+        // keep the fixed (row-shard: global) slice: this leaf's slot is a future parent
+        if (rows) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { const int e = lane * 8 + k; if (e < m.nslice) *reinterpret_cast<longlong2*>(hs + 2 * e) = make_longlong2(ig[k], ih[k]); }
+        } else if (m.mfb > 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { if (lane * 8 + k == m.mfb) *reinterpret_cast<longlong2*>(hs + 2 * m.mfb) = make_longlong2(ig[k], ih[k]); }
         }
       }
       double g[8], h[8];
-      int splittable = 0;
-      if (which == 0) {
+      for (int which = w_lo; which < w_hi; ++which) {
+        int splittable = 0;
+        if (which == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { h[k] = static_cast<double>(ih[k]) * h_inv; g[k] = (ih[k] == 0) ? 0.0 : static_cast<double>(ig[k]) * g_inv; }
-        const double po = (c->num_leaves == 1)
-            ? leaf_output(GainCfg{1, 1, 0, a.params.l1, a.params.l2, a.params.max_delta_step, a.params.path_smooth}, LS.sum_g, LS.sum_h, LS.count, 0.0)
-            : LS.output;
-        out = find_best_threshold(g, h, lane, f, m, a.params, gc, LS.sum_g, LS.sum_h, LS.count, po, &splittable);
-      } else {
-        // larger child = parent - smaller (exact), written in place into the parent's slot
-        const Leaf& LL = a.leaves[larger];
-        long long* hl = a.pool + static_cast<int64_t>(LL.slot) * a.slot_stride + slice;
+          for (int k = 0; k < 8; ++k) { h[k] = static_cast<double>(ih[k]) * h_inv; g[k] = (ih[k] == 0) ? 0.0 : static_cast<double>(ig[k]) * g_inv; }
+          const double po = (c->num_leaves == 1)
+              ? leaf_output(GainCfg{1, 1, 0, a.params.l1, a.params.l2, a.params.max_delta_step, a.params.path_smooth}, LS.sum_g, LS.sum_h, LS.count, 0.0)
+              : LS.output;
+          out[0] = find_best_threshold(g, h, lane, f, m, a.params, gc, LS.sum_g, LS.sum_h, LS.count, po, &splittable);
+        } else {
+          if (larger < 0) continue;
+          // larger child = parent - smaller (exact), written in place into the parent's slot
+          const Leaf& LL = a.leaves[larger];
+          long long* hl = a.pool + static_cast<int64_t>(LL.slot) * a.slot_stride + slice;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int e = lane * 8 + k;
-          if (e < m.nslice) {
-            longlong2 v = *reinterpret_cast<const longlong2*>(hl + 2 * e);
-            v.x -= ig[k]; v.y -= ih[k];
-            *reinterpret_cast<longlong2*>(hl + 2 * e) = v;
-            h[k] = static_cast<double>(v.y) * h_inv;
-            g[k] = (v.y == 0) ? 0.0 : static_cast<double>(v.x) * g_inv;
-          } else { g[k] = 0.0; h[k] = 0.0; }
+          for (int k = 0; k < 8; ++k) {
+            const int e = lane * 8 + k;
+            if (e < m.nslice) {
+              longlong2 v = *reinterpret_cast<const longlong2*>(hl + 2 * e);
+              v.x -= ig[k]; v.y -= ih[k];
+              *reinterpret_cast<longlong2*>(hl + 2 * e) = v;
+              h[k] = static_cast<double>(v.y) * h_inv;
+              g[k] = (v.y == 0) ? 0.0 : static_cast<double>(v.x) * g_inv;
+            } else { g[k] = 0.0; h[k] = 0.0; }
+          }
+          out[1] = find_best_threshold(g, h, lane, f, m, a.params, gc, LL.sum_g, LL.sum_h, LL.count, LL.output, &splittable);
         }
-        out = find_best_threshold(g, h, lane, f, m, a.params, gc, LL.sum_g, LL.sum_h, LL.count, LL.output, &splittable);
+        new_flag[which] = splittable;
       }
-      new_flag = splittable;
     }
     if (lane == 0) {
-      a.cand[which * F + f] = out;
-      a.splittable_new[which * F + f] = static_cast<uint8_t>(new_flag);
+      for (int which = w_lo; which < w_hi; ++which) {
+        a.cand[which * F + f] = out[which];
+        a.splittable_new[which * F + f] = static_cast<uint8_t>(new_flag[which]);
+      }
     }
   }
   // block-level arg-max (gain, then smaller real feature index) so that k_select scans F/8 entries only
-  if (lane == 0) { s_gain[warp] = out.gain; s_real[warp] = out.feature < 0 ? 0x7fffffff : out.real; s_feat[warp] = out.feature; }
+  if (lane == 0) {
+    for (int which = w_lo; which < w_hi; ++which) {
+      s_gain[which][warp] = out[which].gain; s_real[which][warp] = out[which].feature < 0 ? 0x7fffffff : out[which].real;
+      s_feat[which][warp] = out[which].feature;
+    }
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 2 && static_cast<int>(threadIdx.x) >= w_lo && static_cast<int>(threadIdx.x) < w_hi) {
+    const int which = threadIdx.x;
     BlockBest bb; bb.gain = -INFINITY; bb.real = 0x7fffffff; bb.feature = -1;
     for (int w = 0; w < kScanWarps; ++w) {
-      if (s_feat[w] < 0) continue;
-      if (s_gain[w] > bb.gain || (s_gain[w] == bb.gain && s_real[w] < bb.real)) { bb.gain = s_gain[w]; bb.real = s_real[w]; bb.feature = s_feat[w]; }
+      if (s_feat[which][w] < 0) continue;
+      if (s_gain[which][w] > bb.gain || (s_gain[which][w] == bb.gain && s_real[which][w] < bb.real)) { bb.gain = s_gain[which][w]; bb.real = s_real[which][w]; bb.feature = s_feat[which][w]; }
     }
     a.block_best[which * gridDim.x + blockIdx.x] = bb;
   }
@@ -391,14 +443,6 @@ struct SelectArgs {
   CommPeers peers;              // world == 1: no exchange
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 // payload written by a peer GPU: read it around L1 (the acquire on the sequence word orders it)
 __device__ __forceinline__ Cand load_cand_sys(const Cand* p) {
   static_assert(sizeof(Cand) % 8 == 0, "Cand must be a multiple of 8 bytes");
@@ -409,7 +453,6 @@ __device__ __forceinline__ Cand load_cand_sys(const Cand* p) {
   for (int i = 0; i < static_cast<int>(sizeof(Cand) / 8); ++i) d[i] = __ldcv(s + i);
   return out;
 }
-constexpr long long kWatchdogCycles = 20000000000ll;   // ~10 s: a missing peer becomes an error, not a hang
 
 __device__ __forceinline__ bool cand_better(double ga, int fa_real, double gb, int fb_real) {
   if (ga != gb) return ga > gb;
@@ -453,7 +496,9 @@ __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
       const int leaf = which == 0 ? smaller : larger;
       if (leaf < 0) continue;
       uint8_t* dst = a.splittable + static_cast<int64_t>(a.leaves[leaf].slot) * F;
-      for (int f = tid - 64; f < F; f += 192) { const uint8_t v = a.splittable_new[which * F + f]; if (v != 2) dst[f] = v; }
+      const bool rows = a.peers.world > 1 && a.peers.mode == 1;       // row-shard: only my feature slice was scanned
+      const int f0 = rows ? a.peers.f_lo : 0, f1 = rows ? a.peers.f_lo + a.peers.f_cnt : F;
+      for (int f = f0 + tid - 64; f < f1; f += 192) { const uint8_t v = a.splittable_new[which * F + f]; if (v != 2) dst[f] = v; }
     }
   }
   __syncthreads();
@@ -476,10 +521,7 @@ __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
     __syncthreads();
     if (tid < W) {
       CommBlock* mine = a.peers.block[me];
-      const long long t0 = clock64();
-      while (ld_acquire_sys(&mine->mail_seq[par][tid]) != seq) {
-        if (clock64() - t0 > kWatchdogCycles) { c->error = 1; break; }
-      }
+      if (!wait_seq(&mine->mail_seq[par][tid], seq)) c->error = 1;
     }
     __syncthreads();
     if (tid < 2) {
@@ -524,10 +566,10 @@ __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
       if (L.best.gain <= 0.0 || L.best.feature < 0 || c->num_leaves >= a.max_leaves) {
         c->cur_valid = 0;
       } else {
-        c->cur_leaf = best_leaf; c->cur_begin = L.begin; c->cur_count = L.count; c->cur_buf = L.buf;
+        c->cur_leaf = best_leaf; c->cur_begin = L.begin; c->cur_count = L.lcount; c->cur_buf = L.buf;
         c->cur_feature = L.best.feature; c->cur_threshold = L.best.threshold; c->cur_default_left = L.best.default_left;
-        c->cur_owner = L.best.owner;
-        if (L.best.owner == a.peers.rank) c->cur_meta = a.feat[L.best.feature];   // only the owner holds the column
+        c->cur_owner = a.peers.mode == 1 ? a.peers.rank : L.best.owner;   // row-shard: every rank holds every column
+        if (c->cur_owner == a.peers.rank) c->cur_meta = a.feat[L.best.feature];   // only the owner holds the column
         c->part_blocks_done = 0;
         c->flag_seq += 1;          // sequence number of the flag push that applies this split
       }

@@ -50,7 +50,7 @@ struct Leaf {
   int32_t buf;                 // which of the two ping-pong index buffers holds the segment
   int32_t depth;
   int32_t slot;                // histogram pool slot
-  int32_t pad;
+  int32_t lcount;              // rows of this leaf held by THIS rank (== count except in row-shard mode)
   double sum_g, sum_h, output; // leaf_splits.hpp: sum_gradients_, sum_hessians_, weight_
   Cand best;                   // best_split_per_leaf_[leaf]
 };
@@ -79,6 +79,8 @@ struct Ctl {
   unsigned long long flag_seq; // number of flag pushes done so far
   uint32_t part_blocks_done;   // last-block detection in k_part_flags
   uint32_t pad2;
+  unsigned long long hist_seq; // row-shard: number of "my local histogram is complete" signals sent
+  unsigned long long misc_seq; // row-shard: number of small all-gathers (root sums, left counts) done
 };
 
 // One applied split, copied back to the host once per tree (mirrors LGBMB200_Split)
@@ -91,17 +93,25 @@ struct SplitRec {
 struct PartialSum { double g, h; float gmax, hmax; };
 
 // ---- feature-shard exchange over NVLink peer memory (one CommBlock per rank, IPC-mapped by every peer)
-constexpr int kMaxRanks = 16;
+constexpr int kMaxRanks = 8;
 struct CommBlock {
   Cand mail[2][kMaxRanks][2];                 // [parity][source rank][smaller, larger] best candidates
   unsigned long long mail_seq[2][kMaxRanks];  // written by the source rank after its payload
   unsigned long long flags_seq[2];            // written by the split's owner after pushing the go-left flags
   unsigned long long pad[6];
+  // row-shard mode
+  unsigned long long hist_seq[kMaxRanks];     // hist_seq[r]: rank r's local histogram #seq is complete
+  double misc[2][kMaxRanks][8];               // small all-gather payloads (root sums / left counts)
+  unsigned long long misc_seq[2][kMaxRanks];
   // followed by: uint32_t flag_words[2][ceil(num_data/32)] (bit-packed go-left flags)
 };
 struct CommPeers {
   CommBlock* block[kMaxRanks];                // block[r] = rank r's CommBlock (own entry = local pointer)
   int32_t rank, world;
+  int32_t mode;                               // 0 = feature-shard (all rows x column slice), 1 = row-shard (row slice x all columns)
+  int32_t f_lo, f_cnt;                        // row-shard: the feature slice this rank reduces and scans
+  int32_t pad;
+  long long* pool[kMaxRanks];                 // row-shard: every rank's histogram pool (peer-mapped)
   int64_t flags_stride;                       // bytes between the two flag-word buffers
 };
 __host__ __device__ inline uint32_t* comm_flag_words(CommBlock* b, int parity, int64_t stride) {

@@ -66,3 +66,22 @@ def make_sharded_learner(shard_layout: Layout, config: Config, rank: int, world:
         counts = [int(x) for x in gather(str(shard_layout.num_features).encode(), rank, world)]
         L.comm_connect(rank, world, b"".join(handles), feature_offsets(counts))
     return L
+
+
+def shard_rows(num_data: int, world: int) -> list[tuple[int, int]]:
+    """[row_lo, row_hi) per rank: contiguous blocks of ceil(N/world) rows, the reference's own rule
+    (src/boosting/cuda/nccl_gbdt_component.hpp:32-44)."""
+    per = (num_data + world - 1) // world
+    return [(min(num_data, r * per), min(num_data, (r + 1) * per)) for r in range(world)]
+
+
+def make_row_sharded_learner(shard_layout: Layout, config: Config, rank: int, world: int, gather=gather_bytes) -> B200TreeLearner:
+    """shard_layout: this rank's ROW slice (all columns).  Train() takes the gradients of those rows only and
+    grows the same tree on every rank; leaf_count / split counts are global."""
+    L = B200TreeLearner(config)
+    L.init(shard_layout, is_constant_hessian=False)
+    if world > 1:
+        comm = gather(L.comm_export(), rank, world)
+        pool = gather(L.comm_export_pool(), rank, world)
+        L.comm_connect_rows(rank, world, b"".join(comm), b"".join(pool))
+    return L

@@ -325,6 +325,17 @@ class B200TreeLearner:
         hb = (C.c_uint8 * len(all_handles)).from_buffer_copy(all_handles)
         check(lib().LGBMB200_LearnerCommConnect(self.handle, C.c_int32(rank), C.c_int32(world), hb, _p(off)))
 
+    def comm_export_pool(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        check(lib().LGBMB200_LearnerCommExportPool(self.handle, buf))
+        return bytes(buf)
+
+    def comm_connect_rows(self, rank: int, world: int, comm_handles: bytes, pool_handles: bytes) -> None:
+        assert len(comm_handles) == 64 * world == len(pool_handles)
+        a = (C.c_uint8 * len(comm_handles)).from_buffer_copy(comm_handles)
+        b = (C.c_uint8 * len(pool_handles)).from_buffer_copy(pool_handles)
+        check(lib().LGBMB200_LearnerCommConnectRows(self.handle, C.c_int32(rank), C.c_int32(world), a, b))
+
     def get_leaf_index(self) -> np.ndarray:
         out = np.empty(self.layout.num_data, np.int32)
         check(lib().LGBMB200_LearnerGetLeafIndex(self.handle, _p(out)))

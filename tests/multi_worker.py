@@ -39,16 +39,27 @@ def main():
     lo, hi = D.shard_columns(f, world)[rank]
     shard = full.column_slice(lo, hi) if hi > lo else D.empty_shard(n, rank)
     cfg = lgb.Config(num_leaves=leaves, gpu_device_id=int(os.environ.get("LOCAL_RANK", rank)))
-    L = D.make_sharded_learner(shard, cfg, rank, world)
+    if mode == "rows":
+        r0, r1 = D.shard_rows(n, world)[rank]
+        shard = lgb.Layout.identity(bins[r0:r1])
+        L = D.make_row_sharded_learner(shard, cfg, rank, world)
+        gl, hl = g[r0:r1], h[r0:r1]
+    else:
+        L = D.make_sharded_learner(shard, cfg, rank, world)
+        gl, hl = g, h
     trees = []
     for it in range(3):
-        t = L.train(g * (1 + 0.1 * it), h)
+        t = L.train(gl * (1 + 0.1 * it), hl)
         trees.append(t)
     lb, lc, idx = L.get_partition(trees[-1].num_leaves)
+    if mode == "rows":
+        # local partition: every local row in exactly one leaf; report per-leaf local counts for a global check
+        assert sorted(idx[idx >= 0].tolist()) == list(range(len(gl)))
     out = dict(rank=rank, trees=[dict(n=t.num_leaves, feature=t.splits["feature"].tolist(), leaf=t.splits["leaf"].tolist(),
                                       threshold=t.splits["threshold"].tolist(), gain=t.splits["gain"].tolist(),
                                       leaf_value=t.leaf_value.tolist(), leaf_count=t.leaf_count.tolist()) for t in trees],
-               part_hash=int(np.bitwise_xor.reduce(idx.astype(np.int64) * (np.arange(len(idx)) + 1))))
+               part_hash=int(np.bitwise_xor.reduce(idx.astype(np.int64) * (np.arange(len(idx)) + 1))),
+               local_leaf_count=lc.tolist())
     if rank == 0:
         # single-GPU learner on the full matrix as the reference for the sharded result
         S = lgb.B200TreeLearner(cfg)

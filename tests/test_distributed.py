@@ -80,3 +80,28 @@ def test_feature_shard_world2_matches_single_gpu(n, f, leaves):
         assert ts["threshold"] == tm["threshold"] and ts["leaf_count"] == tm["leaf_count"]
         np.testing.assert_allclose(ts["gain"], tm["gain"], rtol=1e-5)
         np.testing.assert_allclose(ts["leaf_value"], tm["leaf_value"], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,f,leaves", [(30000, 28, 31), (20001, 40, 15)])
+def test_row_shard_world2_matches_single_gpu(n, f, leaves):
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    outs = launch(2, ["rows", n, f, leaves])
+    a, b = outs
+    for ta, tb in zip(a["trees"], b["trees"]):
+        assert ta == tb                      # identical decisions and identical (global) values on every rank
+    # local leaf counts add up to the global leaf counts of the last tree
+    glob = a["trees"][-1]["leaf_count"]
+    assert [x + y for x, y in zip(a["local_leaf_count"], b["local_leaf_count"])] == glob
+    for ts, tm in zip(a["single"], a["trees"]):
+        assert ts["n"] == tm["n"] and ts["feature"] == tm["feature"] and ts["leaf"] == tm["leaf"]
+        assert ts["threshold"] == tm["threshold"] and ts["leaf_count"] == tm["leaf_count"]
+        np.testing.assert_allclose(ts["gain"], tm["gain"], rtol=1e-5)
+        np.testing.assert_allclose(ts["leaf_value"], tm["leaf_value"], rtol=1e-5, atol=1e-9)
+
+
+def test_shard_rows_contract():
+    from lightgbm_b200.distributed import shard_rows
+    assert shard_rows(10, 3) == [(0, 4), (4, 8), (8, 10)]
+    assert shard_rows(11_000_000, 8)[-1] == (9_625_000, 11_000_000)
