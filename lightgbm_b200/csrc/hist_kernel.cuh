@@ -229,17 +229,29 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a) {
       const float2* sgh = reinterpret_cast<const float2*>(sb + kStageBinBytes);
       if (cnt == kStageRows) {
         constexpr int K = kHistBatch;
-        // fully unrolled: the stage reads are plain loads (free to be hoisted above the previous batch's
-        // histogram stores, which are asm volatile and ordered among themselves)
+        // software pipeline (measured: 5 % faster than letting ptxas hoist the stage reads): the next batch's bins
+        // and (g,h) are fetched from the stage BEFORE this batch's histogram stores are issued
+        uint32_t nb[K]; float2 nq[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) nb[i] = sbin[i * 32];
+#pragma unroll
+        for (int i = 0; i < K; i += 2) {
+          const float4 t = *reinterpret_cast<const float4*>(sgh + i);
+          nq[i] = make_float2(t.x, t.y); nq[i + 1] = make_float2(t.z, t.w);
+        }
 #pragma unroll
         for (int r = 0; r < kStageRows; r += K) {
           uint32_t cb[K]; float2 cq[K];
 #pragma unroll
-          for (int i = 0; i < K; ++i) cb[i] = sbin[(r + i) * 32];
+          for (int i = 0; i < K; ++i) { cb[i] = nb[i]; cq[i] = nq[i]; }
+          if (r + K < kStageRows) {
 #pragma unroll
-          for (int i = 0; i < K; i += 2) {
-            const float4 t = *reinterpret_cast<const float4*>(sgh + r + i);
-            cq[i] = make_float2(t.x, t.y); cq[i + 1] = make_float2(t.z, t.w);
+            for (int i = 0; i < K; ++i) nb[i] = sbin[(r + K + i) * 32];
+#pragma unroll
+            for (int i = 0; i < K; i += 2) {
+              const float4 t = *reinterpret_cast<const float4*>(sgh + r + K + i);
+              nq[i] = make_float2(t.x, t.y); nq[i + 1] = make_float2(t.z, t.w);
+            }
           }
           rmw_batch<K>(hbase, cb, cq);
         }
