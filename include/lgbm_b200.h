@@ -52,7 +52,8 @@ typedef struct {
   double  path_smooth;
   int32_t use_cuda_graph;           /* 1: replay the whole per-tree launch sequence as one CUDA graph */
   int32_t reserved;                 /* bit 0: do NOT keep the column-major copy of the bin matrix used by the
-                                       partition kernels (saves num_data*num_columns bytes of HBM) */
+                                       partition kernels (saves num_data*num_columns bytes of HBM);
+                                       bit 1: do NOT stage contiguous (root) histogram passes with TMA tile copies */
 } LGBMB200_Config;
 
 /*

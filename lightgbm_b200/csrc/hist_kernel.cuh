@@ -26,6 +26,8 @@
 //     leaf's slot of the histogram pool with RED.ADD.64.  Integer adds are associative, so the global
 //     histogram does not depend on the order in which warps flush, and parent - child is exact.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "types.cuh"
 
 namespace b200 {
@@ -54,6 +56,7 @@ struct HistArgs {
   int64_t slot_stride;            // int64 elements per slot
   int32_t num_colgroups;          // ceil(num_columns / 32)
   int32_t min_rows_per_item;      // do not split a column group over more warps than n / this
+  int32_t use_tma;                // 1: contiguous (root, un-bagged) stages are staged by TMA tile copies
   // explicit mode (stand-alone ConstructHistogram hook): explicit_n >= 0
   int32_t explicit_n;
   int32_t explicit_slot;
@@ -124,6 +127,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   }
 }
 
+// ---- TMA (bulk async copies, completion by mbarrier complete_tx) ---------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(bytes) : "memory");
+}
+// 2-D tile [32 rows x 32 columns] of the row-major bin matrix -> shared memory (UTMALDG)
+__device__ __forceinline__ void tma_load_tile_2d(void* smem_dst, const CUtensorMap* tmap, int col, int row, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(tmap), "r"(col), "r"(row),
+                 "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))) : "memory");
+}
+// contiguous bytes -> shared memory (UBLKCP); size multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc), "r"(bytes),
+                 "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))) : "memory");
+}
+
 // Work decomposition shared by the producer and the consumer warp of a pair.
 struct HistWork {
   int n, begin, slot;
@@ -153,7 +173,7 @@ __device__ __forceinline__ bool hist_work_setup(const HistArgs& a, int pair, His
   return true;
 }
 
-__global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a) {
+__global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_producer = warp >= kHistWarps;
@@ -184,6 +204,21 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a) {
       const int half = (lane & 1) * 16;
       const int32_t* ip = w.idx ? w.idx + w.begin : nullptr;
       for (int p0 = r0; p0 < r1; p0 += kStageRows) {
+        if (a.use_tma && ip == nullptr && p0 + kStageRows <= r1) {
+          // contiguous rows (root of an un-bagged tree): ONE 2-D TMA tile (32 rows x 32 columns of the row-major
+          // matrix) + one bulk copy of the 32 (g,h) pairs per stage; both complete on the stage's mbarrier
+          mbar_wait(empty + slot, phase ^ 1);
+          unsigned char* sb = ring + slot * kStageBytes;
+          if (lane == 0) {
+            mbar_arrive_expect_tx(full + slot, kStageBytes);
+            tma_load_tile_2d(sb, &tmap, cg * kColGroup, p0, full + slot);
+            tma_load_1d(sb + kStageBinBytes, a.gh + p0, kStageRows * 8, full + slot);
+          } else {
+            mbar_arrive(full + slot);
+          }
+          if (++slot == kStages) { slot = 0; phase ^= 1; }
+          continue;
+        }
         // row ids: lane -> (g,h) of row p0+lane; lane pair -> 32-byte bin segment of rows p0+lane/2 and +16
         const int pa = p0 + (lane >> 1), pb = pa + 16, pg = p0 + lane;
         int ra = -1, rb = -1, rg = -1;

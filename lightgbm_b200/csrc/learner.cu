@@ -140,6 +140,7 @@ class Learner {
     have_feature_mask_ = false;
     bag_count_ = -1;
     CUDA_CHECK(cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+    BuildTensorMap();
     inited_ = true;
     AllocTreeState();
     CUDA_CHECK(cudaDeviceSynchronize());
@@ -306,7 +307,6 @@ class Learner {
       CUDA_CHECK(cudaMemcpyAsync(hess_stage_.p, hess, sizeof(float) * N_, cudaMemcpyHostToDevice, stream_));
       g = grad_stage_.p; h = hess_stage_.p;
     }
-    const int32_t* bag_saved_count = nullptr; (void)bag_saved_count;
     // prep with "no bagging" semantics over all rows: packs gh and sets the fixed-point scales
     PrepArgs pa = MakePrepArgs(g, h);
     pa.bag = nullptr; pa.bag_count = 0;
@@ -326,7 +326,7 @@ class Learner {
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, stream_));
-    k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha);
+    k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha, tmap_);
     CUDA_CHECK(cudaEventRecord(e1, stream_));
     launches_ += 3;
     CUDA_CHECK(cudaGetLastError());
@@ -458,7 +458,32 @@ class Learner {
     ha.leaves = leaves_.p; ha.ctl = ctl_.p; ha.pool = reinterpret_cast<unsigned long long*>(pool_.p);
     ha.slot_stride = slot_stride_; ha.num_colgroups = Cpad_ / kColGroup; ha.min_rows_per_item = 2048;
     ha.explicit_n = -1; ha.explicit_slot = 0; ha.explicit_idx = nullptr;
+    ha.use_tma = have_tmap_ ? 1 : 0;
     return ha;
+  }
+
+  // 2-D tensor map over the row-major bin matrix {Cpad, N} with a {32 columns, 32 rows} box, for the TMA tile
+  // loads of contiguous (root) stages.  cuTensorMapEncodeTiled is fetched from the driver at run time, so the
+  // library keeps depending on libcudart only.  LGBMB200_Config.reserved bit 1 turns TMA staging off.
+  void BuildTensorMap() {
+    have_tmap_ = false;
+    std::memset(&tmap_, 0, sizeof(tmap_));
+    if (cfg_.reserved & 2) return;
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+        qres != cudaDriverEntryPointSuccess) { cudaGetLastError(); return; }
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(Cpad_), static_cast<cuuint64_t>(N_)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(pitch_)};
+    const cuuint32_t box[2] = {kColGroup, kStageRows};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = reinterpret_cast<EncodeTiled>(fn)(&tmap_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, bins_.p, gdim, gstride, box, estride,
+                                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    have_tmap_ = (r == CUDA_SUCCESS);
   }
 
   // The fixed per-tree launch sequence (see file header).
@@ -500,7 +525,7 @@ class Learner {
         launches_ += 2;
         if (it == NL - 1) break;   // the tree is full: no need to look for further splits
       }
-      k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha);
+      k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha, tmap_);
       Stamp(kProfHist);
       if (row_mode) { k_hist_signal<<<1, 32, 0, stream_>>>(peers_, ctl_.p); ++launches_; }
       k_scan<<<dim3(std::max(scan_blocks, 1), row_mode ? 1 : 2), kScanWarps * 32, 0, stream_>>>(sa);
@@ -603,6 +628,8 @@ class Learner {
   cudaEvent_t t0_ = nullptr, t1_ = nullptr;
   DevBuf<PartialSum> partials_;
   CommPeers peers_{};
+  CUtensorMap tmap_;
+  bool have_tmap_ = false;
   void* comm_local_ = nullptr;
   int64_t comm_stride_ = 0;
   std::vector<void*> comm_opened_;

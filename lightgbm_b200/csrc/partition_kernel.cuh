@@ -112,7 +112,10 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
     }
   }
   __shared__ int s_cnt[kPartThreads / 32];
-  if (lane == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  if (lane == 0) {
+    s_cnt[threadIdx.x >> 5] = cnt;
+    if (W > 1) __threadfence_system();      // this lane's peer stores are ordered before the block's publication
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     int t = 0;
@@ -151,7 +154,8 @@ __global__ void __launch_bounds__(kPartThreads) k_part_count(const PartArgs a) {
   int lo, hi;
   part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
   int cnt = 0;
-  for (int wi = (lo >> 5) + threadIdx.x; wi < ((hi + 31) >> 5); wi += kPartThreads) cnt += __popc(__ldcv(fw + wi));
+  // (empty blocks have lo == hi == n: they must not count the leaf's last, partial word again)
+  for (int wi = (lo >> 5) + threadIdx.x; lo < hi && wi < ((hi + 31) >> 5); wi += kPartThreads) cnt += __popc(__ldcv(fw + wi));
   __shared__ int s_cnt[kPartThreads / 32];
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);

@@ -38,7 +38,8 @@ def main():
     full = lgb.Layout.identity(bins)
     lo, hi = D.shard_columns(f, world)[rank]
     shard = full.column_slice(lo, hi) if hi > lo else D.empty_shard(n, rank)
-    cfg = lgb.Config(num_leaves=leaves, gpu_device_id=int(os.environ.get("LOCAL_RANK", rank)))
+    cfg = lgb.Config(num_leaves=leaves, gpu_device_id=int(os.environ.get("LOCAL_RANK", rank)),
+                     use_cuda_graph=not os.environ.get("NO_GRAPH"))
     if mode == "rows":
         r0, r1 = D.shard_rows(n, world)[rank]
         shard = lgb.Layout.identity(bins[r0:r1])
