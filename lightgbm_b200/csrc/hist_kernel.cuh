@@ -145,13 +145,16 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, un
 }
 
 // Work decomposition shared by the producer and the consumer warp of a pair.
+// Items are numbered column-group-major (item j -> column group j / splits, row part j % splits) and dealt to
+// warp slots in order, so the three consumer warps of a CTA normally work on consecutive row parts of the SAME
+// column group and can merge their private tables in shared memory before touching global memory.
 struct HistWork {
   int n, begin, slot;
   const int32_t* idx;
-  int CG, per, items, total_warps, gw;
+  int CG, splits, per, items, total_warps;
 };
 
-__device__ __forceinline__ bool hist_work_setup(const HistArgs& a, int pair, HistWork* w) {
+__device__ __forceinline__ bool hist_work_setup(const HistArgs& a, HistWork* w) {
   if (a.explicit_n >= 0) {
     w->n = a.explicit_n; w->begin = 0; w->slot = a.explicit_slot; w->idx = a.explicit_idx;
   } else {
@@ -164,13 +167,16 @@ __device__ __forceinline__ bool hist_work_setup(const HistArgs& a, int pair, His
   }
   if (w->n <= 0) return false;
   w->total_warps = gridDim.x * kHistWarps;
-  w->gw = pair * gridDim.x + blockIdx.x;                       // spread the first items over all SMs
   w->CG = a.num_colgroups;
   const int max_splits = max(1, w->total_warps / w->CG);
-  const int splits = min(max_splits, max(1, (w->n + a.min_rows_per_item - 1) / a.min_rows_per_item));
-  w->per = (((w->n + splits - 1) / splits) + 31) & ~31;
-  w->items = w->CG * splits;
+  w->splits = min(max_splits, max(1, (w->n + a.min_rows_per_item - 1) / a.min_rows_per_item));
+  w->per = (((w->n + w->splits - 1) / w->splits) + 31) & ~31;
+  w->items = w->CG * w->splits;
   return true;
+}
+
+__device__ __forceinline__ void consumer_bar_sync() {          // the 3 consumer warps only (named barrier 1)
+  asm volatile("bar.sync 1, %0;" ::"n"(kHistWarps * 32) : "memory");
 }
 
 __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, const __grid_constant__ CUtensorMap tmap) {
@@ -188,15 +194,17 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
   __syncthreads();
 
   HistWork w;
-  if (!hist_work_setup(a, pair, &w)) return;
+  if (!hist_work_setup(a, &w)) return;
   unsigned char* wbase = smem + pair * kWarpSmemBytes;
   unsigned char* ring = wbase + kWarpHistBytes;
 
   if (is_producer) {
     // ------------------------------------------------------------------ producer warp: stage rows
     int slot = 0; unsigned phase = 0;
-    for (int item = w.gw; item < w.items; item += w.total_warps) {
-      const int cg = item % w.CG, part = item / w.CG;
+    for (int base = blockIdx.x * kHistWarps; base < w.items; base += w.total_warps) {
+      const int item = base + pair;
+      if (item >= w.items) continue;
+      const int cg = item / w.splits, part = item % w.splits;
       const int r0 = part * w.per;
       const int r1 = min(w.n, r0 + w.per);
       if (r0 >= r1) continue;
@@ -240,13 +248,18 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
   // -------------------------------------------------------------------- consumer warp: accumulate
   float2* H = reinterpret_cast<float2*>(wbase) + lane;            // lane's column of the [bin][lane] table
   const unsigned hbase = static_cast<unsigned>(__cvta_generic_to_shared(H));   // + bin*256 = the lane's cell
+  const unsigned hbase0 = static_cast<unsigned>(__cvta_generic_to_shared(reinterpret_cast<float2*>(smem) + lane));
   const double gs = a.ctl->g_scale, hs = a.ctl->h_scale;
   int slot = 0; unsigned phase = 0;
-  for (int item = w.gw; item < w.items; item += w.total_warps) {
-    const int cg = item % w.CG, part = item / w.CG;
+  for (int base = blockIdx.x * kHistWarps; base < w.items; base += w.total_warps) {
+    const int item = base + pair;
+    // merge path: all three warps of the CTA hold items of the same column group (CTA-uniform condition)
+    const bool merge = (base + kHistWarps - 1 < w.items) && (base / w.splits == (base + kHistWarps - 1) / w.splits);
+    if (item >= w.items) continue;                                 // only possible when !merge
+    const int cg = item / w.splits, part = item % w.splits;
     const int r0 = part * w.per;
     const int r1 = min(w.n, r0 + w.per);
-    if (r0 >= r1) continue;
+    if (r0 >= r1 && !merge) continue;
 
     // zero the warp-private histogram (the producer is already filling the ring meanwhile)
     {
@@ -305,18 +318,37 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
       if (++slot == kStages) { slot = 0; phase ^= 1; }
     }
 
-    // flush: fp32 partial -> int64 fixed point, RED.ADD.64 into the leaf's pool slot
+    // flush: fp32 partials -> int64 fixed point, RED.ADD.64 into the leaf's pool slot.
     unsigned long long* dst = a.pool + static_cast<int64_t>(w.slot) * a.slot_stride +
                               (static_cast<int64_t>(cg) * kColGroup + lane) * (kBinsPerColumn * 2);
-#pragma unroll 4
-    for (int b = 0; b < kBinsPerColumn; ++b) {
-      const float2 v = lds64(hbase + (b << 8));
-      if (v.x != 0.f || v.y != 0.f) {
-        atomicAdd(dst + 2 * b, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v.x) * gs)));
-        atomicAdd(dst + 2 * b + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v.y) * hs)));
+    if (merge) {
+      // the CTA's three tables cover the same 32 columns: sum them in shared memory (fixed order 0,1,2 =>
+      // deterministic) and let each warp flush a third of the bins => 3x fewer global atomics
+      consumer_bar_sync();
+      const int b_lo = pair * 86, b_hi = min(kBinsPerColumn, b_lo + 86);
+#pragma unroll 2
+      for (int b = b_lo; b < b_hi; ++b) {
+        const float2 v0 = lds64(hbase0 + (b << 8));
+        const float2 v1 = lds64(hbase0 + kWarpSmemBytes + (b << 8));
+        const float2 v2 = lds64(hbase0 + 2 * kWarpSmemBytes + (b << 8));
+        const float gx = (v0.x + v1.x) + v2.x, hx = (v0.y + v1.y) + v2.y;
+        if (gx != 0.f || hx != 0.f) {
+          atomicAdd(dst + 2 * b, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(gx) * gs)));
+          atomicAdd(dst + 2 * b + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(hx) * hs)));
+        }
       }
+      consumer_bar_sync();            // the tables are free to be zeroed for the next item
+    } else {
+#pragma unroll 4
+      for (int b = 0; b < kBinsPerColumn; ++b) {
+        const float2 v = lds64(hbase + (b << 8));
+        if (v.x != 0.f || v.y != 0.f) {
+          atomicAdd(dst + 2 * b, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v.x) * gs)));
+          atomicAdd(dst + 2 * b + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v.y) * hs)));
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 

@@ -101,35 +101,48 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
       const unsigned word = __ballot_sync(0xffffffffu, left);
       if (lane == 0 && (i - lane) < hi) {
         const int wi = (i - lane) >> 5;
-        if (W > 1) {
-#pragma unroll
-          for (int r = 0; r < kMaxRanks; ++r) if (r < W) comm_flag_words(a.peers.block[r], par, a.peers.flags_stride)[wi] = word;
-        } else {
-          a.flag_words[wi] = word;
-        }
+        if (W > 1) comm_flag_words(a.peers.block[me], par, a.peers.flags_stride)[wi] = word;   // own buffer; k_part_push ships it
+        else a.flag_words[wi] = word;
         cnt += __popc(word);
       }
     }
   }
   __shared__ int s_cnt[kPartThreads / 32];
-  if (lane == 0) {
-    s_cnt[threadIdx.x >> 5] = cnt;
-    if (W > 1) __threadfence_system();      // this lane's peer stores are ordered before the block's publication
-  }
+  if (lane == 0) s_cnt[threadIdx.x >> 5] = cnt;
   __syncthreads();
   if (threadIdx.x == 0) {
     int t = 0;
 #pragma unroll
     for (int w = 0; w < kPartThreads / 32; ++w) t += s_cnt[w];
     a.block_left[blockIdx.x] = t;
-    if (W > 1) {
-      // last block publishes "flags of push #fseq are complete" to every rank
+  }
+}
+
+// feature-shard mode, owner only: ship the bit-packed flag words (n/8 bytes) from the owner's buffer into every
+// peer's buffer with coalesced 16-byte peer stores over NVLink, then publish the sequence number (last block).
+__global__ void __launch_bounds__(kPartThreads) k_part_push(const PartArgs a) {
+  Ctl* c = a.ctl;
+  if (!c->cur_valid) return;
+  const int W = a.peers.world, me = a.peers.rank;
+  if (c->cur_owner != me) return;
+  const unsigned long long fseq = c->flag_seq;
+  const int par = static_cast<int>(fseq & 1);
+  const int nvec = ((c->cur_count + 31) / 32 + 3) / 4;                 // uint4 chunks (buffers are 256-byte padded)
+  const uint4* src = reinterpret_cast<const uint4*>(comm_flag_words(a.peers.block[me], par, a.peers.flags_stride));
+  for (int i = blockIdx.x * kPartThreads + threadIdx.x; i < nvec; i += gridDim.x * kPartThreads) {
+    const uint4 v = src[i];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r) {
+      if (r < W && r != me) reinterpret_cast<uint4*>(comm_flag_words(a.peers.block[r], par, a.peers.flags_stride))[i] = v;
+    }
+  }
+  __threadfence_system();                // every thread orders its own peer stores
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&c->part_blocks_done, 1u);
+    if (done == gridDim.x - 1) {
       __threadfence_system();
-      const unsigned done = atomicAdd(&c->part_blocks_done, 1u);
-      if (done == gridDim.x - 1) {
-        __threadfence_system();
-        for (int r = 0; r < W; ++r) st_release_sys(&a.peers.block[r]->flags_seq[par], fseq);
-      }
+      for (int r = 0; r < W; ++r) st_release_sys(&a.peers.block[r]->flags_seq[par], fseq);
     }
   }
 }
