@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "C3"), choices=list(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override rows (debug only; makes the number INVALID)")
-    ap.add_argument("--ref-rows", type=int, default=1_000_000, help="row sample for the CPU reference arm")
+    ap.add_argument("--ref-rows", type=int, default=500_000, help="row sample for the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
