@@ -169,7 +169,15 @@ __device__ __forceinline__ bool hist_work_setup(const HistArgs& a, HistWork* w) 
   w->total_warps = gridDim.x * kHistWarps;
   w->CG = a.num_colgroups;
   const int max_splits = max(1, w->total_warps / w->CG);
-  w->splits = min(max_splits, max(1, (w->n + a.min_rows_per_item - 1) / a.min_rows_per_item));
+  // row parts per column group: balance the per-row work (~17 ns per row and warp) against the per-item fixed
+  // cost (zeroing + the merged flush, ~16K/3 global atomics per item at ~0.2 G atomics/us):
+  // t(s) = n/s * t_row + CG*s * t_item  =>  s* = sqrt(n * t_row / (CG * t_item)) ~ sqrt(0.7 n / CG)
+  int sp = static_cast<int>(sqrtf(0.7f * static_cast<float>(w->n) / static_cast<float>(w->CG)));
+  sp = min(max_splits, max(1, min(sp, (w->n + a.min_rows_per_item - 1) / a.min_rows_per_item)));
+  // whole CTAs per column group => every CTA can merge its tables (not when the warp count is the limit:
+  // there the rows per warp matter more than the flush)
+  if (sp >= kHistWarps && sp < max_splits) sp -= sp % kHistWarps;
+  w->splits = sp;
   w->per = (((w->n + w->splits - 1) / w->splits) + 31) & ~31;
   w->items = w->CG * w->splits;
   return true;

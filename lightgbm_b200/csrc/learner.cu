@@ -456,7 +456,7 @@ class Learner {
     HistArgs ha;
     ha.bins = bins_.p; ha.pitch = pitch_; ha.gh = gh_.p; ha.idx0 = idx0_.p; ha.idx1 = idx1_.p;
     ha.leaves = leaves_.p; ha.ctl = ctl_.p; ha.pool = reinterpret_cast<unsigned long long*>(pool_.p);
-    ha.slot_stride = slot_stride_; ha.num_colgroups = Cpad_ / kColGroup; ha.min_rows_per_item = 2048;
+    ha.slot_stride = slot_stride_; ha.num_colgroups = Cpad_ / kColGroup; ha.min_rows_per_item = 64;
     ha.explicit_n = -1; ha.explicit_slot = 0; ha.explicit_idx = nullptr;
     ha.use_tma = have_tmap_ ? 1 : 0;
     return ha;
