@@ -160,6 +160,9 @@ LGBMB200_EXPORT int LGBMB200_LearnerConstructHistogram(LGBMB200_LearnerHandle h,
  * (reference src/objective/regression_objective.hpp:127-142) and the number of kernels launched so far. */
 LGBMB200_EXPORT int LGBMB200_L2Gradients(LGBMB200_LearnerHandle h, const double* score_dev, const float* label_dev,
                                          float* grad_dev, float* hess_dev, int32_t n);
+/* Binary logloss gradients (reference src/objective/binary_objective.hpp:105-121, unweighted); labels in {0,1}. */
+LGBMB200_EXPORT int LGBMB200_BinaryGradients(LGBMB200_LearnerHandle h, const double* score_dev, const float* label_dev,
+                                             float* grad_dev, float* hess_dev, int32_t n, double sigmoid);
 LGBMB200_EXPORT int64_t LGBMB200_LearnerKernelLaunches(LGBMB200_LearnerHandle h);
 /* Sum of CUDA-event time spent in histogram-construction launches since the last reset (ms) and the
  * algorithmic bytes they covered; used by bench.py for the roofline of the dominant kernel. */

@@ -18,7 +18,7 @@ from .tree_learner import B200TreeLearner, Config, DeviceArray, Layout, Tree
 class B200Booster:
     def __init__(self, layout: Layout, label: np.ndarray, config: Config, learning_rate: float = 0.1,
                  boost_from_average: bool = True, device_resident: bool = True, learner: B200TreeLearner | None = None,
-                 pinned: bool = False):
+                 pinned: bool = False, objective: str = "regression", sigmoid: float = 1.0):
         if learner is None:
             learner = B200TreeLearner(config)
             learner.init(layout, is_constant_hessian=True)
@@ -28,8 +28,17 @@ class B200Booster:
         self.device_resident = device_resident
         self.label = np.ascontiguousarray(label, dtype=np.float32)
         self.trees: list[Tree] = []
-        # BoostFromAverage (gbdt.cpp:328-350, RegressionL2loss::BoostFromScore): mean label
-        self.init_score = float(np.mean(self.label, dtype=np.float64)) if boost_from_average else 0.0
+        assert objective in ("regression", "binary")
+        self.objective, self.sigmoid = objective, float(sigmoid)
+        # BoostFromAverage (gbdt.cpp:328-350): RegressionL2loss::BoostFromScore = mean label;
+        # BinaryLogloss::BoostFromScore = log(p/(1-p))/sigmoid (binary_objective.hpp:139-165)
+        if not boost_from_average:
+            self.init_score = 0.0
+        elif objective == "regression":
+            self.init_score = float(np.mean(self.label, dtype=np.float64))
+        else:
+            pavg = min(max(float(np.mean(self.label > 0, dtype=np.float64)), 1e-15), 1 - 1e-15)
+            self.init_score = float(np.log(pavg / (1 - pavg)) / self.sigmoid)
         score0 = np.full(self.n, self.init_score, dtype=np.float64)
         if device_resident:
             self.d_label = DeviceArray(self.n * 4).upload(self.label)
@@ -50,10 +59,19 @@ class B200Booster:
     def update(self) -> Tree:
         """One boosting iteration: gradients -> Train -> Shrinkage -> UpdateScore."""
         if self.device_resident:
-            self.learner.l2_gradients(self.d_score, self.d_label, self.d_grad, self.d_hess, self.n)
+            if self.objective == "regression":
+                self.learner.l2_gradients(self.d_score, self.d_label, self.d_grad, self.d_hess, self.n)
+            else:
+                self.learner.binary_gradients(self.d_score, self.d_label, self.d_grad, self.d_hess, self.n, self.sigmoid)
             tree = self.learner.train(self.d_grad, self.d_hess)
         else:
-            np.subtract(self.score, self.label, out=self.grad, casting="unsafe")   # g = score - label, h = 1
+            if self.objective == "regression":
+                np.subtract(self.score, self.label, out=self.grad, casting="unsafe")   # g = score - label, h = 1
+            else:
+                lab = np.where(self.label > 0, 1.0, -1.0)
+                resp = -lab * self.sigmoid / (1.0 + np.exp(lab * self.sigmoid * self.score))
+                self.grad[:] = resp
+                self.hess[:] = np.abs(resp) * (self.sigmoid - np.abs(resp))
             tree = self.learner.train(self.grad, self.hess)
         tree.shrinkage(self.lr)
         if tree.num_leaves > 1:
@@ -77,6 +95,12 @@ class B200Booster:
         if self.device_resident:
             return self.d_score.download(np.float64, self.n)
         return self.score
+
+    def logloss(self) -> float:
+        s = self.scores()
+        p = 1.0 / (1.0 + np.exp(-self.sigmoid * s))
+        y = self.label > 0
+        return float(-np.mean(np.where(y, np.log(np.maximum(p, 1e-15)), np.log(np.maximum(1 - p, 1e-15)))))
 
     def l2(self) -> float:
         s = self.scores()

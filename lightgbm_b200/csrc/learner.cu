@@ -406,6 +406,12 @@ class Learner {
     CUDA_CHECK(cudaGetLastError());
   }
 
+  void BinaryGradients(const double* score, const float* label, float* grad, float* hess, int n, double sigmoid) {
+    k_binary_gradients<<<num_sms_ * 4, 256, 0, stream_>>>(score, label, grad, hess, n, sigmoid);
+    ++launches_;
+    CUDA_CHECK(cudaGetLastError());
+  }
+
   void SetProfiling(int enable) {
     profiling_ = enable != 0;
     if (profiling_ && hist_events_.empty()) {
@@ -747,6 +753,13 @@ int LGBMB200_L2Gradients(LGBMB200_LearnerHandle h, const double* score_dev, cons
   API_BEGIN();
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->L2Gradients(score_dev, label_dev, grad_dev, hess_dev, n);
+  API_END();
+}
+int LGBMB200_BinaryGradients(LGBMB200_LearnerHandle h, const double* score_dev, const float* label_dev, float* grad_dev, float* hess_dev,
+                             int32_t n, double sigmoid) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->BinaryGradients(score_dev, label_dev, grad_dev, hess_dev, n, sigmoid);
   API_END();
 }
 int64_t LGBMB200_LearnerKernelLaunches(LGBMB200_LearnerHandle h) { return h ? static_cast<Learner*>(h)->launches() : 0; }

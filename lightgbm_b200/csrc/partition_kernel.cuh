@@ -493,4 +493,15 @@ __global__ void k_l2_gradients(const double* score, const float* label, float* g
   }
 }
 
+// Binary logloss gradients (binary_objective.hpp:105-121, unweighted, label_weights = 1): label in {0,1}
+__global__ void k_binary_gradients(const double* score, const float* label, float* grad, float* hess, int n, double sigmoid) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int lab = label[i] > 0.0f ? 1 : -1;
+    const double response = -lab * sigmoid / (1.0 + exp(lab * sigmoid * score[i]));
+    const double abs_response = fabs(response);
+    grad[i] = static_cast<float>(response);
+    hess[i] = static_cast<float>(abs_response * (sigmoid - abs_response));
+  }
+}
+
 }  // namespace b200

@@ -353,6 +353,10 @@ class B200TreeLearner:
         check(lib().LGBMB200_L2Gradients(self.handle, _ptr_of(score_dev)[0], _ptr_of(label_dev)[0],
                                          _ptr_of(grad_dev)[0], _ptr_of(hess_dev)[0], C.c_int32(n)))
 
+    def binary_gradients(self, score_dev, label_dev, grad_dev, hess_dev, n: int, sigmoid: float = 1.0) -> None:
+        check(lib().LGBMB200_BinaryGradients(self.handle, _ptr_of(score_dev)[0], _ptr_of(label_dev)[0],
+                                             _ptr_of(grad_dev)[0], _ptr_of(hess_dev)[0], C.c_int32(n), C.c_double(sigmoid)))
+
     def set_profiling(self, enable: bool) -> None:
         check(lib().LGBMB200_LearnerSetProfiling(self.handle, C.c_int32(1 if enable else 0)))
 

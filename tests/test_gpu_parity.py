@@ -213,3 +213,22 @@ def test_row_major_partition_path_matches_column_major(mods):
     b = lgb.B200TreeLearner(cfg); b.init(lay)
     tb = b.train(g, h)
     assert np.array_equal(ta.splits, tb.splits) and np.array_equal(ta.leaf_count, tb.leaf_count)
+
+
+def test_binary_objective_device_resident_equals_host_mode(mods):
+    """Binary logloss gradients on the device (binary_objective.hpp:105-121) vs the numpy host path."""
+    lgb, _ = mods
+    n, f = 30000, 12
+    bins, _, _, _ = synth_identity(n, f, seed=41)
+    rng = np.random.default_rng(3)
+    y = (rng.random(n) < 1 / (1 + np.exp(-((bins[:, 0] / 127.0 - 1) * 2 - (bins[:, 1] / 127.0 - 1))))).astype(np.float32)
+    lay = lgb.Layout.identity(bins)
+    cfg = lgb.Config(num_leaves=15)
+    a = lgb.B200Booster(lay, y, cfg, learning_rate=0.2, device_resident=True, objective="binary")
+    b = lgb.B200Booster(lay, y, cfg, learning_rate=0.2, device_resident=False, objective="binary")
+    l0 = a.logloss()
+    for _ in range(6):
+        ta, tb = a.update(), b.update()
+        assert np.array_equal(ta.splits[["leaf", "feature", "threshold"]], tb.splits[["leaf", "feature", "threshold"]])
+    np.testing.assert_allclose(a.scores(), b.scores(), rtol=1e-5, atol=1e-7)
+    assert a.logloss() < l0 * 0.9
