@@ -104,6 +104,21 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def effective_cores():
+    """Host threads this process can really use: min(affinity, cgroup quota)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -133,7 +148,7 @@ def run_reference(args, wl, rank, world):
         return None
     from oracle import refapi
     rows = min(wl["rows"], args.ref_rows)
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     bins = gen_bins(rows, wl["cols"], wl["seed"])
     y = gen_label(rows, wl["cols"], wl["seed"], bins[:, :32])
     X = bins.astype(np.float32)
@@ -145,20 +160,33 @@ def run_reference(args, wl, rank, world):
     del X
     # histogram layout: neither force_col_wise nor force_row_wise is set, so the reference times both layouts itself
     # at Booster creation and keeps the faster one (Dataset::GetShareStates, dataset.cpp:655-727) — its stock
-    # behaviour; forcing row-wise on a 100+-thread host is pathological (per-thread histogram merges).
-    bp = dict(dsp, objective="regression", num_leaves=wl["leaves"], learning_rate=0.1, min_data_in_leaf=20, device_type="cpu")
-    bst = refapi.RefBooster(ds, bp)
-    for _ in range(args.warmup):
+    # behaviour.  Thread count: all the host threads it can use, but shared GPU boxes advertise more logical CPUs
+    # than a tenant gets; OpenMP spin-waits then collapse (measured: 49 s/iter at 128 threads vs ~16 usable cores),
+    # so the count is halved while the first iteration is implausibly slow.
+    threads = cores
+    while True:
+        bp = dict(dsp, objective="regression", num_leaves=wl["leaves"], learning_rate=0.1, min_data_in_leaf=20,
+                  device_type="cpu", num_threads=threads)
+        bst = refapi.RefBooster(ds, bp)
+        t0 = time.time()
+        bst.update()
+        t_first = time.time() - t0
+        if t_first < 8.0 or threads <= 8:
+            break
+        bst.free()
+        threads //= 2
+    for _ in range(max(args.warmup - 1, 0)):
         bst.update()
     t0 = time.time()
     for _ in range(args.steps):
         bst.update()
     dt = (time.time() - t0) / args.steps
     bst.free()
+    cores = threads
     best_mode = "col/row-wise chosen by the reference's own auto-timing"
     scale = rows / wl["rows"]
     value = (1.0 / dt) * scale
-    sample = f"{rows} of {wl['rows']} rows x {wl['cols']} cols, {wl['leaves']} leaves, {best_mode} (faster of col/row-wise), " \
+    sample = f"{rows} of {wl['rows']} rows x {wl['cols']} cols, {wl['leaves']} leaves, {best_mode}, " \
              f"{cores} threads; it/s scaled by {scale:g}; dataset construction {t_ds:.1f}s excluded"
     return dict(value=value, ms_per_step=dt * 1e3 / scale, cores=cores, sample=sample)
 
