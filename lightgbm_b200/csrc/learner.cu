@@ -525,11 +525,6 @@ class Learner {
       if (it > 0) {
         k_part_flags<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
         Stamp(kProfPartFlags);
-        if (peers_.world > 1 && peers_.mode == 0) {
-          k_part_push<<<num_sms_, kPartThreads, 0, stream_>>>(pt);
-          k_part_count<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
-          launches_ += 2; Stamp(kProfPartCount);
-        }
         k_part_scatter<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
         Stamp(kProfPartScatter);
         launches_ += 2;

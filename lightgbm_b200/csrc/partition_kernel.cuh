@@ -59,8 +59,8 @@ __device__ __forceinline__ void part_block_range(int n, int nblocks, int b, int*
 // Go-left flags are BIT-packed, one 32-bit ballot word per 32 consecutive rows of the leaf (leaf-relative
 // index i -> word i>>5, bit i&31).  Block ranges are multiples of 256 rows, so every warp owns whole words.
 // Single GPU: words go to the local scratch.  Feature-shard: only the split's owner computes them and
-// pushes each word into every rank's flag buffer over NVLink (n/8 bytes per peer), then publishes a
-// sequence number; k_part_count on every rank waits for it.
+// pushes them (and its per-block left counts) into every rank's CommBlock over NVLink (n/8 bytes per peer),
+// then publishes a sequence number; k_part_scatter on every rank waits for it.
 constexpr int kPartUnroll = 4;
 
 __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
       const unsigned word = __ballot_sync(0xffffffffu, left);
       if (lane == 0 && (i - lane) < hi) {
         const int wi = (i - lane) >> 5;
-        if (W > 1) comm_flag_words(a.peers.block[me], par, a.peers.flags_stride)[wi] = word;   // own buffer; k_part_push ships it
+        if (W > 1) comm_flag_words(a.peers.block[me], par, a.peers.flags_stride)[wi] = word;   // own buffer first; pushed to the peers below
         else a.flag_words[wi] = word;
         cnt += __popc(word);
       }
@@ -109,76 +109,38 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
   }
   __shared__ int s_cnt[kPartThreads / 32];
   if (lane == 0) s_cnt[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
+  __syncthreads();                         // also: this block's flag words (global) are visible block-wide
+  int t = 0;
 #pragma unroll
-    for (int w = 0; w < kPartThreads / 32; ++w) t += s_cnt[w];
-    a.block_left[blockIdx.x] = t;
+  for (int w = 0; w < kPartThreads / 32; ++w) t += s_cnt[w];
+  if (W == 1) {
+    if (threadIdx.x == 0) a.block_left[blockIdx.x] = t;
+    return;
   }
-}
-
-// feature-shard mode, owner only: ship the bit-packed flag words (n/8 bytes) from the owner's buffer into every
-// peer's buffer with coalesced 16-byte peer stores over NVLink, then publish the sequence number (last block).
-__global__ void __launch_bounds__(kPartThreads) k_part_push(const PartArgs a) {
-  Ctl* c = a.ctl;
-  if (!c->cur_valid) return;
-  const int W = a.peers.world, me = a.peers.rank;
-  if (c->cur_owner != me) return;
-  const unsigned long long fseq = c->flag_seq;
-  const int par = static_cast<int>(fseq & 1);
-  const int nvec = ((c->cur_count + 31) / 32 + 3) / 4;                 // uint4 chunks (buffers are 256-byte padded)
-  const uint4* src = reinterpret_cast<const uint4*>(comm_flag_words(a.peers.block[me], par, a.peers.flags_stride));
-  for (int i = blockIdx.x * kPartThreads + threadIdx.x; i < nvec; i += gridDim.x * kPartThreads) {
-    const uint4 v = src[i];
+  // feature-shard, owner: push this block's words (a contiguous, 32-byte aligned run) and its left count into
+  // every rank's CommBlock with coalesced 16-byte peer stores over NVLink; the last block publishes the sequence
+  // number.  Peers need no counting pass: k_part_scatter waits for the sequence number and reads blk_left.
+  {
+    const int w_lo = lo >> 5, w_hi = (hi + 31) >> 5;
+    const uint4* src = reinterpret_cast<const uint4*>(comm_flag_words(a.peers.block[me], par, a.peers.flags_stride) + w_lo);
+    const int nvec = (w_hi - w_lo + 3) / 4;
+    for (int i = threadIdx.x; i < nvec; i += kPartThreads) {
+      const uint4 v = src[i];
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r) {
-      if (r < W && r != me) reinterpret_cast<uint4*>(comm_flag_words(a.peers.block[r], par, a.peers.flags_stride))[i] = v;
+      for (int r = 0; r < kMaxRanks; ++r) {
+        if (r < W && r != me) reinterpret_cast<uint4*>(comm_flag_words(a.peers.block[r], par, a.peers.flags_stride) + w_lo)[i] = v;
+      }
     }
-  }
-  __threadfence_system();                // every thread orders its own peer stores
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned done = atomicAdd(&c->part_blocks_done, 1u);
-    if (done == gridDim.x - 1) {
-      __threadfence_system();
-      for (int r = 0; r < W; ++r) st_release_sys(&a.peers.block[r]->flags_seq[par], fseq);
+    if (threadIdx.x < W) a.peers.block[threadIdx.x]->blk_left[par][blockIdx.x] = t;
+    __threadfence_system();                // every thread orders its own peer stores
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned done = atomicAdd(&c->part_blocks_done, 1u);
+      if (done == gridDim.x - 1) {
+        __threadfence_system();
+        for (int r = 0; r < W; ++r) st_release_sys(&a.peers.block[r]->flags_seq[par], fseq);
+      }
     }
-  }
-}
-
-// feature-shard mode: every rank (owner included) waits for the pushed flag words, then counts lefts per block
-__global__ void __launch_bounds__(kPartThreads) k_part_count(const PartArgs a) {
-  Ctl* c = a.ctl;
-  if (!c->cur_valid) return;
-  const unsigned long long fseq = c->flag_seq;
-  const int par = static_cast<int>(fseq & 1);
-  CommBlock* mine = a.peers.block[a.peers.rank];
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) {
-    const int ok = wait_seq(&mine->flags_seq[par], fseq) ? 1 : 0;
-    if (!ok) c->error = 1;
-    s_ok = ok;
-  }
-  __syncthreads();
-  if (!s_ok) { a.block_left[blockIdx.x] = 0; return; }
-  const int n = c->cur_count;
-  const uint32_t* fw = comm_flag_words(mine, par, a.peers.flags_stride);
-  int lo, hi;
-  part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
-  int cnt = 0;
-  // (empty blocks have lo == hi == n: they must not count the leaf's last, partial word again)
-  for (int wi = (lo >> 5) + threadIdx.x; lo < hi && wi < ((hi + 31) >> 5); wi += kPartThreads) cnt += __popc(__ldcv(fw + wi));
-  __shared__ int s_cnt[kPartThreads / 32];
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-#pragma unroll
-    for (int w = 0; w < kPartThreads / 32; ++w) t += s_cnt[w];
-    a.block_left[blockIdx.x] = t;
   }
 }
 
@@ -190,9 +152,17 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
   int32_t* dst = (c->cur_buf ? a.idx0 : a.idx1) + begin;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* fw = a.flag_words;
+  const int32_t* block_left = a.block_left;
   if (a.peers.world > 1 && a.peers.mode == 0) {
-    if (c->error) return;
-    fw = comm_flag_words(a.peers.block[a.peers.rank], static_cast<int>(c->flag_seq & 1), a.peers.flags_stride);
+    // feature-shard: the flag words and per-block counts of this split are pushed by the split's owner
+    CommBlock* mine = a.peers.block[a.peers.rank];
+    const int par = static_cast<int>(c->flag_seq & 1);
+    __shared__ int s_ok;
+    if (tid == 0) { s_ok = wait_seq(&mine->flags_seq[par], c->flag_seq) ? 1 : 0; if (!s_ok) c->error = 1; }
+    __syncthreads();
+    if (!s_ok) return;
+    fw = comm_flag_words(mine, par, a.peers.flags_stride);
+    block_left = mine->blk_left[par];
   }
 
   // offsets from the per-block counts (gridDim.x <= 1024)
@@ -200,7 +170,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
   __shared__ int s_before, s_total;
   int before = 0, total = 0;
   for (int j = tid; j < static_cast<int>(gridDim.x); j += kPartThreads) {
-    const int v = a.block_left[j];
+    const int v = __ldcv(block_left + j);
     total += v;
     if (j < static_cast<int>(blockIdx.x)) before += v;
   }

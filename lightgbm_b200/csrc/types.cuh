@@ -103,6 +103,7 @@ struct CommBlock {
   unsigned long long hist_seq[kMaxRanks];     // hist_seq[r]: rank r's local histogram #seq is complete
   double misc[2][kMaxRanks][8];               // small all-gather payloads (root sums / left counts)
   unsigned long long misc_seq[2][kMaxRanks];
+  int32_t blk_left[2][1024];                  // feature-shard: the owner's per-block left counts, pushed with the flags
   // followed by: uint32_t flag_words[2][ceil(num_data/32)] (bit-packed go-left flags)
 };
 struct CommPeers {
