@@ -53,7 +53,8 @@ typedef struct {
   int32_t use_cuda_graph;           /* 1: replay the whole per-tree launch sequence as one CUDA graph */
   int32_t reserved;                 /* bit 0: do NOT keep the column-major copy of the bin matrix used by the
                                        partition kernels (saves num_data*num_columns bytes of HBM);
-                                       bit 1: do NOT stage contiguous (root) histogram passes with TMA tile copies */
+                                       bit 1: do NOT stage contiguous (root) histogram passes with TMA tile copies;
+                                       bit 2: legacy column-group-major work mapping in the histogram kernel */
 } LGBMB200_Config;
 
 /*

@@ -57,6 +57,7 @@ struct HistArgs {
   int32_t num_colgroups;          // ceil(num_columns / 32)
   int32_t min_rows_per_item;      // do not split a column group over more warps than n / this
   int32_t use_tma;                // 1: contiguous (root, un-bagged) stages are staged by TMA tile copies
+  int32_t map_mode;               // 0: items dealt column-group-major; 1: one CTA = (column group, 3 row parts), adjacent CTAs = adjacent column groups
   // explicit mode (stand-alone ConstructHistogram hook): explicit_n >= 0
   int32_t explicit_n;
   int32_t explicit_slot;
@@ -152,6 +153,7 @@ struct HistWork {
   int n, begin, slot;
   const int32_t* idx;
   int CG, splits, per, items, total_warps;
+  int mode, rounds_total;        // mode 1: rounds_total = CG * ceil(splits/3) virtual CTAs
 };
 
 __device__ __forceinline__ bool hist_work_setup(const HistArgs& a, HistWork* w) {
@@ -173,14 +175,53 @@ __device__ __forceinline__ bool hist_work_setup(const HistArgs& a, HistWork* w) 
   // cost (zeroing + the merged flush, ~16K/3 global atomics per item at ~0.2 G atomics/us):
   // t(s) = n/s * t_row + CG*s * t_item  =>  s* = sqrt(n * t_row / (CG * t_item)) ~ sqrt(0.7 n / CG)
   int sp = static_cast<int>(sqrtf(0.7f * static_cast<float>(w->n) / static_cast<float>(w->CG)));
-  sp = min(max_splits, max(1, min(sp, (w->n + a.min_rows_per_item - 1) / a.min_rows_per_item)));
-  // whole CTAs per column group => every CTA can merge its tables (not when the warp count is the limit:
-  // there the rows per warp matter more than the flush)
-  if (sp >= kHistWarps && sp < max_splits) sp -= sp % kHistWarps;
+  sp = max(1, min(sp, (w->n + a.min_rows_per_item - 1) / a.min_rows_per_item));
+  w->mode = a.map_mode;
+  if (w->mode == 1) {
+    // one CTA = one column group x three consecutive row parts (always mergeable); CTAs b, b+1 work on adjacent
+    // column groups of the SAME rows at the same time, so the two 32-byte sectors of a 64-byte DRAM atom are
+    // fetched once (the second hits in L2).  One wave: at most floor(grid / CG) triples per column group.
+    const int max_triples = max(1, static_cast<int>(gridDim.x) / w->CG);
+    const int triples = min(max_triples, (sp + kHistWarps - 1) / kHistWarps);
+    sp = min(sp, triples * kHistWarps);
+    if (sp > kHistWarps) sp = triples * kHistWarps;          // full triples
+    w->rounds_total = w->CG * triples;
+  } else {
+    sp = min(max_splits, sp);
+    // whole CTAs per column group => every CTA can merge its tables (not when the warp count is the limit:
+    // there the rows per warp matter more than the flush)
+    if (sp >= kHistWarps && sp < max_splits) sp -= sp % kHistWarps;
+    w->rounds_total = 0;
+  }
   w->splits = sp;
   w->per = (((w->n + w->splits - 1) / w->splits) + 31) & ~31;
   w->items = w->CG * w->splits;
   return true;
+}
+
+// item of (round r, warp pair p): returns false if this warp has nothing to do in this round
+struct HistItem { int cg, part; bool valid, merge; };
+__device__ __forceinline__ bool hist_round_valid(const HistWork& w, int round) {
+  return w.mode == 1 ? (static_cast<int>(blockIdx.x) + round * static_cast<int>(gridDim.x) < w.rounds_total)
+                     : (static_cast<int>(blockIdx.x) * kHistWarps + round * w.total_warps < w.items);
+}
+__device__ __forceinline__ HistItem hist_item(const HistWork& w, int round, int pair) {
+  HistItem it;
+  if (w.mode == 1) {
+    const int v = blockIdx.x + round * gridDim.x;
+    it.cg = v % w.CG;
+    const int t = v / w.CG;
+    it.part = t * kHistWarps + pair;
+    it.valid = it.part < w.splits;
+    it.merge = (t * kHistWarps + kHistWarps - 1) < w.splits;
+  } else {
+    const int base = blockIdx.x * kHistWarps + round * w.total_warps;
+    const int item = base + pair;
+    it.valid = item < w.items;
+    it.cg = item / w.splits; it.part = item % w.splits;
+    it.merge = (base + kHistWarps - 1 < w.items) && (base / w.splits == (base + kHistWarps - 1) / w.splits);
+  }
+  return it;
 }
 
 __device__ __forceinline__ void consumer_bar_sync() {          // the 3 consumer warps only (named barrier 1)
@@ -209,10 +250,10 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
   if (is_producer) {
     // ------------------------------------------------------------------ producer warp: stage rows
     int slot = 0; unsigned phase = 0;
-    for (int base = blockIdx.x * kHistWarps; base < w.items; base += w.total_warps) {
-      const int item = base + pair;
-      if (item >= w.items) continue;
-      const int cg = item / w.splits, part = item % w.splits;
+    for (int round = 0; hist_round_valid(w, round); ++round) {
+      const HistItem it = hist_item(w, round, pair);
+      if (!it.valid) continue;
+      const int cg = it.cg, part = it.part;
       const int r0 = part * w.per;
       const int r1 = min(w.n, r0 + w.per);
       if (r0 >= r1) continue;
@@ -259,12 +300,12 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
   const unsigned hbase0 = static_cast<unsigned>(__cvta_generic_to_shared(reinterpret_cast<float2*>(smem) + lane));
   const double gs = a.ctl->g_scale, hs = a.ctl->h_scale;
   int slot = 0; unsigned phase = 0;
-  for (int base = blockIdx.x * kHistWarps; base < w.items; base += w.total_warps) {
-    const int item = base + pair;
+  for (int round = 0; hist_round_valid(w, round); ++round) {
+    const HistItem it = hist_item(w, round, pair);
     // merge path: all three warps of the CTA hold items of the same column group (CTA-uniform condition)
-    const bool merge = (base + kHistWarps - 1 < w.items) && (base / w.splits == (base + kHistWarps - 1) / w.splits);
-    if (item >= w.items) continue;                                 // only possible when !merge
-    const int cg = item / w.splits, part = item % w.splits;
+    const bool merge = it.merge;
+    if (!it.valid) continue;                                       // only possible when !merge
+    const int cg = it.cg, part = it.part;
     const int r0 = part * w.per;
     const int r1 = min(w.n, r0 + w.per);
     if (r0 >= r1 && !merge) continue;

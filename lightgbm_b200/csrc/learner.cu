@@ -465,6 +465,7 @@ class Learner {
     ha.slot_stride = slot_stride_; ha.num_colgroups = Cpad_ / kColGroup; ha.min_rows_per_item = 64;
     ha.explicit_n = -1; ha.explicit_slot = 0; ha.explicit_idx = nullptr;
     ha.use_tma = have_tmap_ ? 1 : 0;
+    ha.map_mode = (cfg_.reserved & 4) ? 0 : 1;
     return ha;
   }
 

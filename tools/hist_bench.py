@@ -8,7 +8,10 @@ n = int(os.environ.get("HB_ROWS", 1_000_000)); f = int(os.environ.get("HB_COLS",
 rng = np.random.default_rng(0)
 bins = rng.integers(0, 255, (n, f), dtype=np.uint8)
 g = rng.normal(size=n).astype(np.float32); h = np.ones(n, np.float32)
-L = lgb.B200TreeLearner(lgb.Config(num_leaves=4, use_cuda_graph=False))
+cfg = lgb.Config(num_leaves=4, use_cuda_graph=False)
+_orig = cfg.to_c
+cfg.to_c = lambda: (lambda c: (setattr(c, "reserved", int(os.environ.get("HB_RESERVED", 0))), c)[1])(_orig())
+L = lgb.B200TreeLearner(cfg)
 L.init(lgb.Layout.identity(bins))
 from lightgbm_b200.tree_learner import DeviceArray
 dg = DeviceArray(n * 4).upload(g); dh = DeviceArray(n * 4).upload(h)
