@@ -534,7 +534,8 @@ class Learner {
       k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha, tmap_);
       Stamp(kProfHist);
       if (row_mode) { k_hist_signal<<<1, 32, 0, stream_>>>(peers_, ctl_.p); ++launches_; }
-      k_scan<<<dim3(std::max(scan_blocks, 1), row_mode ? 1 : 2), kScanWarps * 32, 0, stream_>>>(sa);
+      if (row_mode) k_scan<true><<<dim3(std::max(scan_blocks, 1), 1), kScanWarps * 32, 0, stream_>>>(sa);
+      else k_scan<false><<<dim3(std::max(scan_blocks, 1), 2), kScanWarps * 32, 0, stream_>>>(sa);
       Stamp(kProfScan);
       k_select<<<1, 256, 0, stream_>>>(se);
       Stamp(kProfSelect);

@@ -283,11 +283,12 @@ __device__ __forceinline__ Cand cand_none() {
 // (the reduce-scatter of DataParallelTreeLearner, data_parallel_tree_learner.cpp:283+, fused into the scan's
 // load phase; int64 fixed point => the sum is exact and order-independent).  The global slice is written back
 // into this rank's own pool so that later subtractions (parent - smaller) stay local.
-__global__ void __launch_bounds__(kScanWarps * 32, 1) k_scan(const ScanArgs a) {
+template <bool ROWS>
+__global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const ScanArgs a) {
   Ctl* c = a.ctl;
   if (!c->cur_valid || !c->do_find) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool rows = a.peers.world > 1 && a.peers.mode == 1;
+  constexpr bool rows = ROWS;
   const int f = (rows ? a.peers.f_lo : 0) + blockIdx.x * kScanWarps + warp;
   const int f_end = rows ? a.peers.f_lo + a.peers.f_cnt : a.num_features;
   const int F = a.num_features;
@@ -307,29 +308,29 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) k_scan(const ScanArgs a) {
     if (!s_ok) return;
   }
 
-  Cand out[2] = {cand_none(), cand_none()};
-  int new_flag[2] = {2, 2};
   const int w_lo = rows ? 0 : blockIdx.y, w_hi = rows ? 2 : blockIdx.y + 1;     // which children this warp handles
+  const bool in_range = f < f_end;
+  bool used = false;
+  int inherit_flag0 = 2;
+  FeatMeta m = {};
+  long long ig[8], ih[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { ig[k] = 0; ih[k] = 0; }
+  int64_t slice = 0;
 
-  if (f < f_end) {
+  if (in_range) {
     const Leaf& LS = a.leaves[smaller];
-    bool used = (a.feature_used == nullptr) || a.feature_used[f];
+    used = (a.feature_used == nullptr) || a.feature_used[f];
     if (used && larger >= 0 && !a.splittable[static_cast<int64_t>(a.leaves[larger].slot) * F + f]) {
       // parent was not splittable on this feature (serial_tree_learner.cpp:397-402): both children inherit it
-      used = false; new_flag[0] = 0;
+      used = false; inherit_flag0 = 0;
     }
     if (used) {
-      const FeatMeta m = a.feat[f];
-      const GainCfg gc = make_gain_cfg(a.params);
-      const double g_inv = c->g_inv, h_inv = c->h_inv;
-      const int64_t slice = (static_cast<int64_t>(m.col) * kBinsPerColumn + m.lo) * 2;
+      m = a.feat[f];
+      slice = (static_cast<int64_t>(m.col) * kBinsPerColumn + m.lo) * 2;
       const int64_t soff = static_cast<int64_t>(LS.slot) * a.slot_stride + slice;
       long long* hs = a.pool + soff;
-
       // smaller child's slice (row-shard: summed over every rank's local histogram)
-      long long ig[8], ih[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { ig[k] = 0; ih[k] = 0; }
       if (rows) {
         for (int r = 0; r < a.peers.world; ++r) {
           const long long* hp = a.peers.pool[r] + soff;
@@ -369,49 +370,53 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) k_scan(const ScanArgs a) {
           for (int k = 0; k < 8; ++k) { if (lane * 8 + k == m.mfb) *reinterpret_cast<longlong2*>(hs + 2 * m.mfb) = make_longlong2(ig[k], ih[k]); }
         }
       }
-      double g[8], h[8];
-      for (int which = w_lo; which < w_hi; ++which) {
-        int splittable = 0;
-        if (which == 0) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { h[k] = static_cast<double>(ih[k]) * h_inv; g[k] = (ih[k] == 0) ? 0.0 : static_cast<double>(ig[k]) * g_inv; }
-          const double po = (c->num_leaves == 1)
-              ? leaf_output(GainCfg{1, 1, 0, a.params.l1, a.params.l2, a.params.max_delta_step, a.params.path_smooth}, LS.sum_g, LS.sum_h, LS.count, 0.0)
-              : LS.output;
-          out[0] = find_best_threshold(g, h, lane, f, m, a.params, gc, LS.sum_g, LS.sum_h, LS.count, po, &splittable);
-        } else {
-          if (larger < 0) continue;
-          // larger child = parent - smaller (exact), written in place into the parent's slot
-          const Leaf& LL = a.leaves[larger];
-          long long* hl = a.pool + static_cast<int64_t>(LL.slot) * a.slot_stride + slice;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int e = lane * 8 + k;
-            if (e < m.nslice) {
-              longlong2 v = *reinterpret_cast<const longlong2*>(hl + 2 * e);
-              v.x -= ig[k]; v.y -= ih[k];
-              *reinterpret_cast<longlong2*>(hl + 2 * e) = v;
-              h[k] = static_cast<double>(v.y) * h_inv;
-              g[k] = (v.y == 0) ? 0.0 : static_cast<double>(v.x) * g_inv;
-            } else { g[k] = 0.0; h[k] = 0.0; }
-          }
-          out[1] = find_best_threshold(g, h, lane, f, m, a.params, gc, LL.sum_g, LL.sum_h, LL.count, LL.output, &splittable);
-        }
-        new_flag[which] = splittable;
-      }
-    }
-    if (lane == 0) {
-      for (int which = w_lo; which < w_hi; ++which) {
-        a.cand[which * F + f] = out[which];
-        a.splittable_new[which * F + f] = static_cast<uint8_t>(new_flag[which]);
-      }
     }
   }
-  // block-level arg-max (gain, then smaller real feature index) so that k_select scans F/8 entries only
-  if (lane == 0) {
-    for (int which = w_lo; which < w_hi; ++which) {
-      s_gain[which][warp] = out[which].gain; s_real[which][warp] = out[which].feature < 0 ? 0x7fffffff : out[which].real;
-      s_feat[which][warp] = out[which].feature;
+
+  // one child at a time (no per-child arrays: keeps the kernel at 2 CTAs/SM)
+#pragma unroll 1
+  for (int which = w_lo; which < w_hi; ++which) {
+    Cand out = cand_none();
+    int new_flag = (which == 0) ? inherit_flag0 : 2;
+    if (used && !(which == 1 && larger < 0)) {
+      const GainCfg gc = make_gain_cfg(a.params);
+      const double g_inv = c->g_inv, h_inv = c->h_inv;
+      double g[8], h[8];
+      int splittable = 0;
+      if (which == 0) {
+        const Leaf& LS = a.leaves[smaller];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { h[k] = static_cast<double>(ih[k]) * h_inv; g[k] = (ih[k] == 0) ? 0.0 : static_cast<double>(ig[k]) * g_inv; }
+        const double po = (c->num_leaves == 1)
+            ? leaf_output(GainCfg{1, 1, 0, a.params.l1, a.params.l2, a.params.max_delta_step, a.params.path_smooth}, LS.sum_g, LS.sum_h, LS.count, 0.0)
+            : LS.output;
+        out = find_best_threshold(g, h, lane, f, m, a.params, gc, LS.sum_g, LS.sum_h, LS.count, po, &splittable);
+      } else {
+        // larger child = parent - smaller (exact), written in place into the parent's slot
+        const Leaf& LL = a.leaves[larger];
+        long long* hl = a.pool + static_cast<int64_t>(LL.slot) * a.slot_stride + slice;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = lane * 8 + k;
+          if (e < m.nslice) {
+            longlong2 v = *reinterpret_cast<const longlong2*>(hl + 2 * e);
+            v.x -= ig[k]; v.y -= ih[k];
+            *reinterpret_cast<longlong2*>(hl + 2 * e) = v;
+            h[k] = static_cast<double>(v.y) * h_inv;
+            g[k] = (v.y == 0) ? 0.0 : static_cast<double>(v.x) * g_inv;
+          } else { g[k] = 0.0; h[k] = 0.0; }
+        }
+        out = find_best_threshold(g, h, lane, f, m, a.params, gc, LL.sum_g, LL.sum_h, LL.count, LL.output, &splittable);
+      }
+      new_flag = splittable;
+    }
+    if (lane == 0) {
+      if (in_range && !(which == 1 && larger < 0 && !rows)) {
+        a.cand[which * F + f] = out;
+        a.splittable_new[which * F + f] = static_cast<uint8_t>(new_flag);
+      }
+      // block-level arg-max input (gain, then smaller real feature index) so that k_select scans F/8 entries only
+      s_gain[which][warp] = out.gain; s_real[which][warp] = out.feature < 0 ? 0x7fffffff : out.real; s_feat[which][warp] = out.feature;
     }
   }
   __syncthreads();
