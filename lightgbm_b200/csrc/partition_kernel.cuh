@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
   {
     const int w_lo = lo >> 5, w_hi = (hi + 31) >> 5;
     const uint4* src = reinterpret_cast<const uint4*>(comm_flag_words(a.peers.block[me], par, a.peers.flags_stride) + w_lo);
-    const int nvec = (w_hi - w_lo + 3) / 4;
+    const int nvec = lo < hi ? (w_hi - w_lo + 3) / 4 : 0;       // empty blocks (lo == hi == n) push nothing
     for (int i = threadIdx.x; i < nvec; i += kPartThreads) {
       const uint4 v = src[i];
 #pragma unroll
