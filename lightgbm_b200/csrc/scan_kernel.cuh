@@ -46,8 +46,12 @@ __device__ __forceinline__ double threshold_l1(double s, double l1) {
   return sign_of(s) * r;
 }
 
+// NOTE on code size: the first version of k_scan inlined the fp64 divisions of the gain formula ~100 times
+// (26K SASS instructions = 416 KB) and spent most of its time waiting for instruction fetch
+// (profiles/r01_scan_icache_bound.txt: stall_no_instruction 21.7 per issue).  The gain helpers are therefore
+// real functions (__noinline__), called from a single scan site per direction.
 // feature_histogram.hpp:716-738 CalculateSplittedLeafOutput (no monotone constraints)
-__device__ __forceinline__ double leaf_output(const GainCfg& c, double sg, double sh, int n, double parent_output) {
+__device__ __noinline__ double leaf_output(const GainCfg& c, double sg, double sh, int n, double parent_output) {
   double ret = c.use_l1 ? -threshold_l1(sg, c.l1) / (sh + c.l2) : -sg / (sh + c.l2);
   if (c.use_max_output) {
     if (c.max_delta_step > 0 && fabs(ret) > c.max_delta_step) ret = sign_of(ret) * c.max_delta_step;
@@ -60,11 +64,17 @@ __device__ __forceinline__ double leaf_output(const GainCfg& c, double sg, doubl
 }
 
 // feature_histogram.hpp:799-828 GetLeafGain / GetLeafGainGivenOutput
-__device__ __forceinline__ double leaf_gain(const GainCfg& c, double sg, double sh, int n, double parent_output) {
+__device__ __noinline__ double leaf_gain(const GainCfg& c, double sg, double sh, int n, double parent_output) {
   const double g = c.use_l1 ? threshold_l1(sg, c.l1) : sg;
   if (!c.use_max_output && !c.use_smoothing) return (g * g) / (sh + c.l2);
   const double out = leaf_output(c, sg, sh, n, parent_output);
   return -(2.0 * g * out + (sh + c.l2) * out * out);
+}
+
+// GetSplitGains (feature_histogram.hpp:758-797, no monotone constraints): left + right leaf gains
+__device__ __noinline__ double split_gain(const GainCfg& c, double lg, double lh, int lc, double rg, double rh, int rc, double parent_output) {
+  if (!c.use_l1 && !c.use_max_output && !c.use_smoothing) return (lg * lg) / (lh + c.l2) + (rg * rg) / (rh + c.l2);
+  return leaf_gain(c, lg, lh, lc, parent_output) + leaf_gain(c, rg, rh, rc, parent_output);
 }
 
 __device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
@@ -78,7 +88,7 @@ struct DirBest {
 // One scan direction over the lane's 8 slice entries g[k], h[k] (entry e = lane*8+k <-> bin e+offset).
 // Returns the warp-wide best candidate (all lanes hold the same result); *any_splittable is OR-ed.
 template <bool REVERSE>
-__device__ __forceinline__ DirBest scan_direction(const double (&g)[8], const double (&h)[8], int lane, const FeatMeta& m,
+__device__ __noinline__ DirBest scan_direction(const double (&g)[8], const double (&h)[8], int lane, const FeatMeta& m,
                                                   const Params& P, const GainCfg& gc, double sum_g, double sum_h,
                                                   int num_data, double min_gain_shift, double parent_output,
                                                   bool skip_default, bool na_as_missing, int* any_splittable) {
@@ -153,9 +163,8 @@ __device__ __forceinline__ DirBest scan_direction(const double (&g)[8], const do
     const double other_h = sum_h - acc_h;
     if (other_h < P.min_sum_hessian) return;
     const double other_g = sum_g - acc_g;
-    double cur;
-    if (REVERSE) cur = leaf_gain(gc, other_g, other_h, other_c, parent_output) + leaf_gain(gc, acc_g, acc_h, acc_c, parent_output);
-    else cur = leaf_gain(gc, acc_g, acc_h, acc_c, parent_output) + leaf_gain(gc, other_g, other_h, other_c, parent_output);
+    const double cur = REVERSE ? split_gain(gc, other_g, other_h, other_c, acc_g, acc_h, acc_c, parent_output)
+                               : split_gain(gc, acc_g, acc_h, acc_c, other_g, other_h, other_c, parent_output);
     if (cur <= min_gain_shift) return;
     splittable = 1;
     if (cur > best.gain) {
@@ -231,17 +240,18 @@ __device__ __forceinline__ Cand find_best_threshold(const double (&g)[8], const 
     }
   };
 
-  // direction dispatch: feature_histogram.hpp:396-441
-  if (m.num_bin > 2 && m.missing != 0) {
-    const bool zero = (m.missing == 1);
-    DirBest r = scan_direction<true>(g, h, lane, m, P, gc, sum_g, sum_h, num_data, min_gain_shift, parent_output, zero, !zero, &splittable);
+  // direction dispatch: feature_histogram.hpp:396-441 (one call site per direction keeps the kernel small)
+  const bool two_way = m.num_bin > 2 && m.missing != 0;
+  const bool zero = two_way && m.missing == 1, na = two_way && m.missing == 2;
+  {
+    const DirBest r = scan_direction<true>(g, h, lane, m, P, gc, sum_g, sum_h, num_data, min_gain_shift, parent_output, zero, na, &splittable);
     apply(r, true);
-    DirBest fw = scan_direction<false>(g, h, lane, m, P, gc, sum_g, sum_h, num_data, min_gain_shift, parent_output, zero, !zero, &splittable);
+  }
+  if (two_way) {
+    const DirBest fw = scan_direction<false>(g, h, lane, m, P, gc, sum_g, sum_h, num_data, min_gain_shift, parent_output, zero, na, &splittable);
     apply(fw, false);
-  } else {
-    DirBest r = scan_direction<true>(g, h, lane, m, P, gc, sum_g, sum_h, num_data, min_gain_shift, parent_output, false, false, &splittable);
-    apply(r, true);
-    if (m.missing == 2) out.default_left = 0;
+  } else if (m.missing == 2) {
+    out.default_left = 0;
   }
   *is_splittable = splittable;
   return out;
@@ -383,14 +393,15 @@ __global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const Sc
       const double g_inv = c->g_inv, h_inv = c->h_inv;
       double g[8], h[8];
       int splittable = 0;
+      double sum_g, sum_h, po; int cnt;
       if (which == 0) {
         const Leaf& LS = a.leaves[smaller];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { h[k] = static_cast<double>(ih[k]) * h_inv; g[k] = (ih[k] == 0) ? 0.0 : static_cast<double>(ig[k]) * g_inv; }
-        const double po = (c->num_leaves == 1)
+        sum_g = LS.sum_g; sum_h = LS.sum_h; cnt = LS.count;
+        po = (c->num_leaves == 1)
             ? leaf_output(GainCfg{1, 1, 0, a.params.l1, a.params.l2, a.params.max_delta_step, a.params.path_smooth}, LS.sum_g, LS.sum_h, LS.count, 0.0)
             : LS.output;
-        out = find_best_threshold(g, h, lane, f, m, a.params, gc, LS.sum_g, LS.sum_h, LS.count, po, &splittable);
       } else {
         // larger child = parent - smaller (exact), written in place into the parent's slot
         const Leaf& LL = a.leaves[larger];
@@ -406,8 +417,9 @@ __global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const Sc
             g[k] = (v.y == 0) ? 0.0 : static_cast<double>(v.x) * g_inv;
           } else { g[k] = 0.0; h[k] = 0.0; }
         }
-        out = find_best_threshold(g, h, lane, f, m, a.params, gc, LL.sum_g, LL.sum_h, LL.count, LL.output, &splittable);
+        sum_g = LL.sum_g; sum_h = LL.sum_h; cnt = LL.count; po = LL.output;
       }
+      out = find_best_threshold(g, h, lane, f, m, a.params, gc, sum_g, sum_h, cnt, po, &splittable);
       new_flag = splittable;
     }
     if (lane == 0) {
