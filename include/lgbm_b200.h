@@ -54,7 +54,8 @@ typedef struct {
   int32_t reserved;                 /* bit 0: do NOT keep the column-major copy of the bin matrix used by the
                                        partition kernels (saves num_data*num_columns bytes of HBM);
                                        bit 1: do NOT stage contiguous (root) histogram passes with TMA tile copies;
-                                       bit 2: legacy column-group-major work mapping in the histogram kernel */
+                                       bit 2: legacy column-group-major work mapping in the histogram kernel;
+                                       bit 3: experimental split gradient/hessian histogram kernel (slower; A/B only) */
 } LGBMB200_Config;
 
 /*

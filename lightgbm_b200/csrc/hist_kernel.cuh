@@ -424,4 +424,192 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
   }
 }
 
+// k_hist2: same staging, same work decomposition, but every column group is accumulated by TWO consumer warps that
+// share the staged rows: a g-warp owning a [bin][lane] fp32 table of gradients and an h-warp owning the table of
+// hessians (2 x 32 KB = the 64 KB of the float2 table).  Same shared-memory wavefronts per cell, but 6 consumer
+// warps per SM instead of 3 (two per SMSP on half the SMSPs, all four SMSPs busy): a dependent-issue bubble of one
+// warp is filled by the other, which is what the single-consumer version could not do.
+constexpr int kHist2Threads = 3 * kHistWarps * 32;      // warps 0-2: g consumers, 3-5: h consumers, 6-8: producers
+constexpr int kCompTableBytes = kBinsPerColumn * 32 * 4; // 32768
+
+__device__ __forceinline__ float lds32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
+
+template <int K>
+__device__ __forceinline__ void batch_prepare1(unsigned tbase, const uint32_t (&b)[K], const float (&q)[K], unsigned (&addr)[K], float (&s)[K]) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    addr[i] = tbase + (b[i] << 7);
+    s[i] = q[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) if (b[j] == b[i]) s[i] += q[j];
+  }
+}
+__device__ __forceinline__ void consumer2_bar_sync() {          // the 6 consumer warps only (named barrier 1)
+  asm volatile("bar.sync 1, %0;" ::"n"(2 * kHistWarps * 32) : "memory");
+}
+
+__global__ void __launch_bounds__(kHist2Threads, 1) k_hist2(const HistArgs a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_producer = warp >= 2 * kHistWarps;
+  const int comp = (warp >= kHistWarps && !is_producer) ? 1 : 0;      // 0: gradients, 1: hessians
+  const int pair = warp % kHistWarps;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kHistWarps * kWarpSmemBytes);
+  uint64_t* full = bars + pair * (2 * kStages);       // producer -> consumer: stage landed
+  uint64_t* empty = full + kStages;                   // consumer -> producer: stage consumed
+  if (!is_producer && comp == 0 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, 2); }   // two consumers release a slot
+  }
+  __syncthreads();
+
+  HistWork w;
+  if (!hist_work_setup(a, &w)) return;
+  unsigned char* wbase = smem + pair * kWarpSmemBytes;
+  unsigned char* ring = wbase + kWarpHistBytes;
+
+  if (is_producer) {
+    // ------------------------------------------------------------------ producer warp: stage rows
+    int slot = 0; unsigned phase = 0;
+    for (int round = 0; hist_round_valid(w, round); ++round) {
+      const HistItem it = hist_item(w, round, pair);
+      if (!it.valid) continue;
+      const int cg = it.cg, part = it.part;
+      const int r0 = part * w.per;
+      const int r1 = min(w.n, r0 + w.per);
+      if (r0 >= r1) continue;
+      const uint8_t* colbase = a.bins + static_cast<int64_t>(cg) * kColGroup;
+      const int half = (lane & 1) * 16;
+      const int32_t* ip = w.idx ? w.idx + w.begin : nullptr;
+      for (int p0 = r0; p0 < r1; p0 += kStageRows) {
+        if (a.use_tma && ip == nullptr && p0 + kStageRows <= r1) {
+          // contiguous rows (root of an un-bagged tree): ONE 2-D TMA tile (32 rows x 32 columns of the row-major
+          // matrix) + one bulk copy of the 32 (g,h) pairs per stage; both complete on the stage's mbarrier
+          mbar_wait(empty + slot, phase ^ 1);
+          unsigned char* sb = ring + slot * kStageBytes;
+          if (lane == 0) {
+            mbar_arrive_expect_tx(full + slot, kStageBytes);
+            tma_load_tile_2d(sb, &tmap, cg * kColGroup, p0, full + slot);
+            tma_load_1d(sb + kStageBinBytes, a.gh + p0, kStageRows * 8, full + slot);
+          } else {
+            mbar_arrive(full + slot);
+          }
+          if (++slot == kStages) { slot = 0; phase ^= 1; }
+          continue;
+        }
+        // row ids: lane -> (g,h) of row p0+lane; lane pair -> 32-byte bin segment of rows p0+lane/2 and +16
+        const int pa = p0 + (lane >> 1), pb = pa + 16, pg = p0 + lane;
+        int ra = -1, rb = -1, rg = -1;
+        if (pa < r1) ra = ip ? __ldg(ip + pa) : pa;
+        if (pb < r1) rb = ip ? __ldg(ip + pb) : pb;
+        if (pg < r1) rg = ip ? __ldg(ip + pg) : pg;
+        mbar_wait(empty + slot, phase ^ 1);           // the consumer released this ring slot
+        unsigned char* sb = ring + slot * kStageBytes;
+        if (ra >= 0) cp_async16(sb + (lane >> 1) * kColGroup + half, colbase + static_cast<int64_t>(ra) * a.pitch + half);
+        if (rb >= 0) cp_async16(sb + (16 + (lane >> 1)) * kColGroup + half, colbase + static_cast<int64_t>(rb) * a.pitch + half);
+        if (rg >= 0) cp_async8(sb + kStageBinBytes + lane * 8, a.gh + rg);
+        mbar_arrive_on_cp_async(full + slot);
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer warp: accumulate ONE component
+  unsigned char* tptr = wbase + comp * kCompTableBytes;             // this warp's [bin][lane] fp32 table
+  const unsigned tbase = static_cast<unsigned>(__cvta_generic_to_shared(reinterpret_cast<float*>(tptr) + lane));
+  const unsigned tbase0 = static_cast<unsigned>(__cvta_generic_to_shared(reinterpret_cast<float*>(smem + comp * kCompTableBytes) + lane));
+  const double scale = comp == 0 ? a.ctl->g_scale : a.ctl->h_scale;
+  int slot = 0; unsigned phase = 0;
+  for (int round = 0; hist_round_valid(w, round); ++round) {
+    const HistItem it = hist_item(w, round, pair);
+    const bool merge = it.merge;
+    if (!it.valid) continue;                                       // only possible when !merge
+    const int cg = it.cg, part = it.part;
+    const int r0 = part * w.per;
+    const int r1 = min(w.n, r0 + w.per);
+    if (r0 >= r1 && !merge) continue;
+    {
+      float4* z = reinterpret_cast<float4*>(tptr);
+#pragma unroll 8
+      for (int i = lane; i < kCompTableBytes / 16; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+
+    for (int p0 = r0; p0 < r1; p0 += kStageRows) {
+      mbar_wait(full + slot, phase);
+      const int cnt = min(kStageRows, r1 - p0);
+      const unsigned char* sb = ring + slot * kStageBytes;
+      const unsigned char* sbin = sb + lane;
+      const float* sq = reinterpret_cast<const float*>(sb + kStageBinBytes) + comp;      // q of row r = sq[2 r]
+      if (cnt == kStageRows) {
+        constexpr int K = kHistBatch;
+        uint32_t nb[K]; float nq[K];
+        unsigned addrN[K]; float sN[K];
+        auto fetch = [&](int r) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) nb[i] = sbin[(r + i) * 32];
+#pragma unroll
+          for (int i = 0; i < K; i += 2) {
+            const float4 t = *reinterpret_cast<const float4*>(sq - comp + 2 * (r + i));
+            nq[i] = comp ? t.y : t.x; nq[i + 1] = comp ? t.w : t.z;
+          }
+        };
+        fetch(0);
+        batch_prepare1<K>(tbase, nb, nq, addrN, sN);
+        if (K < kStageRows) fetch(K);
+#pragma unroll
+        for (int r = 0; r < kStageRows; r += K) {
+          unsigned addrC[K]; float sC[K], v[K];
+#pragma unroll
+          for (int i = 0; i < K; ++i) { addrC[i] = addrN[i]; sC[i] = sN[i]; }
+#pragma unroll
+          for (int i = 0; i < K; ++i) v[i] = lds32(addrC[i]);
+          if (r + K < kStageRows) {
+            batch_prepare1<K>(tbase, nb, nq, addrN, sN);
+            if (r + 2 * K < kStageRows) fetch(r + 2 * K);
+          }
+#pragma unroll
+          for (int i = 0; i < K; ++i) sts32(addrC[i], v[i] + sC[i]);
+        }
+      } else {
+        for (int r = 0; r < cnt; ++r) {
+          const uint32_t b = sbin[r * 32];
+          const unsigned addr = tbase + (b << 7);
+          sts32(addr, lds32(addr) + sq[2 * r]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + slot);
+      if (++slot == kStages) { slot = 0; phase ^= 1; }
+    }
+
+    // flush this component: fp32 partial -> int64 fixed point, RED.ADD.64 into the leaf's pool slot
+    unsigned long long* dst = a.pool + static_cast<int64_t>(w.slot) * a.slot_stride +
+                              (static_cast<int64_t>(cg) * kColGroup + lane) * (kBinsPerColumn * 2) + comp;
+    if (merge) {
+      consumer2_bar_sync();
+      const int b_lo = pair * 86, b_hi = min(kBinsPerColumn, b_lo + 86);
+#pragma unroll 2
+      for (int b = b_lo; b < b_hi; ++b) {
+        const float x = (lds32(tbase0 + (b << 7)) + lds32(tbase0 + kWarpSmemBytes + (b << 7))) + lds32(tbase0 + 2 * kWarpSmemBytes + (b << 7));
+        if (x != 0.f) atomicAdd(dst + 2 * b, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(x) * scale)));
+      }
+      consumer2_bar_sync();
+    } else {
+#pragma unroll 4
+      for (int b = 0; b < kBinsPerColumn; ++b) {
+        const float x = lds32(tbase + (b << 7));
+        if (x != 0.f) atomicAdd(dst + 2 * b, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(x) * scale)));
+      }
+      __syncwarp();
+    }
+  }
+}
+
 }  // namespace b200

@@ -140,6 +140,7 @@ class Learner {
     have_feature_mask_ = false;
     bag_count_ = -1;
     CUDA_CHECK(cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+    CUDA_CHECK(cudaFuncSetAttribute(k_hist2, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
     BuildTensorMap();
     inited_ = true;
     AllocTreeState();
@@ -326,7 +327,7 @@ class Learner {
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, stream_));
-    k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha, tmap_);
+    LaunchHist(ha);
     CUDA_CHECK(cudaEventRecord(e1, stream_));
     launches_ += 3;
     CUDA_CHECK(cudaGetLastError());
@@ -493,6 +494,14 @@ class Learner {
     have_tmap_ = (r == CUDA_SUCCESS);
   }
 
+  // reserved bit 3 selects the experimental split kernel k_hist2 (separate gradient / hessian consumer warps,
+  // 6 consumers per SM).  Measured 12 % SLOWER than k_hist on 4M x 1024 (5.45 vs 4.85 ms): the kernel is bound by
+  // shared-memory wavefronts, not by latency, and the split re-reads the staged bins — kept for the record.
+  void LaunchHist(const HistArgs& ha) {
+    if (cfg_.reserved & 8) k_hist2<<<num_sms_, kHist2Threads, kHistSmemBytes, stream_>>>(ha, tmap_);
+    else k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha, tmap_);
+  }
+
   // The fixed per-tree launch sequence (see file header).
   void EnqueueTree(const float* g, const float* h) {
     const int NL = params_.num_leaves;
@@ -531,7 +540,7 @@ class Learner {
         launches_ += 2;
         if (it == NL - 1) break;   // the tree is full: no need to look for further splits
       }
-      k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha, tmap_);
+      LaunchHist(ha);
       Stamp(kProfHist);
       if (row_mode) { k_hist_signal<<<1, 32, 0, stream_>>>(peers_, ctl_.p); ++launches_; }
       if (row_mode) k_scan<true><<<dim3(std::max(scan_blocks, 1), 1), kScanWarps * 32, 0, stream_>>>(sa);
