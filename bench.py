@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=500_000, help="row sample for the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-replicate", action="store_true",
+                    help="N>1: keep one copy of the partition columns across the box (the split's owner pushes go-left bits)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     rank, world, local = dist_env()
@@ -210,7 +212,8 @@ def main():
         wl["rows"] = args.rows
     config = {"workload": f"{args.workload}: {wl['rows']} rows x {wl['cols']} dense features, 255 bins, {wl['leaves']} leaves, "
                           f"L2 regression, min_data_in_leaf=20, lr=0.1",
-              "parallelism": f"feature-shard x{world}" if world > 1 else "single GPU",
+              "parallelism": (f"feature-shard x{world}" + ("" if args.no_replicate else ", partition columns replicated on every GPU"))
+              if world > 1 else "single GPU",
               "l2_flush": "inputs larger than L2 (bin matrix 10.24 GB >> 126 MB)" if wl["rows"] * wl["cols"] > 2e9 else
                           "bin matrix larger than L2 per GPU"}
 
@@ -246,7 +249,7 @@ def main():
     lay = lgb.Layout.identity(bins)
     lay.feat_real_index = np.arange(lo, hi, dtype=np.int32)
     cfg = lgb.Config(num_leaves=leaves, min_data_in_leaf=20, gpu_device_id=local, use_cuda_graph=True)
-    L = D.make_sharded_learner(lay, cfg, rank, world)
+    L = D.make_sharded_learner(lay, cfg, rank, world, replicate_columns=not args.no_replicate)
     B = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=True, learner=L)
     my_cols = hi - lo
 

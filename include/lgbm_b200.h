@@ -188,6 +188,16 @@ LGBMB200_EXPORT int LGBMB200_LearnerCommExport(LGBMB200_LearnerHandle h, uint8_t
 LGBMB200_EXPORT int LGBMB200_LearnerCommConnect(LGBMB200_LearnerHandle h, int32_t rank, int32_t world,
                                                 const uint8_t* all_handles, const int32_t* feature_offsets);
 
+/* Optional, after CommConnect: replicate every rank's column-major partition columns on every rank (costs
+ * total_columns x num_data bytes of HBM per GPU, filled by NVLink peer copies — the 180 GB of a B200 hold a
+ * 10M x 1024 matrix 17 times).  Every rank then computes the go-left flags of every split locally and the per-split
+ * flag push + wait disappears; only the 88-byte candidate exchange stays on the per-split path.  The reference's
+ * feature-parallel learner makes the same trade: every machine holds all the data so that Split() is local
+ * (src/treelearner/feature_parallel_tree_learner.cpp:23-35, docs/Features.rst "Feature Parallel in LightGBM").
+ * Bootstrap: CommExportColumns on every rank -> all-gather the handles -> CommShareColumns on every rank -> barrier. */
+LGBMB200_EXPORT int LGBMB200_LearnerCommExportColumns(LGBMB200_LearnerHandle h, uint8_t* handle_out_64);
+LGBMB200_EXPORT int LGBMB200_LearnerCommShareColumns(LGBMB200_LearnerHandle h, const uint8_t* all_column_handles);
+
 /* ---- Multi-GPU, row-shard (semantic model: DataParallelTreeLearner, reference
  * src/treelearner/data_parallel_tree_learner.cpp, and the reference's own num_gpu>1 mode,
  * src/boosting/cuda/nccl_gbdt_component.hpp:30-57).  Every learner is Init-ed with ITS row slice and ALL columns;

@@ -10,9 +10,36 @@ Two modes, matching the reference's `boosting_on_gpu_` switch (gbdt.cpp:110-135)
 """
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 from .tree_learner import B200TreeLearner, Config, DeviceArray, Layout, Tree
+
+
+_POOL: ThreadPoolExecutor | None = None
+
+
+def _host_threads() -> int:
+    try:
+        return max(1, min(16, len(os.sched_getaffinity(0))))
+    except AttributeError:
+        return max(1, min(16, os.cpu_count() or 1))
+
+
+def _parallel_rows(n: int, fn) -> None:
+    """Host objectives run row-chunked on a few threads, as the reference's OpenMP loops do
+    (regression_objective.hpp:127-142); numpy ufunc inner loops release the GIL."""
+    global _POOL
+    nt = _host_threads()
+    if nt == 1 or n < (1 << 18):
+        fn(0, n)
+        return
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=nt)
+    per = (n + nt - 1) // nt
+    list(_POOL.map(lambda t: fn(t * per, min(n, (t + 1) * per)), range(nt)))
 
 
 class B200Booster:
@@ -66,12 +93,16 @@ class B200Booster:
             tree = self.learner.train(self.d_grad, self.d_hess)
         else:
             if self.objective == "regression":
-                np.subtract(self.score, self.label, out=self.grad, casting="unsafe")   # g = score - label, h = 1
+                def l2(lo, hi):    # g = score - label, h = 1
+                    np.subtract(self.score[lo:hi], self.label[lo:hi], out=self.grad[lo:hi], casting="unsafe")
+                _parallel_rows(self.n, l2)
             else:
-                lab = np.where(self.label > 0, 1.0, -1.0)
-                resp = -lab * self.sigmoid / (1.0 + np.exp(lab * self.sigmoid * self.score))
-                self.grad[:] = resp
-                self.hess[:] = np.abs(resp) * (self.sigmoid - np.abs(resp))
+                def logloss(lo, hi):
+                    lab = np.where(self.label[lo:hi] > 0, 1.0, -1.0)
+                    resp = -lab * self.sigmoid / (1.0 + np.exp(lab * self.sigmoid * self.score[lo:hi]))
+                    self.grad[lo:hi] = resp
+                    self.hess[lo:hi] = np.abs(resp) * (self.sigmoid - np.abs(resp))
+                _parallel_rows(self.n, logloss)
             tree = self.learner.train(self.grad, self.hess)
         tree.shrinkage(self.lr)
         if tree.num_leaves > 1:

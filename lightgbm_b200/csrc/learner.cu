@@ -136,6 +136,7 @@ class Learner {
     CUDA_CHECK(cudaMemset(ctl_.p, 0, sizeof(Ctl)));      // exchange sequence numbers start at 0 on every rank
     peers_ = CommPeers{};
     peers_.rank = 0; peers_.world = 1; peers_.flags_stride = 0;
+    binsT_full_.release(); gmeta_.release();
     feature_used_.alloc(F_);
     have_feature_mask_ = false;
     bag_count_ = -1;
@@ -211,7 +212,7 @@ class Learner {
     for (int i = 0; i < n_leaves - 1; ++i) {
       const SplitRec& r = h_splits_[i];
       LGBMB200_Split& s = out->splits[i];
-      s.leaf = r.leaf; s.feature = r.feature + ((peers_.world > 1 && peers_.mode == 0) ? feature_offsets_[r.owner] : 0); s.threshold = r.threshold; s.default_left = r.default_left;
+      s.leaf = r.leaf; s.feature = r.feature + ((peers_.world > 1 && peers_.mode != 1) ? feature_offsets_[r.owner] : 0); s.threshold = r.threshold; s.default_left = r.default_left;
       s.left_count = r.left_count; s.right_count = r.right_count; s.gain = r.gain;
       s.left_sum_gradient = r.lsg; s.left_sum_hessian = r.lsh; s.left_output = r.lout;
       s.right_sum_gradient = r.rsg; s.right_sum_hessian = r.rsh; s.right_output = r.rout;
@@ -345,12 +346,20 @@ class Learner {
   void CommExport(uint8_t* handle_out) {
     REQUIRE(inited_, "Init first");
     const int64_t stride = ((static_cast<int64_t>(N_) + 31) / 32 * 4 + 255) / 256 * 256;
-    const size_t bytes = sizeof(CommBlock) + 2 * static_cast<size_t>(stride);
+    const size_t bytes = sizeof(CommBlock) + 2 * static_cast<size_t>(stride) + sizeof(FeatMeta) * static_cast<size_t>(F_);
     if (!comm_local_) {
       CUDA_CHECK(cudaMalloc(&comm_local_, bytes));
       CUDA_CHECK(cudaMemset(comm_local_, 0, bytes));
     }
     comm_stride_ = stride;
+    // shard shape + layout contract behind the flag words: what a peer needs to replicate my partition columns
+    {
+      CommBlock* cb = reinterpret_cast<CommBlock*>(comm_local_);
+      const int32_t shape[2] = {F_, C_};
+      CUDA_CHECK(cudaMemcpy(&cb->num_features, shape, sizeof(shape), cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(comm_meta_tail(cb, stride), feat_.p, sizeof(FeatMeta) * F_, cudaMemcpyDeviceToDevice));
+      CUDA_CHECK(cudaDeviceSynchronize());
+    }
     cudaIpcMemHandle_t hnd;
     CUDA_CHECK(cudaIpcGetMemHandle(&hnd, comm_local_));
     static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -371,6 +380,59 @@ class Learner {
       comm_opened_.push_back(p);
     }
     feature_offsets_.assign(feature_offsets, feature_offsets + world + 1);
+    InvalidateGraph();
+  }
+
+  // feature-shard, optional: replicate every rank's column-major partition columns on every rank
+  // (C_total x N bytes of HBM per GPU), so that each rank computes the go-left flags of EVERY split itself and the
+  // per-split flag push + wait over NVLink disappears.  Export first, all-gather the handles, then share; the caller
+  // must barrier after CommShareColumns (peers copy out of this rank's buffer).
+  void CommExportColumns(uint8_t* handle_out) {
+    REQUIRE(inited_ && binsT_.p != nullptr, "Init (with the column-major copy enabled) first");
+    cudaIpcMemHandle_t hnd;
+    CUDA_CHECK(cudaIpcGetMemHandle(&hnd, binsT_.p));
+    std::memcpy(handle_out, &hnd, 64);
+  }
+  void CommShareColumns(const uint8_t* column_handles) {
+    REQUIRE(peers_.world > 1 && peers_.mode != 1, "CommConnect (feature-shard) first");
+    REQUIRE(binsT_.p != nullptr, "the column-major copy is disabled (reserved bit 0)");
+    CUDA_CHECK(cudaStreamSynchronize(stream_));        // my own transpose has finished
+    const int W = peers_.world;
+    std::vector<int32_t> nf(W), nc(W), col_off(W + 1, 0), f_off(W + 1, 0);
+    for (int r = 0; r < W; ++r) {
+      int32_t shape[2];
+      CUDA_CHECK(cudaMemcpy(shape, &peers_.block[r]->num_features, sizeof(shape), cudaMemcpyDefault));
+      nf[r] = shape[0]; nc[r] = shape[1];
+      REQUIRE(nf[r] >= 0 && nc[r] >= 1, "peer CommBlock carries no shard shape (CommExport on every rank first)");
+      col_off[r + 1] = col_off[r] + nc[r]; f_off[r + 1] = f_off[r] + nf[r];
+    }
+    REQUIRE(nf[peers_.rank] == F_ && nc[peers_.rank] == C_, "own shard shape mismatch");
+    binsT_full_.alloc(static_cast<size_t>(col_off[W]) * N_);
+    std::vector<FeatMeta> gm(static_cast<size_t>(std::max(f_off[W], 1)));
+    std::vector<void*> opened;
+    for (int r = 0; r < W; ++r) {
+      const uint8_t* src = binsT_.p;
+      if (r != peers_.rank) {
+        cudaIpcMemHandle_t hnd;
+        std::memcpy(&hnd, column_handles + 64 * r, 64);
+        void* p = nullptr;
+        CUDA_CHECK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+        opened.push_back(p);
+        src = static_cast<const uint8_t*>(p);
+      }
+      CUDA_CHECK(cudaMemcpyAsync(binsT_full_.p + static_cast<size_t>(col_off[r]) * N_, src, static_cast<size_t>(nc[r]) * N_,
+                                 cudaMemcpyDefault, stream_));
+      if (nf[r] > 0)
+        CUDA_CHECK(cudaMemcpy(gm.data() + f_off[r], comm_meta_tail(peers_.block[r], comm_stride_), sizeof(FeatMeta) * nf[r], cudaMemcpyDefault));
+      for (int f = 0; f < nf[r]; ++f) gm[f_off[r] + f].col += col_off[r];
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (void* p : opened) cudaIpcCloseMemHandle(p);
+    gmeta_.alloc(gm.size());
+    CUDA_CHECK(cudaMemcpy(gmeta_.p, gm.data(), sizeof(FeatMeta) * gm.size(), cudaMemcpyHostToDevice));
+    peers_.mode = 2;
+    peers_.gmeta = gmeta_.p;
+    for (int r = 0; r < W; ++r) peers_.feat_off[r] = f_off[r];
     InvalidateGraph();
   }
 
@@ -516,7 +578,7 @@ class Learner {
     const int scan_blocks = ((row_mode ? peers_.f_cnt : F_) + kScanWarps - 1) / kScanWarps;
     SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p, block_best_.p, scan_blocks, splittable_.p, splittable_new_.p, peers_};
     PartArgs pt;
-    pt.bins = bins_.p; pt.binsT = binsT_.p; pt.num_data = N_; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flag_words = reinterpret_cast<uint32_t*>(flags_.p);
+    pt.bins = bins_.p; pt.binsT = peers_.mode == 2 ? binsT_full_.p : binsT_.p; pt.num_data = N_; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flag_words = reinterpret_cast<uint32_t*>(flags_.p);
     pt.block_left = block_left_.p; pt.leaves = leaves_.p; pt.ctl = ctl_.p; pt.splits = splits_.p; pt.params = params_;
     pt.peers = peers_;
     prof_n_ = 0;
@@ -634,6 +696,8 @@ class Learner {
   int64_t pitch_ = 0, slot_stride_ = 0;
   int part_blocks_ = 296, prep_blocks_ = 296;
   DevBuf<FeatMeta> feat_;
+  DevBuf<uint8_t> binsT_full_;     // mode 2: [sum of every rank's columns][N]
+  DevBuf<FeatMeta> gmeta_;
   DevBuf<uint8_t> bins_, binsT_, flags_, feature_used_, splittable_, splittable_new_;
   DevBuf<BlockBest> block_best_;
   DevBuf<float2> gh_;
@@ -798,6 +862,18 @@ int LGBMB200_LearnerCommConnect(LGBMB200_LearnerHandle h, int32_t rank, int32_t 
   API_BEGIN();
   if (!h || !all_handles || !feature_offsets) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->CommConnect(rank, world, all_handles, feature_offsets);
+  API_END();
+}
+int LGBMB200_LearnerCommExportColumns(LGBMB200_LearnerHandle h, uint8_t* handle_out_64) {
+  API_BEGIN();
+  REQUIRE(h && handle_out_64, "null argument");
+  static_cast<Learner*>(h)->CommExportColumns(handle_out_64);
+  API_END();
+}
+int LGBMB200_LearnerCommShareColumns(LGBMB200_LearnerHandle h, const uint8_t* all_column_handles) {
+  API_BEGIN();
+  REQUIRE(h && all_column_handles, "null argument");
+  static_cast<Learner*>(h)->CommShareColumns(all_column_handles);
   API_END();
 }
 int LGBMB200_LearnerCommExportPool(LGBMB200_LearnerHandle h, uint8_t* handle_out_64) {

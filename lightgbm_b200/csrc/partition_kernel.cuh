@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
   const int me = a.peers.rank;
-  const int W = a.peers.mode == 1 ? 1 : a.peers.world;   // row-shard: every rank flags its own rows, no push
+  // row-shard: every rank flags its own rows; mode 2: every rank holds a copy of every partition column and
+  // computes the flags of every split itself (no push, no wait)
+  const int W = a.peers.mode == 0 ? a.peers.world : 1;
   if (W > 1 && c->cur_owner != me) return;        // feature-shard: only the rank that holds the split column computes flags
   const int n = c->cur_count, begin = c->cur_begin;
   const int32_t* src = (c->cur_buf ? a.idx1 : a.idx0) + begin;

@@ -586,7 +586,8 @@ __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
         c->cur_leaf = best_leaf; c->cur_begin = L.begin; c->cur_count = L.lcount; c->cur_buf = L.buf;
         c->cur_feature = L.best.feature; c->cur_threshold = L.best.threshold; c->cur_default_left = L.best.default_left;
         c->cur_owner = a.peers.mode == 1 ? a.peers.rank : L.best.owner;   // row-shard: every rank holds every column
-        if (c->cur_owner == a.peers.rank) c->cur_meta = a.feat[L.best.feature];   // only the owner holds the column
+        if (a.peers.mode == 2) c->cur_meta = a.peers.gmeta[a.peers.feat_off[L.best.owner] + L.best.feature];   // replicated columns
+        else if (c->cur_owner == a.peers.rank) c->cur_meta = a.feat[L.best.feature];   // only the owner holds the column
         c->part_blocks_done = 0;
         c->flag_seq += 1;          // sequence number of the flag push that applies this split
       }

@@ -98,25 +98,33 @@ struct CommBlock {
   Cand mail[2][kMaxRanks][2];                 // [parity][source rank][smaller, larger] best candidates
   unsigned long long mail_seq[2][kMaxRanks];  // written by the source rank after its payload
   unsigned long long flags_seq[2];            // written by the split's owner after pushing the go-left flags
-  unsigned long long pad[6];
+  int32_t num_features, num_columns;          // this rank's shard shape (read by the peers in CommShareColumns)
+  unsigned long long pad[5];
   // row-shard mode
   unsigned long long hist_seq[kMaxRanks];     // hist_seq[r]: rank r's local histogram #seq is complete
   double misc[2][kMaxRanks][8];               // small all-gather payloads (root sums / left counts)
   unsigned long long misc_seq[2][kMaxRanks];
   int32_t blk_left[2][1024];                  // feature-shard: the owner's per-block left counts, pushed with the flags
-  // followed by: uint32_t flag_words[2][ceil(num_data/32)] (bit-packed go-left flags)
+  // followed by: uint32_t flag_words[2][ceil(num_data/32)] (bit-packed go-left flags),
+  //              then FeatMeta[num_features] (this rank's layout contract, for replicated partition columns)
 };
 struct CommPeers {
   CommBlock* block[kMaxRanks];                // block[r] = rank r's CommBlock (own entry = local pointer)
   int32_t rank, world;
-  int32_t mode;                               // 0 = feature-shard (all rows x column slice), 1 = row-shard (row slice x all columns)
+  int32_t mode;                               // 0 = feature-shard (all rows x column slice), 1 = row-shard (row slice x all columns),
+                                              // 2 = feature-shard with every rank's partition columns replicated locally
   int32_t f_lo, f_cnt;                        // row-shard: the feature slice this rank reduces and scans
   int32_t pad;
   long long* pool[kMaxRanks];                 // row-shard: every rank's histogram pool (peer-mapped)
   int64_t flags_stride;                       // bytes between the two flag-word buffers
+  const FeatMeta* gmeta;                      // mode 2: every rank's FeatMeta, columns re-based into the replicated column-major copy
+  int32_t feat_off[kMaxRanks];                // mode 2: first gmeta entry of rank r
 };
 __host__ __device__ inline uint32_t* comm_flag_words(CommBlock* b, int parity, int64_t stride) {
   return reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(b + 1) + parity * stride);
+}
+__host__ __device__ inline FeatMeta* comm_meta_tail(CommBlock* b, int64_t stride) {
+  return reinterpret_cast<FeatMeta*>(reinterpret_cast<uint8_t*>(b + 1) + 2 * stride);
 }
 
 }  // namespace b200

@@ -55,9 +55,14 @@ def gather_bytes(payload: bytes, rank: int, world: int) -> list[bytes]:
     return out
 
 
-def make_sharded_learner(shard_layout: Layout, config: Config, rank: int, world: int, gather=gather_bytes) -> B200TreeLearner:
+def make_sharded_learner(shard_layout: Layout, config: Config, rank: int, world: int, gather=gather_bytes,
+                         replicate_columns: bool = True) -> B200TreeLearner:
     """shard_layout: this rank's column slice (Layout.column_slice of the full layout, or generated directly).
-    Returns a learner whose Train() grows the same tree on every rank, with global inner-feature ids."""
+    Returns a learner whose Train() grows the same tree on every rank, with global inner-feature ids.
+    replicate_columns: also hold a column-major copy of EVERY rank's columns (total_columns x num_data bytes per
+    GPU, filled over NVLink) so that the row partition of every split is computed locally — the reference's
+    feature-parallel trade (every worker holds the full data, docs/Features.rst:109-125).  False keeps one copy of
+    the matrix across the box; the split's owner then pushes the go-left bits to its peers."""
     L = B200TreeLearner(config)
     L.init(shard_layout, is_constant_hessian=False)
     if world > 1:
@@ -65,6 +70,10 @@ def make_sharded_learner(shard_layout: Layout, config: Config, rank: int, world:
         handles = gather(handle, rank, world)
         counts = [int(x) for x in gather(str(shard_layout.num_features).encode(), rank, world)]
         L.comm_connect(rank, world, b"".join(handles), feature_offsets(counts))
+        if replicate_columns:
+            cols = gather(L.comm_export_columns(), rank, world)
+            L.comm_share_columns(b"".join(cols))
+            gather(b"done", rank, world)      # barrier: nobody re-Inits while a peer still copies out of its buffer
     return L
 
 

@@ -325,6 +325,16 @@ class B200TreeLearner:
         hb = (C.c_uint8 * len(all_handles)).from_buffer_copy(all_handles)
         check(lib().LGBMB200_LearnerCommConnect(self.handle, C.c_int32(rank), C.c_int32(world), hb, _p(off)))
 
+    def comm_export_columns(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        check(lib().LGBMB200_LearnerCommExportColumns(self.handle, buf))
+        return bytes(buf)
+
+    def comm_share_columns(self, all_column_handles: bytes) -> None:
+        """Replicate every rank's partition columns locally (NVLink peer copies); barrier afterwards."""
+        hb = (C.c_uint8 * len(all_column_handles)).from_buffer_copy(all_column_handles)
+        check(lib().LGBMB200_LearnerCommShareColumns(self.handle, hb))
+
     def comm_export_pool(self) -> bytes:
         buf = (C.c_uint8 * 64)()
         check(lib().LGBMB200_LearnerCommExportPool(self.handle, buf))

@@ -46,7 +46,7 @@ def main():
         L = D.make_row_sharded_learner(shard, cfg, rank, world)
         gl, hl = g[r0:r1], h[r0:r1]
     else:
-        L = D.make_sharded_learner(shard, cfg, rank, world)
+        L = D.make_sharded_learner(shard, cfg, rank, world, replicate_columns=(mode != "gpupush"))
         gl, hl = g, h
     trees = []
     for it in range(3):

@@ -66,11 +66,12 @@ def _gpu_count():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["gpu", "gpupush"])      # replicated partition columns / owner pushes the go-left bits
 @pytest.mark.parametrize("n,f,leaves", [(30000, 96, 31), (20000, 40, 15)])
-def test_feature_shard_world2_matches_single_gpu(n, f, leaves):
+def test_feature_shard_world2_matches_single_gpu(n, f, leaves, mode):
     if _gpu_count() < 2:
         pytest.skip("needs 2 GPUs")
-    outs = launch(2, ["gpu", n, f, leaves])
+    outs = launch(2, [mode, n, f, leaves])
     a, b = outs
     for ta, tb in zip(a["trees"], b["trees"]):
         assert ta == tb                      # every rank grows the identical tree, bit for bit
