@@ -316,12 +316,15 @@ def main():
         for _ in range(args.warmup):
             H.update()
         barrier()
+        for k in H.host_ms:
+            H.host_ms[k] = 0.0
         t0 = time.time()
         for _ in range(args.steps):
             H.update()
         barrier()
         dt = max_over_ranks((time.time() - t0) / args.steps)
         e2e = {"value": 1.0 / dt, "unit": "iters/sec", "h2d_bytes_per_step": rows * 8, "d2h_bytes_per_step": rows * 4 + 4096,
+               "ms_per_step": dt * 1e3, "host_ms_per_step": {k: v / args.steps for k, v in H.host_ms.items()},
                "note": "host grad/hess (pinned) -> H2D inside Train; per-row leaf ids D2H inside AddPredictionToScore; "
                        "host computes g = score - y and score += leaf_value[leaf_id]"}
 

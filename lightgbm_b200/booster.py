@@ -11,6 +11,7 @@ Two modes, matching the reference's `boosting_on_gpu_` switch (gbdt.cpp:110-135)
 from __future__ import annotations
 
 import os
+import time
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -55,6 +56,7 @@ class B200Booster:
         self.device_resident = device_resident
         self.label = np.ascontiguousarray(label, dtype=np.float32)
         self.trees: list[Tree] = []
+        self.host_ms = {"gradients": 0.0, "train": 0.0, "score": 0.0}   # wall-clock split of update(), host mode
         assert objective in ("regression", "binary")
         self.objective, self.sigmoid = objective, float(sigmoid)
         # BoostFromAverage (gbdt.cpp:328-350): RegressionL2loss::BoostFromScore = mean label;
@@ -92,6 +94,7 @@ class B200Booster:
                 self.learner.binary_gradients(self.d_score, self.d_label, self.d_grad, self.d_hess, self.n, self.sigmoid)
             tree = self.learner.train(self.d_grad, self.d_hess)
         else:
+            t0 = time.perf_counter()
             if self.objective == "regression":
                 def l2(lo, hi):    # g = score - label, h = 1
                     np.subtract(self.score[lo:hi], self.label[lo:hi], out=self.grad[lo:hi], casting="unsafe")
@@ -103,13 +106,19 @@ class B200Booster:
                     self.grad[lo:hi] = resp
                     self.hess[lo:hi] = np.abs(resp) * (self.sigmoid - np.abs(resp))
                 _parallel_rows(self.n, logloss)
+            t1 = time.perf_counter()
             tree = self.learner.train(self.grad, self.hess)
+            t2 = time.perf_counter()
+            self.host_ms["gradients"] += (t1 - t0) * 1e3
+            self.host_ms["train"] += (t2 - t1) * 1e3
         tree.shrinkage(self.lr)
         if tree.num_leaves > 1:
             if self.device_resident:
                 self.learner.add_prediction_to_score(tree, self.d_score)
             else:
+                t3 = time.perf_counter()
                 self.learner.add_prediction_to_score(tree, self.score)
+                self.host_ms["score"] += (time.perf_counter() - t3) * 1e3
         if not self.trees and self.init_score != 0.0:
             tree.add_bias(self.init_score)     # gbdt.cpp:424-427 (first tree carries the average)
         self.trees.append(tree)

@@ -33,6 +33,26 @@ def main():
         dist.destroy_process_group()
         return
 
+    if mode.startswith("golden"):
+        # a fixture read out of a real reference Dataset: EFB bundles, most-freq-bin elision, missing types —
+        # the sharded learners must reproduce the reference's own tree (mode goldenpush: no column replication)
+        import golden_io
+        gd = golden_io.Golden(sys.argv[2])
+        full = lgb.Layout.from_attrs(gd.layout)
+        n, f = full.num_data, full.num_columns
+        g, h = gd.grad.astype(np.float32), gd.hess.astype(np.float32)
+        cfg = lgb.Config(**gd.params, gpu_device_id=int(os.environ.get("LOCAL_RANK", rank)))
+        lo, hi = D.shard_columns(f, world)[rank]
+        shard = full.column_slice(lo, hi) if hi > lo else D.empty_shard(n, rank)
+        L = D.make_sharded_learner(shard, cfg, rank, world, replicate_columns=(mode == "golden"))
+        t = L.train(g, h)
+        ok = golden_io.check_against_reference(t, gd, exact_values=False)
+        print("JSON" + json.dumps(dict(rank=rank, splits_checked=int(ok), num_leaves=int(t.num_leaves),
+                                       feature=t.splits["feature"].tolist(), threshold=t.splits["threshold"].tolist())))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
     n, f, leaves = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     bins, y, g, h = synth_identity(n, f, seed=99)
     full = lgb.Layout.identity(bins)

@@ -84,6 +84,19 @@ def test_feature_shard_world2_matches_single_gpu(n, f, leaves, mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["golden", "goldenpush"])
+@pytest.mark.parametrize("name", ["efb_bundled", "mixed_zero_as_missing", "mixed_missing_binary"])
+def test_feature_shard_world2_reproduces_reference_tree(name, mode):
+    """Column-sharded over 2 GPUs, a fixture with EFB bundles / elided most-frequent bins / missing types must still
+    give the tree the unmodified reference grew (tests/golden/*.npz)."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    a, b = launch(2, [mode, name])
+    assert a["feature"] == b["feature"] and a["threshold"] == b["threshold"] and a["num_leaves"] == b["num_leaves"]
+    assert a["splits_checked"] >= min(3, a["num_leaves"] - 1)     # same bar as the single-GPU golden test (near ties may diverge later)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,f,leaves", [(30000, 28, 31), (20001, 40, 15)])
 def test_row_shard_world2_matches_single_gpu(n, f, leaves):
     if _gpu_count() < 2:
