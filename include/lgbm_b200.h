@@ -113,7 +113,9 @@ LGBMB200_EXPORT const char* LGBMB200_GetLastError(void);
 LGBMB200_EXPORT int LGBMB200_LearnerCreate(const LGBMB200_Config* config, LGBMB200_LearnerHandle* out);
 
 /* TreeLearner::Init(const Dataset*, bool is_constant_hessian) — reference tree_learner.h:38;
- * cuda_single_gpu_tree_learner.cpp:36-93.  Copies the bin matrix (host pointer) to HBM. */
+ * cuda_single_gpu_tree_learner.cpp:36-93.  Copies the bin matrix (host pointer) to HBM.
+ * is_constant_hessian != 0 promises that every hessian passed to Train equals hessians[0] (the objective's
+ * IsConstantHessian(), gbdt.cpp:92); Train then reads only hessians[0] from a host buffer. */
 LGBMB200_EXPORT int LGBMB200_LearnerInit(LGBMB200_LearnerHandle h, const LGBMB200_Layout* layout,
                                          const uint8_t* bins_host, int32_t is_constant_hessian);
 

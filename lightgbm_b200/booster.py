@@ -49,7 +49,9 @@ class B200Booster:
                  pinned: bool = False, objective: str = "regression", sigmoid: float = 1.0):
         if learner is None:
             learner = B200TreeLearner(config)
-            learner.init(layout, is_constant_hessian=True)
+            # RegressionL2loss::IsConstantHessian() is true for unweighted L2 (regression_objective.hpp:165-171);
+            # BinaryLogloss is not.  update_custom() on such a learner must pass equal hessians too.
+            learner.init(layout, is_constant_hessian=(objective == "regression"))
         self.learner = learner
         self.n = layout.num_data
         self.lr = float(learning_rate)

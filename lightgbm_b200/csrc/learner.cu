@@ -82,7 +82,7 @@ class Learner {
     if (inited_ && leaves_changed) AllocTreeState();
   }
 
-  void Init(const LGBMB200_Layout& lay, const uint8_t* bins_host, int /*is_constant_hessian*/) {
+  void Init(const LGBMB200_Layout& lay, const uint8_t* bins_host, int is_constant_hessian) {
     REQUIRE(lay.num_data > 0 && lay.num_columns > 0 && lay.num_features > 0, "empty dataset");
     if (cfg_.gpu_device_id >= 0) { CUDA_CHECK(cudaSetDevice(cfg_.gpu_device_id)); }
     CUDA_CHECK(cudaGetDevice(&device_));
@@ -127,6 +127,7 @@ class Learner {
     }
     gh_.alloc(N_); idx0_.alloc(N_); idx1_.alloc(N_); flags_.alloc((static_cast<size_t>(N_) + 31) / 32 * 4 + 256);
     grad_stage_.alloc(N_); hess_stage_.alloc(N_);
+    const_hess_ = is_constant_hessian != 0; hess_fill_valid_ = false;
     part_blocks_ = num_sms_ * 2;
     if (part_blocks_ > 1024) part_blocks_ = 1024;
     block_left_.alloc(part_blocks_);
@@ -176,7 +177,19 @@ class Learner {
     const float* g = grad; const float* h = hess;
     if (!on_device) {
       CUDA_CHECK(cudaMemcpyAsync(grad_stage_.p, grad, sizeof(float) * N_, cudaMemcpyHostToDevice, stream_));
-      CUDA_CHECK(cudaMemcpyAsync(hess_stage_.p, hess, sizeof(float) * N_, cudaMemcpyHostToDevice, stream_));
+      if (const_hess_) {
+        // Init(..., is_constant_hessian = true): every hessian equals hessians[0] (the reference reads only that
+        // element too, dataset.cpp:1430-1437) => 4 B/row cross PCIe, not 8
+        const float h0 = hess[0];
+        if (!hess_fill_valid_ || h0 != hess_fill_) {
+          k_fill_f32<<<num_sms_ * 4, 256, 0, stream_>>>(hess_stage_.p, h0, N_);
+          ++launches_;
+          CUDA_CHECK(cudaGetLastError());
+          hess_fill_ = h0; hess_fill_valid_ = true;
+        }
+      } else {
+        CUDA_CHECK(cudaMemcpyAsync(hess_stage_.p, hess, sizeof(float) * N_, cudaMemcpyHostToDevice, stream_));
+      }
       g = grad_stage_.p; h = hess_stage_.p;
     }
     const int NL = params_.num_leaves;
@@ -240,19 +253,40 @@ class Learner {
       CUDA_CHECK(cudaStreamSynchronize(stream_));
       return;
     }
-    // host score (the link-seam path, boosting_on_gpu_ == false): ship 4 B/row of leaf ids, add on the host
-    FetchLeafIndex();
+    // host score (the link-seam path, boosting_on_gpu_ == false): ship the per-row leaf ids, add on the host.
+    // Up to 255 leaves the ids travel as one byte per row (0xFF = row outside the bag), else as int32.
+    const bool narrow = num_leaves <= 255;
+    if (narrow) FetchLeafIndex8(); else FetchLeafIndex();
     const int32_t* rl = h_row_leaf_;
-    const int nt = std::max(1, std::min(8, static_cast<int>(std::thread::hardware_concurrency())));
+    const uint8_t* rl8 = h_row_leaf8_;
+    const int hw = static_cast<int>(std::thread::hardware_concurrency());
+    const int nt = std::max(1, std::min(32, hw / std::max(1, peers_.world)));
     std::vector<std::thread> th;
     const int64_t per = (static_cast<int64_t>(N_) + nt - 1) / nt;
     for (int t = 0; t < nt; ++t) {
       th.emplace_back([=]() {
         const int64_t lo = t * per, hi = std::min<int64_t>(N_, lo + per);
-        for (int64_t i = lo; i < hi; ++i) { const int l = rl[i]; if (l >= 0) score[i] += leaf_value[l]; }
+        if (narrow) { for (int64_t i = lo; i < hi; ++i) { const int l = rl8[i]; if (l != 0xFF) score[i] += leaf_value[l]; } }
+        else { for (int64_t i = lo; i < hi; ++i) { const int l = rl[i]; if (l >= 0) score[i] += leaf_value[l]; } }
       });
     }
     for (auto& t : th) t.join();
+  }
+
+  void FetchLeafIndex8() {
+    REQUIRE(inited_ && last_num_leaves_ > 0 && last_num_leaves_ <= 255, "Train first (<= 255 leaves)");
+    if (row_leaf8_.n < static_cast<size_t>(N_)) {
+      row_leaf8_.alloc(N_);
+      if (h_row_leaf8_) cudaFreeHost(h_row_leaf8_);
+      CUDA_CHECK(cudaMallocHost(&h_row_leaf8_, static_cast<size_t>(N_)));
+    }
+    if (bag_count_ >= 0) CUDA_CHECK(cudaMemsetAsync(row_leaf8_.p, 0xFF, static_cast<size_t>(N_), stream_));
+    dim3 grid(std::max(1, std::min(num_sms_ * 4, (N_ + 255) / 256)), last_num_leaves_);
+    k_leaf_index<uint8_t><<<grid, 256, 0, stream_>>>(leaves_.p, idx0_.p, idx1_.p, row_leaf8_.p);
+    ++launches_;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(h_row_leaf8_, row_leaf8_.p, static_cast<size_t>(N_), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
   }
 
   void FetchLeafIndex() {
@@ -260,7 +294,7 @@ class Learner {
     if (row_leaf_.n < static_cast<size_t>(N_)) { row_leaf_.alloc(N_); CUDA_CHECK(cudaMallocHost(&h_row_leaf_, sizeof(int32_t) * N_)); }
     if (bag_count_ >= 0) CUDA_CHECK(cudaMemsetAsync(row_leaf_.p, 0xFF, sizeof(int32_t) * N_, stream_));
     dim3 grid(std::max(1, std::min(num_sms_ * 4, (N_ + 255) / 256)), last_num_leaves_);
-    k_leaf_index<<<grid, 256, 0, stream_>>>(leaves_.p, idx0_.p, idx1_.p, row_leaf_.p);
+    k_leaf_index<int32_t><<<grid, 256, 0, stream_>>>(leaves_.p, idx0_.p, idx1_.p, row_leaf_.p);
     ++launches_;
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(h_row_leaf_, row_leaf_.p, sizeof(int32_t) * N_, cudaMemcpyDeviceToHost, stream_));
@@ -307,6 +341,7 @@ class Learner {
     if (!on_device) {
       CUDA_CHECK(cudaMemcpyAsync(grad_stage_.p, grad, sizeof(float) * N_, cudaMemcpyHostToDevice, stream_));
       CUDA_CHECK(cudaMemcpyAsync(hess_stage_.p, hess, sizeof(float) * N_, cudaMemcpyHostToDevice, stream_));
+      hess_fill_valid_ = false;
       g = grad_stage_.p; h = hess_stage_.p;
     }
     // prep with "no bagging" semantics over all rows: packs gh and sets the fixed-point scales
@@ -683,6 +718,7 @@ class Learner {
     comm_opened_.clear();
     if (comm_local_) { cudaFree(comm_local_); comm_local_ = nullptr; }
     if (h_row_leaf_) { cudaFreeHost(h_row_leaf_); h_row_leaf_ = nullptr; }
+    if (h_row_leaf8_) { cudaFreeHost(h_row_leaf8_); h_row_leaf8_ = nullptr; }
     if (t0_) { cudaEventDestroy(t0_); cudaEventDestroy(t1_); t0_ = nullptr; }
     if (stream_) { cudaStreamDestroy(stream_); stream_ = nullptr; }
   }
@@ -702,9 +738,13 @@ class Learner {
   DevBuf<BlockBest> block_best_;
   DevBuf<float2> gh_;
   DevBuf<float> grad_stage_, hess_stage_;
+  bool const_hess_ = false, hess_fill_valid_ = false;
+  float hess_fill_ = 0.f;
   DevBuf<double> leaf_value_dev_;
   DevBuf<int32_t> idx0_, idx1_, block_left_, bag_, row_leaf_;
   int32_t* h_row_leaf_ = nullptr;
+  DevBuf<uint8_t> row_leaf8_;
+  uint8_t* h_row_leaf8_ = nullptr;
   cudaEvent_t t0_ = nullptr, t1_ = nullptr;
   DevBuf<PartialSum> partials_;
   CommPeers peers_{};

@@ -451,10 +451,15 @@ __global__ void __launch_bounds__(256) k_add_score(const ScoreArgs a) {
 }
 
 // row -> leaf id of the final partition (one grid row per leaf)
-__global__ void __launch_bounds__(256) k_leaf_index(const Leaf* leaves, const int32_t* idx0, const int32_t* idx1, int32_t* row_leaf) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_leaf_index(const Leaf* leaves, const int32_t* idx0, const int32_t* idx1, T* row_leaf) {
   const Leaf& L = leaves[blockIdx.y];
   const int32_t* idx = (L.buf ? idx1 : idx0) + L.begin;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < L.lcount; i += gridDim.x * 256) row_leaf[idx[i]] = blockIdx.y;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < L.lcount; i += gridDim.x * 256) row_leaf[idx[i]] = static_cast<T>(blockIdx.y);
+}
+
+__global__ void k_fill_f32(float* p, float v, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
 
 // L2 objective gradients (regression_objective.hpp:127-142, unweighted): g = score - label, h = 1

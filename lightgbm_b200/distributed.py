@@ -56,7 +56,7 @@ def gather_bytes(payload: bytes, rank: int, world: int) -> list[bytes]:
 
 
 def make_sharded_learner(shard_layout: Layout, config: Config, rank: int, world: int, gather=gather_bytes,
-                         replicate_columns: bool = True) -> B200TreeLearner:
+                         replicate_columns: bool = True, is_constant_hessian: bool = False) -> B200TreeLearner:
     """shard_layout: this rank's column slice (Layout.column_slice of the full layout, or generated directly).
     Returns a learner whose Train() grows the same tree on every rank, with global inner-feature ids.
     replicate_columns: also hold a column-major copy of EVERY rank's columns (total_columns x num_data bytes per
@@ -64,7 +64,7 @@ def make_sharded_learner(shard_layout: Layout, config: Config, rank: int, world:
     feature-parallel trade (every worker holds the full data, docs/Features.rst:109-125).  False keeps one copy of
     the matrix across the box; the split's owner then pushes the go-left bits to its peers."""
     L = B200TreeLearner(config)
-    L.init(shard_layout, is_constant_hessian=False)
+    L.init(shard_layout, is_constant_hessian=is_constant_hessian)
     if world > 1:
         handle = L.comm_export()
         handles = gather(handle, rank, world)
