@@ -55,7 +55,8 @@ typedef struct {
                                        partition kernels (saves num_data*num_columns bytes of HBM);
                                        bit 1: do NOT stage contiguous (root) histogram passes with TMA tile copies;
                                        bit 2: legacy column-group-major work mapping in the histogram kernel;
-                                       bit 3: experimental split gradient/hessian histogram kernel (slower; A/B only) */
+                                       bit 3: experimental split gradient/hessian histogram kernel (slower; A/B only);
+                                       bit 4: programmatic dependent launch between the kernels of the per-split chain */
 } LGBMB200_Config;
 
 /*

@@ -9,6 +9,14 @@
 
 namespace b200 {
 
+// Programmatic dependent launch (LGBMB200_Config.reserved bit 4): every kernel of the per-split chain first waits
+// for its predecessor grid (a no-op when the launch carries no programmatic edge), then lets ITS successor's CTAs
+// be scheduled, so that the next kernel's launch latency overlaps this kernel's execution.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

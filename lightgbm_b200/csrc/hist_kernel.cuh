@@ -28,6 +28,7 @@
 #pragma once
 #include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 
+#include "comm.cuh"
 #include "types.cuh"
 
 namespace b200 {
@@ -259,6 +260,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
     for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, 1); }
   }
   __syncthreads();
+  pdl_enter();          // barrier init above overlaps the predecessor's tail; everything below reads its results
 
   HistWork w;
   if (!hist_work_setup(a, &w)) return;
@@ -467,6 +469,7 @@ __global__ void __launch_bounds__(kHist2Threads, 1) k_hist2(const HistArgs a, co
     for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, 2); }   // two consumers release a slot
   }
   __syncthreads();
+  pdl_enter();          // barrier init above overlaps the predecessor's tail; everything below reads its results
 
   HistWork w;
   if (!hist_work_setup(a, &w)) return;

@@ -594,9 +594,24 @@ class Learner {
   // reserved bit 3 selects the experimental split kernel k_hist2 (separate gradient / hessian consumer warps,
   // 6 consumers per SM).  Measured 12 % SLOWER than k_hist on 4M x 1024 (5.45 vs 4.85 ms): the kernel is bound by
   // shared-memory wavefronts, not by latency, and the split re-reads the staged bins — kept for the record.
-  void LaunchHist(const HistArgs& ha) {
-    if (cfg_.reserved & 8) k_hist2<<<num_sms_, kHist2Threads, kHistSmemBytes, stream_>>>(ha, tmap_);
-    else k_hist<<<num_sms_, kHistThreads, kHistSmemBytes, stream_>>>(ha, tmap_);
+  void LaunchHist(const HistArgs& ha, bool chain = false) {
+    if (cfg_.reserved & 8) LaunchChain(chain, k_hist2, dim3(num_sms_), dim3(kHist2Threads), kHistSmemBytes, ha, tmap_);
+    else LaunchChain(chain, k_hist, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
+  }
+
+  // Launch of a kernel of the per-split chain.  With LGBMB200_Config.reserved bit 4 the launch carries a
+  // programmatic-dependent-launch edge to its predecessor (see pdl_enter() in comm.cuh); inside stream capture
+  // this becomes a programmatic graph edge.  Profiling mode (an event after every launch) keeps plain launches.
+  template <typename... KArgs, typename... Args>
+  void LaunchChain(bool chain, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = stream_;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = (chain && (cfg_.reserved & 16) && !profiling_) ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...));
   }
 
   // The fixed per-tree launch sequence (see file header).
@@ -630,20 +645,20 @@ class Learner {
     for (int it = 0; it < NL - 1 + 1; ++it) {
       // it == 0: root pass; it >= 1: apply split it-1, then find splits for its two children
       if (it > 0) {
-        k_part_flags<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
+        LaunchChain(true, k_part_flags, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
         Stamp(kProfPartFlags);
-        k_part_scatter<<<part_blocks_, kPartThreads, 0, stream_>>>(pt);
+        LaunchChain(true, k_part_scatter, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
         Stamp(kProfPartScatter);
         launches_ += 2;
         if (it == NL - 1) break;   // the tree is full: no need to look for further splits
       }
-      LaunchHist(ha);
+      LaunchHist(ha, it > 0);          // it == 0 follows a memset node: plain dependency
       Stamp(kProfHist);
-      if (row_mode) { k_hist_signal<<<1, 32, 0, stream_>>>(peers_, ctl_.p); ++launches_; }
-      if (row_mode) k_scan<true><<<dim3(std::max(scan_blocks, 1), 1), kScanWarps * 32, 0, stream_>>>(sa);
-      else k_scan<false><<<dim3(std::max(scan_blocks, 1), 2), kScanWarps * 32, 0, stream_>>>(sa);
+      if (row_mode) { LaunchChain(true, k_hist_signal, dim3(1), dim3(32), 0, peers_, ctl_.p); ++launches_; }
+      if (row_mode) LaunchChain(true, k_scan<true>, dim3(std::max(scan_blocks, 1), 1), dim3(kScanWarps * 32), 0, sa);
+      else LaunchChain(true, k_scan<false>, dim3(std::max(scan_blocks, 1), 2), dim3(kScanWarps * 32), 0, sa);
       Stamp(kProfScan);
-      k_select<<<1, 256, 0, stream_>>>(se);
+      LaunchChain(true, k_select, dim3(1), dim3(256), 0, se);
       Stamp(kProfSelect);
       launches_ += 3;
     }

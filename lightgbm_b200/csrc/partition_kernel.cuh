@@ -64,6 +64,7 @@ __device__ __forceinline__ void part_block_range(int n, int nblocks, int b, int*
 constexpr int kPartUnroll = 4;
 
 __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
+  pdl_enter();
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
   const int me = a.peers.rank;
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
 }
 
 __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a) {
+  pdl_enter();
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
   const int n = c->cur_count, begin = c->cur_begin;
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(32) k_root_init(const PrepArgs a) {
 // row-shard: tell every peer that this rank's local histogram for the current iteration is complete
 // (launched right after k_hist: stream order guarantees the REDs have been performed)
 __global__ void __launch_bounds__(32) k_hist_signal(const CommPeers peers, Ctl* c) {
+  pdl_enter();
   if (!c->cur_valid || !c->do_find) return;
   const unsigned long long seq = c->hist_seq + 1;
   if (threadIdx.x < peers.world) {

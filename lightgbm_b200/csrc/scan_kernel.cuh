@@ -295,6 +295,7 @@ __device__ __forceinline__ Cand cand_none() {
 // into this rank's own pool so that later subtractions (parent - smaller) stay local.
 template <bool ROWS>
 __global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const ScanArgs a) {
+  pdl_enter();
   Ctl* c = a.ctl;
   if (!c->cur_valid || !c->do_find) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -477,6 +478,7 @@ __device__ __forceinline__ bool cand_better(double ga, int fa_real, double gb, i
 }
 
 __global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
+  pdl_enter();
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -8,6 +8,7 @@ in lightgbm_b200/lib/liblgbm_b200.so (hand-written sm_100a CUDA); there is no CP
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -64,11 +65,12 @@ class Config:
     path_smooth: float = 0.0
     gpu_device_id: int = -1
     use_cuda_graph: bool = True
+    reserved: int = int(os.environ.get("LGBMB200_RESERVED", "0"))   # experiment switches, see include/lgbm_b200.h
 
     def to_c(self) -> _CConfig:
         return _CConfig(self.num_leaves, self.max_depth, self.min_data_in_leaf, self.gpu_device_id,
                         self.min_sum_hessian_in_leaf, self.lambda_l1, self.lambda_l2, self.min_gain_to_split,
-                        self.max_delta_step, self.path_smooth, 1 if self.use_cuda_graph else 0, 0)
+                        self.max_delta_step, self.path_smooth, 1 if self.use_cuda_graph else 0, int(self.reserved))
 
 
 @dataclass

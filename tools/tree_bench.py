@@ -1,5 +1,7 @@
-"""Trains a few trees on an N x F synthetic matrix (for ncu captures of the non-histogram kernels)."""
-import os, sys, time
+"""Trains a few trees on an N x F synthetic matrix (ncu captures of the non-histogram kernels, A/B of launch
+options).  Prints the device time per tree (CUDA events on the learner's stream) and a hash of the split records so
+that two runs with different LGBMB200_RESERVED bits can be checked for identical trees."""
+import hashlib, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lightgbm_b200 as lgb
@@ -10,5 +12,12 @@ rng = np.random.default_rng(0)
 bins = rng.integers(0, 255, (n, f), dtype=np.uint8)
 y = ((bins[:, :32] / 127.0 - 1) @ rng.normal(size=32) + 0.5 * rng.normal(size=n)).astype(np.float32)
 B = lgb.B200Booster(lgb.Layout.identity(bins), y, lgb.Config(num_leaves=leaves, use_cuda_graph=os.environ.get("TB_GRAPH", "1") == "1"), learning_rate=0.1)
+ms, h = [], hashlib.sha1()
 for _ in range(trees):
-    t0 = time.time(); B.update(); print(f"tree {time.time()-t0:.4f}s")
+    B.learner.timer_start()
+    t = B.update()
+    ms.append(B.learner.timer_stop())
+    h.update(t.splits.tobytes()); h.update(t.leaf_value.tobytes())
+warm = ms[min(2, len(ms) - 1):]
+print(f"reserved={lgb.Config().reserved} rows={n} cols={f} leaves={leaves} device_ms_per_tree mean={np.mean(warm):.3f} min={np.min(warm):.3f} "
+      f"trees_sha1={h.hexdigest()[:16]}")
