@@ -627,6 +627,8 @@ class Learner {
     const bool row_mode = peers_.world > 1 && peers_.mode == 1;
     const int scan_blocks = ((row_mode ? peers_.f_cnt : F_) + kScanWarps - 1) / kScanWarps;
     SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p, block_best_.p, scan_blocks, splittable_.p, splittable_new_.p, peers_};
+    const bool fuse_select = (cfg_.reserved & 32) != 0;
+    sa.fuse_select = fuse_select ? 1 : 0; sa.sel = se;
     PartArgs pt;
     pt.bins = bins_.p; pt.binsT = peers_.mode == 2 ? binsT_full_.p : binsT_.p; pt.num_data = N_; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flag_words = reinterpret_cast<uint32_t*>(flags_.p);
     pt.block_left = block_left_.p; pt.leaves = leaves_.p; pt.ctl = ctl_.p; pt.splits = splits_.p; pt.params = params_;
@@ -658,9 +660,9 @@ class Learner {
       if (row_mode) LaunchChain(true, k_scan<true>, dim3(std::max(scan_blocks, 1), 1), dim3(kScanWarps * 32), 0, sa);
       else LaunchChain(true, k_scan<false>, dim3(std::max(scan_blocks, 1), 2), dim3(kScanWarps * 32), 0, sa);
       Stamp(kProfScan);
-      LaunchChain(true, k_select, dim3(1), dim3(256), 0, se);
+      if (!fuse_select) LaunchChain(true, k_select, dim3(1), dim3(256), 0, se);
       Stamp(kProfSelect);
-      launches_ += 3;
+      launches_ += fuse_select ? 2 : 3;
     }
     CUDA_CHECK(cudaGetLastError());
   }

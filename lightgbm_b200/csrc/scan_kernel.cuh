@@ -259,6 +259,23 @@ __device__ __forceinline__ Cand find_best_threshold(const double (&g)[8], const 
 
 struct BlockBest { double gain; int32_t real; int32_t feature; };   // per k_scan block: its best candidate
 
+// k_select's arguments (the kernel is at the end of this file).  With LGBMB200_Config.reserved bit 5 the LAST block
+// of k_scan to finish runs the selection itself (select_body) and the k_select launch is dropped from the chain.
+struct SelectArgs {
+  const FeatMeta* feat;
+  int32_t num_features;
+  int32_t max_leaves;
+  Leaf* leaves;
+  Ctl* ctl;
+  const Cand* cand;
+  const BlockBest* block_best;  // [2][scan_blocks]
+  int32_t scan_blocks;
+  uint8_t* splittable;          // [slot][num_features]
+  const uint8_t* splittable_new;  // [2][num_features] written by k_scan
+  CommPeers peers;              // world == 1: no exchange
+};
+__device__ __noinline__ void select_body(const SelectArgs& a);
+
 struct ScanArgs {
   const FeatMeta* feat;
   const uint8_t* feature_used;      // by-tree mask or nullptr
@@ -273,6 +290,8 @@ struct ScanArgs {
   Cand* cand;                       // [2][num_features]: smaller, larger
   BlockBest* block_best;            // [2][scan_blocks]
   CommPeers peers;                  // row-shard: whose pools to sum, which feature slice is mine
+  int32_t fuse_select;              // 1: the last block to finish runs select_body(sel)
+  SelectArgs sel;
 };
 
 constexpr int kScanWarps = 8;
@@ -294,10 +313,15 @@ __device__ __forceinline__ Cand cand_none() {
 // load phase; int64 fixed point => the sum is exact and order-independent).  The global slice is written back
 // into this rank's own pool so that later subtractions (parent - smaller) stay local.
 template <bool ROWS>
-__global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const ScanArgs a) {
+__global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const __grid_constant__ ScanArgs a) {
   pdl_enter();
   Ctl* c = a.ctl;
-  if (!c->cur_valid || !c->do_find) return;
+  if (!c->cur_valid) return;
+  if (!c->do_find) {
+    // nothing to scan (BeforeFindBestSplit said no): the selection over the existing leaves still has to run
+    if (a.fuse_select && blockIdx.x == 0 && blockIdx.y == 0) select_body(a.sel);
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr bool rows = ROWS;
   const int f = (rows ? a.peers.f_lo : 0) + blockIdx.x * kScanWarps + warp;
@@ -442,25 +466,24 @@ __global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const Sc
     }
     a.block_best[which * gridDim.x + blockIdx.x] = bb;
   }
+  if (a.fuse_select) {
+    // last-block-done: every block publishes its results, the last one to arrive selects
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&c->scan_done, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (threadIdx.x == 0) c->scan_done = 0;
+      select_body(a.sel);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // k_select: per-leaf arg-max over features (SplitInfo::operator>, split_info.hpp:138-164), then the
 // arg-max over leaves (array_args.h:45-60) and the snapshot of the split to apply next.
-struct SelectArgs {
-  const FeatMeta* feat;
-  int32_t num_features;
-  int32_t max_leaves;
-  Leaf* leaves;
-  Ctl* ctl;
-  const Cand* cand;
-  const BlockBest* block_best;  // [2][scan_blocks]
-  int32_t scan_blocks;
-  uint8_t* splittable;          // [slot][num_features]
-  const uint8_t* splittable_new;  // [2][num_features] written by k_scan
-  CommPeers peers;              // world == 1: no exchange
-};
-
 // payload written by a peer GPU: read it around L1 (the acquire on the sequence word orders it)
 __device__ __forceinline__ Cand load_cand_sys(const Cand* p) {
   static_assert(sizeof(Cand) % 8 == 0, "Cand must be a multiple of 8 bytes");
@@ -477,8 +500,12 @@ __device__ __forceinline__ bool cand_better(double ga, int fa_real, double gb, i
   return fa_real < fb_real;
 }
 
-__global__ void __launch_bounds__(256) k_select(const SelectArgs a) {
+__global__ void __launch_bounds__(256) k_select(const __grid_constant__ SelectArgs a) {
   pdl_enter();
+  select_body(a);
+}
+
+__device__ __noinline__ void select_body(const SelectArgs& a) {
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
