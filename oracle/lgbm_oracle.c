@@ -217,6 +217,157 @@ int orc_find_best_threshold(const OrcLayout* L, const OrcParams* P, int f, doubl
   return is_splittable;
 }
 
+/* ---- quantized-gradient path -------------------------------------------------------------------- */
+
+/* GradientDiscretizer::DiscretizeGradients (gradient_discretizer.cpp:68-160).  static_cast<int8_t>(double)
+ * truncates toward zero. */
+void orc_discretize(const float* grad, const float* hess, int32_t n, OrcQuant* Q,
+                    const double* random_g, const double* random_h, float* qgrad, float* qhess) {
+  double max_g = fabs((double)grad[0]), max_h = fabs((double)hess[0]);
+  for (int32_t i = 0; i < n; ++i) {
+    const double ag = fabs((double)grad[i]), ah = fabs((double)hess[i]);
+    if (ag > max_g) max_g = ag;
+    if (ah > max_h) max_h = ah;
+  }
+  Q->grad_scale = max_g / (double)(Q->num_grad_quant_bins / 2);
+  Q->hess_scale = Q->is_constant_hessian ? max_h : max_h / (double)Q->num_grad_quant_bins;
+  const double inv_g = 1.0f / Q->grad_scale, inv_h = 1.0f / Q->hess_scale;
+  for (int32_t i = 0; i < n; ++i) {
+    const double g = grad[i];
+    const double rg = random_g ? random_g[i] : 0.5;
+    qgrad[i] = (float)(g >= 0.0f ? (int8_t)(g * inv_g + rg) : (int8_t)(g * inv_g - rg));
+    if (Q->is_constant_hessian) qhess[i] = 1.0f;
+    else qhess[i] = (float)(int8_t)((double)hess[i] * inv_h + (random_h ? random_h[i] : 0.5));
+  }
+}
+
+typedef struct { double gain; int threshold; int64_t ilg, ilh; } IntBest;
+
+/* feature_histogram.hpp:1059-1350 FindBestThresholdSequentiallyInt, one direction.  The reference packs
+ * (gradient << bits | hessian) into one integer and picks 16/32-bit accumulators per leaf; with no overflow
+ * (which its bit-width rule guarantees) that is exact integer arithmetic on the two sums, restated here with
+ * separate int64 values. */
+static void scan_one_direction_int(const double* d, int num_bin, int offset, int default_bin, const OrcParams* P,
+                                   const GainCfg* gc, int64_t tot_g, int64_t tot_h, double grad_scale, double hess_scale,
+                                   int32_t num_data, double min_gain_shift, double parent_output, int reverse,
+                                   int skip_default, int na_as_missing, int* is_splittable, OrcSplit* out,
+                                   int64_t* out_ilg, int64_t* out_ilh) {
+  double best_gain = K_MIN_SCORE;
+  int64_t best_ilg = 0, best_ilh = 0;
+  int best_threshold = num_bin;
+  const double cnt_factor = (double)num_data / (double)(uint32_t)tot_h;
+
+  if (reverse) {
+    int64_t rg = 0, rh = 0;
+    const int t_end = 1 - offset;
+    for (int t = num_bin - 1 - offset - na_as_missing; t >= t_end; --t) {
+      if (skip_default && (t + offset) == default_bin) continue;
+      rg += (int64_t)d[2 * t]; rh += (int64_t)d[2 * t + 1];
+      const int32_t right_count = round_int((double)(uint32_t)rh * cnt_factor);
+      const double srh = (double)(uint32_t)rh * hess_scale;
+      if (right_count < P->min_data_in_leaf || srh < P->min_sum_hessian_in_leaf) continue;
+      const int32_t left_count = num_data - right_count;
+      if (left_count < P->min_data_in_leaf) break;
+      const int64_t lg = tot_g - rg, lh = tot_h - rh;
+      const double slh = (double)(uint32_t)lh * hess_scale;
+      if (slh < P->min_sum_hessian_in_leaf) break;
+      const double srg = (double)rg * grad_scale, slg = (double)lg * grad_scale;
+      const double cur = leaf_gain(gc, slg, slh + K_EPS, left_count, parent_output) +
+                         leaf_gain(gc, srg, srh + K_EPS, right_count, parent_output);
+      if (cur <= min_gain_shift) continue;
+      *is_splittable = 1;
+      if (cur > best_gain) { best_ilg = lg; best_ilh = lh; best_threshold = t - 1 + offset; best_gain = cur; }
+    }
+  } else {
+    int64_t lg = 0, lh = 0;
+    int t = 0;
+    const int t_end = num_bin - 2 - offset;
+    if (na_as_missing && offset == 1) {
+      lg = tot_g; lh = tot_h;
+      for (int i = 0; i < num_bin - offset; ++i) { lg -= (int64_t)d[2 * i]; lh -= (int64_t)d[2 * i + 1]; }
+      t = -1;
+    }
+    for (; t <= t_end; ++t) {
+      if (skip_default && (t + offset) == default_bin) continue;
+      if (t >= 0) { lg += (int64_t)d[2 * t]; lh += (int64_t)d[2 * t + 1]; }
+      const int32_t left_count = round_int((double)(uint32_t)lh * cnt_factor);
+      const double slh = (double)(uint32_t)lh * hess_scale;
+      if (left_count < P->min_data_in_leaf || slh < P->min_sum_hessian_in_leaf) continue;
+      const int32_t right_count = num_data - left_count;
+      if (right_count < P->min_data_in_leaf) break;
+      const int64_t rg = tot_g - lg, rh = tot_h - lh;
+      const double srh = (double)(uint32_t)rh * hess_scale;
+      if (srh < P->min_sum_hessian_in_leaf) break;
+      const double srg = (double)rg * grad_scale, slg = (double)lg * grad_scale;
+      const double cur = leaf_gain(gc, slg, slh + K_EPS, left_count, parent_output) +
+                         leaf_gain(gc, srg, srh + K_EPS, right_count, parent_output);
+      if (cur <= min_gain_shift) continue;
+      *is_splittable = 1;
+      if (cur > best_gain) { best_ilg = lg; best_ilh = lh; best_threshold = t + offset; best_gain = cur; }
+    }
+  }
+
+  if (*is_splittable && best_gain > out->gain + min_gain_shift) {
+    /* feature_histogram.hpp:1303-1346 */
+    const int64_t irg = tot_g - best_ilg, irh = tot_h - best_ilh;
+    const double slg = (double)best_ilg * grad_scale, slh = (double)(uint32_t)best_ilh * hess_scale;
+    const double srg = (double)irg * grad_scale, srh = (double)(uint32_t)irh * hess_scale;
+    const int32_t lc = round_int((double)(uint32_t)best_ilh * cnt_factor);
+    const int32_t rc = round_int((double)(uint32_t)irh * cnt_factor);
+    out->threshold = best_threshold;
+    out->left_output = leaf_output(gc, slg, slh, lc, parent_output);
+    out->left_count = lc;
+    out->left_sum_gradient = slg; out->left_sum_hessian = slh;
+    out->right_output = leaf_output(gc, srg, srh, rc, parent_output);
+    out->right_count = rc;
+    out->right_sum_gradient = srg; out->right_sum_hessian = srh;
+    out->gain = best_gain - min_gain_shift;
+    out->default_left = reverse;
+    *out_ilg = best_ilg; *out_ilh = best_ilh;
+  }
+}
+
+int orc_find_best_threshold_int(const OrcLayout* L, const OrcParams* P, int f, double* hist, int do_fix,
+                                int64_t tot_g, int64_t tot_h, double grad_scale, double hess_scale,
+                                int32_t num_data, double parent_output, OrcSplit* out,
+                                int64_t* out_ilg, int64_t* out_ilh) {
+  const int num_bin = L->feat_num_bin[f], mfb = L->feat_mfb[f];
+  const int offset = (mfb == 0) ? 1 : 0;
+  const int missing = L->feat_missing[f], default_bin = L->feat_default_bin[f];
+  double* d = hist + ((size_t)L->feat_column[f] * 256 + L->feat_lo[f]) * 2;
+  const GainCfg gc = gain_cfg(P);
+
+  /* Dataset::FixHistogramInt (dataset.cpp:1540-1576) */
+  if (do_fix && mfb > 0) {
+    double fg = (double)tot_g, fh = (double)tot_h;
+    for (int i = 0; i < num_bin; ++i) {
+      if (i != mfb) { fg -= d[2 * i]; fh -= d[2 * i + 1]; }
+    }
+    d[2 * mfb] = fg; d[2 * mfb + 1] = fh;
+  }
+
+  /* FindBestThresholdInt (:176-189) + BeforeNumericalInt (:209-228) */
+  out->default_left = 1;
+  out->gain = K_MIN_SCORE;
+  out->feature = f;
+  int is_splittable = 0;
+  const double sum_gradient = (double)(int32_t)tot_g * grad_scale;
+  const double sum_hessian = (double)(uint32_t)tot_h * hess_scale;
+  const double min_gain_shift = leaf_gain(&gc, sum_gradient, sum_hessian, num_data, parent_output) + P->min_gain_to_split;
+
+#define SCAN_INT(rev, skip, na) scan_one_direction_int(d, num_bin, offset, default_bin, P, &gc, tot_g, tot_h, grad_scale, hess_scale, \
+    num_data, min_gain_shift, parent_output, rev, skip, na, &is_splittable, out, out_ilg, out_ilh)
+  if (num_bin > 2 && missing != ORC_MISSING_NONE) {
+    if (missing == ORC_MISSING_ZERO) { SCAN_INT(1, 1, 0); SCAN_INT(0, 1, 0); }
+    else { SCAN_INT(1, 0, 1); SCAN_INT(0, 0, 1); }
+  } else {
+    SCAN_INT(1, 0, 0);
+    if (missing == ORC_MISSING_NAN) out->default_left = 0;
+  }
+#undef SCAN_INT
+  return is_splittable;
+}
+
 /* FeatureGroup::Split -> DenseBin::Split -> SplitInner (feature_group.h:398-425, dense_bin.hpp:314-447) */
 int32_t orc_partition(const OrcLayout* L, const uint8_t* bins, int f, int threshold, int default_left,
                       int32_t* indices, int32_t n) {
@@ -289,10 +440,16 @@ static int split_better(const OrcSplit* a, int a_real, const OrcSplit* b, int b_
   return fa < fb;
 }
 
-int orc_train_tree(const OrcLayout* L, const uint8_t* bins, const float* grad, const float* hess,
-                   const int32_t* bag_indices, int32_t bag_count, const uint8_t* feature_used,
-                   const OrcParams* P, OrcTree* T) {
+/* Q == NULL: full-precision path.  Q != NULL: grad/hess hold the discretized values (exact small integers) and
+ * true_grad/true_hess the original gradients (only read by quant_train_renew_leaf). */
+static int train_impl(const OrcLayout* L, const uint8_t* bins, const float* grad, const float* hess,
+                      const int32_t* bag_indices, int32_t bag_count, const uint8_t* feature_used,
+                      const OrcParams* P, OrcTree* T, const OrcQuant* Q, const float* true_grad, const float* true_hess) {
   const int F = L->num_features, C = L->num_columns, NL = P->num_leaves;
+  int64_t* leaf_ig = (int64_t*)calloc(NL, sizeof(int64_t));     /* LeafSplits::int_sum_gradients_and_hessians_ */
+  int64_t* leaf_ih = (int64_t*)calloc(NL, sizeof(int64_t));
+  int64_t* best_ilg = (int64_t*)calloc(NL, sizeof(int64_t));    /* SplitInfo::left_sum_gradient_and_hessian */
+  int64_t* best_ilh = (int64_t*)calloc(NL, sizeof(int64_t));
   const size_t HS = (size_t)C * 512;
   const GainCfg gc_root = {1, 1, 0, P->lambda_l1, P->lambda_l2, P->max_delta_step, P->path_smooth};
 
@@ -311,7 +468,16 @@ int orc_train_tree(const OrcLayout* L, const uint8_t* bins, const float* grad, c
   for (int i = 0; i < NL; ++i) { best[i].feature = -1; best[i].gain = K_MIN_SCORE; T->leaf_begin[i] = 0; T->leaf_count[i] = 0; T->leaf_depth[i] = 0; }
   T->leaf_count[0] = n_root;
   double sg = 0.0, sh = 0.0;
-  for (int32_t i = 0; i < n_root; ++i) { const int32_t r = T->indices[i]; sg += grad[r]; sh += hess[r]; }
+  if (!Q) {
+    for (int32_t i = 0; i < n_root; ++i) { const int32_t r = T->indices[i]; sg += grad[r]; sh += hess[r]; }
+  } else {
+    /* LeafSplits::Init(int8 ...) (leaf_splits.hpp:117-140 / :170-195): fp64 sums of int*scale + the packed int sum */
+    for (int32_t i = 0; i < n_root; ++i) {
+      const int32_t r = T->indices[i];
+      sg += (double)grad[r] * Q->grad_scale; sh += (double)hess[r] * Q->hess_scale;
+      leaf_ig[0] += (int64_t)grad[r]; leaf_ih[0] += (int64_t)hess[r];
+    }
+  }
   leaf_sg[0] = sg; leaf_sh[0] = sh;
   T->root_sum_gradient = sg; T->root_sum_hessian = sh;
   /* root output (serial_tree_learner.cpp:207-211): <USE_MC,L1,MAX_OUTPUT,!SMOOTHING>, num_data_ */
@@ -370,9 +536,12 @@ int orc_train_tree(const OrcLayout* L, const uint8_t* bins, const float* grad, c
       for (int f = 0; f < F; ++f) {
         if (!used[f]) continue;
         OrcSplit s; memset(&s, 0, sizeof(s));
-        sp_small[f] = (uint8_t)orc_find_best_threshold(L, P, f, h_small, 1, leaf_sg[smaller], leaf_sh[smaller], T->leaf_count[smaller], po_small, &s);
+        int64_t ilg = 0, ilh = 0;
+        if (!Q) sp_small[f] = (uint8_t)orc_find_best_threshold(L, P, f, h_small, 1, leaf_sg[smaller], leaf_sh[smaller], T->leaf_count[smaller], po_small, &s);
+        else sp_small[f] = (uint8_t)orc_find_best_threshold_int(L, P, f, h_small, 1, leaf_ig[smaller], leaf_ih[smaller], Q->grad_scale, Q->hess_scale,
+                                                              T->leaf_count[smaller], po_small, &s, &ilg, &ilh);
         s.leaf = smaller;
-        if (split_better(&s, L->feat_real_index[f], &bs, bs_real)) { bs = s; bs_real = L->feat_real_index[f]; }
+        if (split_better(&s, L->feat_real_index[f], &bs, bs_real)) { bs = s; bs_real = L->feat_real_index[f]; best_ilg[smaller] = ilg; best_ilh[smaller] = ilh; }
         if (larger < 0) continue;
         /* FeatureHistogram::Subtract (feature_histogram.hpp:96-145) on the feature's slice */
         {
@@ -383,9 +552,11 @@ int orc_train_tree(const OrcLayout* L, const uint8_t* bins, const float* grad, c
         OrcSplit l; memset(&l, 0, sizeof(l));
         /* FixHistogram is NOT re-run for the larger leaf when subtracting (:581-597): its mfb entry is
          * parent(fixed) - smaller(fixed). */
-        sp_large[f] = (uint8_t)orc_find_best_threshold(L, P, f, h_large, 0, leaf_sg[larger], leaf_sh[larger], T->leaf_count[larger], po_large, &l);
+        if (!Q) sp_large[f] = (uint8_t)orc_find_best_threshold(L, P, f, h_large, 0, leaf_sg[larger], leaf_sh[larger], T->leaf_count[larger], po_large, &l);
+        else sp_large[f] = (uint8_t)orc_find_best_threshold_int(L, P, f, h_large, 0, leaf_ig[larger], leaf_ih[larger], Q->grad_scale, Q->hess_scale,
+                                                              T->leaf_count[larger], po_large, &l, &ilg, &ilh);
         l.leaf = larger;
-        if (split_better(&l, L->feat_real_index[f], &bl, bl_real)) { bl = l; bl_real = L->feat_real_index[f]; }
+        if (split_better(&l, L->feat_real_index[f], &bl, bl_real)) { bl = l; bl_real = L->feat_real_index[f]; best_ilg[larger] = ilg; best_ilh[larger] = ilh; }
       }
       free(used);
       bs.leaf = smaller; best[smaller] = bs;
@@ -423,9 +594,45 @@ int orc_train_tree(const OrcLayout* L, const uint8_t* bins, const float* grad, c
     /* children sums come from the SplitInfo (:857-878) */
     leaf_sg[best_leaf] = s->left_sum_gradient; leaf_sh[best_leaf] = s->left_sum_hessian;
     leaf_sg[next_leaf] = s->right_sum_gradient; leaf_sh[next_leaf] = s->right_sum_hessian;
+    if (Q) {
+      /* SplitInfo::{left,right}_sum_gradient_and_hessian -> LeafSplits::Init (serial_tree_learner.cpp:880-905) */
+      const int64_t pg = leaf_ig[best_leaf], ph = leaf_ih[best_leaf];
+      leaf_ig[best_leaf] = best_ilg[best_leaf]; leaf_ih[best_leaf] = best_ilh[best_leaf];
+      leaf_ig[next_leaf] = pg - best_ilg[best_leaf]; leaf_ih[next_leaf] = ph - best_ilh[best_leaf];
+    }
     left_leaf = best_leaf; right_leaf = next_leaf;
   }
 
+  if (Q && Q->renew_leaf) {
+    /* GradientDiscretizer::RenewIntGradTreeOutput (gradient_discretizer.cpp:236-259, serial_tree_learner.cpp:241-244):
+     * leaf outputs from the ORIGINAL gradients, <USE_L1, USE_MAX_OUTPUT, !USE_SMOOTHING>, parent_output 0 */
+    for (int leaf = 0; leaf < T->num_leaves; ++leaf) {
+      double tg = 0.0, th = 0.0;
+      const int32_t* idx = T->indices + T->leaf_begin[leaf];
+      for (int32_t i = 0; i < T->leaf_count[leaf]; ++i) { tg += true_grad[idx[i]]; th += true_hess[idx[i]]; }
+      T->leaf_value[leaf] = leaf_output(&gc_root, tg, th, T->leaf_count[leaf], 0.0);
+    }
+  }
+
   free(pool); free(splittable); free(best); free(leaf_sg); free(leaf_sh);
+  free(leaf_ig); free(leaf_ih); free(best_ilg); free(best_ilh);
   return 0;
+}
+
+int orc_train_tree(const OrcLayout* L, const uint8_t* bins, const float* grad, const float* hess,
+                   const int32_t* bag_indices, int32_t bag_count, const uint8_t* feature_used,
+                   const OrcParams* P, OrcTree* T) {
+  return train_impl(L, bins, grad, hess, bag_indices, bag_count, feature_used, P, T, NULL, NULL, NULL);
+}
+
+int orc_train_tree_quant(const OrcLayout* L, const uint8_t* bins, const float* grad, const float* hess,
+                         const int32_t* bag_indices, int32_t bag_count, const uint8_t* feature_used,
+                         const OrcParams* P, OrcQuant* Q, OrcTree* T) {
+  float* qg = (float*)malloc(sizeof(float) * (size_t)L->num_data);
+  float* qh = (float*)malloc(sizeof(float) * (size_t)L->num_data);
+  if (!qg || !qh) return -1;
+  orc_discretize(grad, hess, L->num_data, Q, NULL, NULL, qg, qh);
+  const int rc = train_impl(L, bins, qg, qh, bag_indices, bag_count, feature_used, P, T, Q, grad, hess);
+  free(qg); free(qh);
+  return rc;
 }

@@ -104,6 +104,37 @@ int orc_train_tree(const OrcLayout* L, const uint8_t* bins, const float* grad, c
                    const int32_t* bag_indices, int32_t bag_count, const uint8_t* feature_used,
                    const OrcParams* P, OrcTree* out);
 
+/* ---- Quantized-gradient training (Config::use_quantized_grad) -------------------------------
+ * GradientDiscretizer::DiscretizeGradients (gradient_discretizer.cpp:68-160) without stochastic rounding
+ * (Config::stochastic_rounding = false; the stochastic branch draws from per-thread std::mt19937 streams whose
+ * layout depends on OMP_NUM_THREADS and is therefore not a fixed function of the inputs).  Writes the int8 values
+ * as floats (exact) so that the fp64 histogram code can be reused: integer sums are exact in fp64.
+ * random_g / random_h: optional [num_data] values in [0,1) replacing the 0.5 rounding offset (the stochastic form,
+ * :120-139, with random_value_pos already applied); NULL -> deterministic rounding. */
+typedef struct {
+  int32_t num_grad_quant_bins;     /* config.h:638 */
+  int32_t is_constant_hessian;
+  int32_t renew_leaf;              /* Config::quant_train_renew_leaf (config.h:645) */
+  double  grad_scale, hess_scale;  /* outputs of orc_discretize */
+} OrcQuant;
+
+void orc_discretize(const float* grad, const float* hess, int32_t num_data, OrcQuant* Q,
+                    const double* random_g, const double* random_h, float* qgrad, float* qhess);
+
+/* FixHistogramInt + FindBestThresholdInt for one feature (feature_histogram.hpp:176-189, :209-228, :1059-1350).
+ * `hist` holds exact integer sums (as fp64); int_sum_g / int_sum_h are the leaf's integer totals. */
+int orc_find_best_threshold_int(const OrcLayout* L, const OrcParams* P, int feature, double* hist, int do_fix,
+                                int64_t int_sum_g, int64_t int_sum_h, double grad_scale, double hess_scale,
+                                int32_t num_data, double parent_output, OrcSplit* out,
+                                int64_t* best_left_int_g, int64_t* best_left_int_h);
+
+/* SerialTreeLearner::Train with use_quantized_grad (serial_tree_learner.cpp:182-248 and the quantized branches
+ * :195-197, :241-244, :308-328, :857-905, :979-989).  grad/hess are the ORIGINAL gradients; Q->grad_scale /
+ * hess_scale are filled in. */
+int orc_train_tree_quant(const OrcLayout* L, const uint8_t* bins, const float* grad, const float* hess,
+                         const int32_t* bag_indices, int32_t bag_count, const uint8_t* feature_used,
+                         const OrcParams* P, OrcQuant* Q, OrcTree* out);
+
 #ifdef __cplusplus
 }
 #endif
