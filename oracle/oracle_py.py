@@ -59,6 +59,7 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
         _lib.orc_train_tree.restype = C.c_int
+        _lib.orc_train_tree_quant.restype = C.c_int
         _lib.orc_partition.restype = C.c_int32
         _lib.orc_find_best_threshold.restype = C.c_int
     return _lib
@@ -129,6 +130,52 @@ def train_tree(lay, grad, hess, bag_indices=None, feature_used=None, **params) -
     n = T.num_leaves
     return OracleTree(n, splits[:n - 1].copy(), lv[:n], lw[:n], lc[:n], ld[:n], lb[:n], idx,
                       T.root_sum_gradient, T.root_sum_hessian)
+
+
+class _OrcQuant(C.Structure):
+    _fields_ = [("num_grad_quant_bins", C.c_int32), ("is_constant_hessian", C.c_int32), ("renew_leaf", C.c_int32),
+                ("grad_scale", C.c_double), ("hess_scale", C.c_double)]
+
+
+def discretize(grad, hess, num_grad_quant_bins=4, is_constant_hessian=False, random_g=None, random_h=None):
+    """GradientDiscretizer::DiscretizeGradients; returns (int8 g, int8 h, grad_scale, hess_scale)."""
+    g = np.ascontiguousarray(grad, dtype=np.float32); h = np.ascontiguousarray(hess, dtype=np.float32)
+    Q = _OrcQuant(num_grad_quant_bins, 1 if is_constant_hessian else 0, 0, 0.0, 0.0)
+    qg, qh = np.zeros(len(g), np.float32), np.zeros(len(g), np.float32)
+    rg = None if random_g is None else np.ascontiguousarray(random_g, dtype=np.float64)
+    rh = None if random_h is None else np.ascontiguousarray(random_h, dtype=np.float64)
+    lib().orc_discretize(_p(g), _p(h), C.c_int32(len(g)), C.byref(Q), None if rg is None else _p(rg),
+                         None if rh is None else _p(rh), _p(qg), _p(qh))
+    return qg.astype(np.int8), qh.astype(np.int8), Q.grad_scale, Q.hess_scale
+
+
+def train_tree_quant(lay, grad, hess, num_grad_quant_bins=4, is_constant_hessian=False, renew_leaf=False,
+                     bag_indices=None, feature_used=None, **params) -> OracleTree:
+    """SerialTreeLearner::Train with use_quantized_grad=true, stochastic_rounding=false."""
+    L, keep = make_layout(lay)
+    P = make_params(**params)
+    NL = P.num_leaves
+    bins = np.ascontiguousarray(lay.bins, dtype=np.uint8)
+    g = np.ascontiguousarray(grad, dtype=np.float32)
+    h = np.ascontiguousarray(hess, dtype=np.float32)
+    splits = np.zeros(max(NL - 1, 1), dtype=SPLIT_DTYPE)
+    lv, lw = np.zeros(NL), np.zeros(NL)
+    lc, ld, lb = (np.zeros(NL, np.int32) for _ in range(3))
+    idx = np.zeros(max(lay.num_data, 1), np.int32)
+    T = _OrcTree(0, _p(splits), _p(lv), _p(lw), _p(lc), _p(ld), _p(lb), _p(idx), 0.0, 0.0)
+    Q = _OrcQuant(num_grad_quant_bins, 1 if is_constant_hessian else 0, 1 if renew_leaf else 0, 0.0, 0.0)
+    bag = None if bag_indices is None else np.ascontiguousarray(bag_indices, dtype=np.int32)
+    fu = None if feature_used is None else np.ascontiguousarray(feature_used, dtype=np.uint8)
+    r = lib().orc_train_tree_quant(C.byref(L), _p(bins), _p(g), _p(h), None if bag is None else _p(bag),
+                                   C.c_int32(0 if bag is None else len(bag)), None if fu is None else _p(fu),
+                                   C.byref(P), C.byref(Q), C.byref(T))
+    if r != 0:
+        raise RuntimeError("orc_train_tree_quant failed")
+    n = T.num_leaves
+    t = OracleTree(n, splits[:n - 1].copy(), lv[:n], lw[:n], lc[:n], ld[:n], lb[:n], idx,
+                   T.root_sum_gradient, T.root_sum_hessian)
+    t.grad_scale, t.hess_scale = Q.grad_scale, Q.hess_scale
+    return t
 
 
 def construct_histogram(lay, indices, grad, hess) -> np.ndarray:

@@ -43,16 +43,29 @@ def thresholds_to_bins(lay, tree):
     return np.array(feats, np.int32), np.array(bins, np.int32)
 
 
-def run_case(name, X, grad, hess, ds_params=None, learner=None, y=None):
+def run_case(name, X, grad, hess, ds_params=None, learner=None, y=None, quant=None, label=None):
+    """quant: dict(num_grad_quant_bins=, quant_train_renew_leaf=) -> the reference trains with use_quantized_grad=true,
+    stochastic_rounding=false (the stochastic branch draws from per-thread mt19937 streams: not a function of the inputs
+    alone).  label: train through objective=regression (boost_from_average=false, so g = -label, h = 1 and the learner
+    is Init-ed with is_constant_hessian=true) instead of custom gradients."""
     ds_params = dict(BASE_DS, **(ds_params or {}))
     lp = dict(DEFAULTS, **(learner or {}))
-    ds = refapi.RefDataset(np.asarray(X, dtype=np.float64), np.zeros(len(X), np.float32), ds_params)
+    lab = np.zeros(len(X), np.float32) if label is None else np.asarray(label, np.float32)
+    ds = refapi.RefDataset(np.asarray(X, dtype=np.float64), lab, ds_params)
     lay = ds.layout()
     bp = dict(ds_params, **BASE_BOOST, **lp)
     bp["device_type"] = "cpu"     # Dataset may be *constructed* with cuda rules (dense bundles); training is CPU
+    if quant is not None:
+        bp.update(use_quantized_grad="true", stochastic_rounding="false", num_grad_quant_bins=quant["num_grad_quant_bins"],
+                  quant_train_renew_leaf="true" if quant.get("quant_train_renew_leaf") else "false")
+    if label is not None:
+        bp.update(objective="regression", boost_from_average="false")
     bst = refapi.RefBooster(ds, bp)
     g = np.ascontiguousarray(grad, np.float32); h = np.ascontiguousarray(hess, np.float32)
-    bst.update_custom(g, h)
+    if label is None:
+        bst.update_custom(g, h)
+    else:
+        bst.update()
     t = bst.trees()[0]
     feats, tbins = (thresholds_to_bins(lay, t) if t.num_leaves > 1 else (np.zeros(0, np.int32), np.zeros(0, np.int32)))
     d = lay.to_npz_dict()
@@ -64,6 +77,9 @@ def run_case(name, X, grad, hess, ds_params=None, learner=None, y=None):
              ref_leaf_weight=t.leaf_weight, ref_threshold_real=t.threshold)
     if y is not None:
         d["kat_y"] = np.asarray(y, np.float64)
+    if quant is not None:
+        d["quant"] = np.array([quant["num_grad_quant_bins"], 1 if quant.get("quant_train_renew_leaf") else 0,
+                               1 if label is not None else 0], np.int32)     # bins, renew_leaf, is_constant_hessian
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **d)
     print(f"{name}: N={lay.num_data} C={lay.num_columns} F={lay.num_features} leaves={t.num_leaves} "
@@ -72,7 +88,44 @@ def run_case(name, X, grad, hess, ds_params=None, learner=None, y=None):
     bst.free(); ds.free()
 
 
+def quantized_cases():
+    """use_quantized_grad fixtures (own RNG stream, so the full-precision fixtures above stay byte-identical)."""
+    rng = np.random.default_rng(4242)
+    nan = np.nan
+    n, f = 6000, 12
+    bins = rng.integers(0, 255, (n, f))
+    yv = (bins[:, :6] / 127.0 - 1) @ rng.normal(size=6) + 0.3 * rng.normal(size=n)
+    # constant hessian through the L2 objective (g = -label, h = 1): int hessian == 1, hess_scale = 1
+    run_case("quant_l2_consthess", bins, -yv, np.ones(n), dict(enable_bundle="false"), dict(num_leaves=31),
+             quant=dict(num_grad_quant_bins=4), label=yv)
+    # custom gradients: hessians are discretized too
+    p = 1 / (1 + np.exp(-0.5 * yv)); yb = (rng.random(n) < p).astype(float); q = np.full(n, 0.5)
+    run_case("quant_logistic_bins16", bins, q - yb + 0.1 * rng.normal(size=n), q * (1 - q) + 0.2 * rng.random(n),
+             dict(enable_bundle="false"), dict(num_leaves=31, lambda_l2=1.0), quant=dict(num_grad_quant_bins=16))
+    run_case("quant_renew_leaf", bins, -yv, 0.5 + rng.random(n), dict(enable_bundle="false"),
+             dict(num_leaves=24, min_data_in_leaf=30, lambda_l1=0.1, max_delta_step=0.6),
+             quant=dict(num_grad_quant_bins=6, quant_train_renew_leaf=True))
+    # reference-binned features with NaN / zero-as-missing / most-frequent-bin elision, quantized
+    n, f = 5000, 10
+    X = rng.normal(size=(n, f))
+    X[rng.random((n, f)) < 0.08] = nan
+    X[:, 3] = np.where(rng.random(n) < 0.85, 0.0, X[:, 3])
+    X[:, 4] = np.where(rng.random(n) < 0.8, 2.5, rng.normal(size=n))
+    X[:, 6] = (rng.random(n) < 0.5).astype(float)
+    logit = np.nan_to_num(X[:, 0]) - 0.7 * np.nan_to_num(X[:, 1]) + (X[:, 4] == 2.5) * 0.8 + np.isnan(X[:, 2]) * 1.0
+    yb = (rng.random(n) < 1 / (1 + np.exp(-logit))).astype(float)
+    pp = np.full(n, 0.5)
+    run_case("quant_mixed_missing", X, pp - yb, pp * (1 - pp) + 0.05 * rng.random(n), dict(max_bin=63, device_type="cuda"),
+             dict(num_leaves=31, min_data_in_leaf=10), quant=dict(num_grad_quant_bins=8))
+    run_case("quant_mixed_zero_as_missing", X, pp - yb, pp * (1 - pp) + 0.05 * rng.random(n),
+             dict(max_bin=63, zero_as_missing="true", device_type="cuda"), dict(num_leaves=31, min_data_in_leaf=10),
+             quant=dict(num_grad_quant_bins=4))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "quant":
+        quantized_cases()
+        return
     rng = np.random.default_rng(2024)
     nan = np.nan
     # --- the reference's own known-answer tables (test_engine.py:201-292): 1 tree, lr 1, pred == y
@@ -125,6 +178,7 @@ def main():
     yv = X[:, 0] * 0.05 - X[:, 5] * 0.03 + (X[:, 9] > 20) * 1.0 + 0.2 * rng.normal(size=n)
     run_case("efb_bundled", X, -yv, np.ones(n), dict(enable_bundle="true", device_type="cuda", max_bin=63),
              dict(num_leaves=31, min_data_in_leaf=10))
+    quantized_cases()
 
 
 if __name__ == "__main__":

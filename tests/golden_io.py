@@ -25,6 +25,9 @@ class Golden:
         self.params = {k: (int(v) if k in INT_KEYS else float(v)) for k, v in zip(LEARNER_KEYS, d["params"])}
         self.ref = {k[4:]: d[k] for k in d if k.startswith("ref_")}
         self.kat_y = d.get("kat_y")
+        q = d.get("quant")        # use_quantized_grad fixtures: [num_grad_quant_bins, renew_leaf, is_constant_hessian]
+        self.quant = None if q is None else dict(num_grad_quant_bins=int(q[0]), renew_leaf=bool(q[1]),
+                                                 is_constant_hessian=bool(q[2]))
 
 
 def check_against_reference(tree, g: Golden, exact_values: bool, rtol: float = 1e-5):
