@@ -56,7 +56,16 @@ typedef struct {
                                        bit 1: do NOT stage contiguous (root) histogram passes with TMA tile copies;
                                        bit 2: legacy column-group-major work mapping in the histogram kernel;
                                        bit 3: experimental split gradient/hessian histogram kernel (slower; A/B only);
-                                       bit 4: programmatic dependent launch between the kernels of the per-split chain */
+                                       bit 4: programmatic dependent launch between the kernels of the per-split chain;
+                                       bit 5: k_select folded into the last block of k_scan */
+  /* ---- quantized-gradient training (reference config.h:626-651; gradient_discretizer.cpp) */
+  int32_t use_quantized_grad;       /* 1: discretize (g,h) to int8 per tree, integer histograms, integer split scan */
+  int32_t num_grad_quant_bins;      /* config.h:638, default 4 */
+  int32_t quant_train_renew_leaf;   /* 1: leaf outputs re-derived from the original gradients after the tree */
+  int32_t stochastic_rounding;      /* 1: g/scale + U[0,1) (own counter-based generator: NOT the reference's per-thread
+                                       mt19937 streams); 0: round half away from zero, reproducing the reference exactly */
+  int32_t seed;                     /* Config::seed, used by stochastic rounding */
+  int32_t pad_;
 } LGBMB200_Config;
 
 /*
@@ -106,6 +115,8 @@ typedef struct {
   int32_t* leaf_depth;          /* out [num_leaves]                                                      */
   double   root_sum_gradient;   /* out                                                                   */
   double   root_sum_hessian;    /* out                                                                   */
+  double   grad_scale;          /* out: GradientDiscretizer::grad_scale() of this tree (0 without use_quantized_grad) */
+  double   hess_scale;          /* out: GradientDiscretizer::hess_scale()                                */
 } LGBMB200_Tree;
 
 LGBMB200_EXPORT const char* LGBMB200_GetLastError(void);

@@ -23,6 +23,13 @@ LGBMB200_Config B200TreeLearner::ToB200Config(const Config* c) {
   o.path_smooth = c->path_smooth;
   o.use_cuda_graph = 1;
   o.reserved = 0;
+  // quantized-gradient training (config.h:626-651)
+  o.use_quantized_grad = c->use_quantized_grad ? 1 : 0;
+  o.num_grad_quant_bins = c->num_grad_quant_bins;
+  o.quant_train_renew_leaf = c->quant_train_renew_leaf ? 1 : 0;
+  o.stochastic_rounding = c->stochastic_rounding ? 1 : 0;
+  o.seed = c->seed;
+  o.pad_ = 0;
   return o;
 }
 
@@ -34,7 +41,6 @@ B200TreeLearner::B200TreeLearner(const Config* config) : config_(config), col_sa
   // features of the reference learner that this hot-path library does not cover
   if (!config->monotone_constraints.empty()) Log::Fatal("lgbm_b200: monotone constraints are not supported");
   if (config->extra_trees) Log::Fatal("lgbm_b200: extra_trees is not supported");
-  if (config->use_quantized_grad) Log::Fatal("lgbm_b200: use_quantized_grad is not supported yet");
   if (config->feature_fraction_bynode < 1.0) Log::Fatal("lgbm_b200: feature_fraction_bynode is not supported");
   if (config->cegb_tradeoff < 1.0 || config->cegb_penalty_split > 0.0) Log::Fatal("lgbm_b200: CEGB is not supported");
   LGBMB200_Config c = ToB200Config(config);
@@ -127,6 +133,10 @@ Tree* B200TreeLearner::Train(const score_t* gradients, const score_t* hessians, 
                 s.left_count, s.right_count, s.left_sum_hessian, s.right_sum_hessian,
                 static_cast<float>(s.gain + config_->min_gain_to_split),
                 train_data_->FeatureBinMapper(s.feature)->missing_type(), s.default_left != 0);
+  }
+  if (config_->use_quantized_grad && config_->quant_train_renew_leaf) {
+    // RenewIntGradTreeOutput (gradient_discretizer.cpp:236-259) ran on the device: Tree::SetLeafOutput per leaf
+    for (int i = 0; i < t.num_leaves; ++i) tree->SetLeafOutput(i, leaf_value[i]);
   }
   return tree.release();
 }

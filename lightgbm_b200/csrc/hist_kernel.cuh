@@ -110,14 +110,15 @@ __device__ __forceinline__ void rmw_batch(unsigned hbase, const uint32_t (&b)[K]
 
 // The same batch update split in two so that the caller can software-pipeline it: batch_prepare (pure ALU: cell
 // addresses + the duplicate-combined increments) of batch k+1 is placed in the shadow of batch k's LDS latency.
-template <int K>
+template <bool QUANT> __device__ __forceinline__ float2 acc2(float2 a, float2 b);
+template <int K, bool QUANT>
 __device__ __forceinline__ void batch_prepare(unsigned hbase, const uint32_t (&b)[K], const float2 (&q)[K], unsigned (&addr)[K], float2 (&s)[K]) {
 #pragma unroll
   for (int i = 0; i < K; ++i) {
     addr[i] = hbase + (b[i] << 8);
     s[i] = q[i];
 #pragma unroll
-    for (int j = 0; j < i; ++j) if (b[j] == b[i]) { s[i].x += q[j].x; s[i].y += q[j].y; }
+    for (int j = 0; j < i; ++j) if (b[j] == b[i]) s[i] = acc2<QUANT>(s[i], q[j]);
   }
 }
 
@@ -247,6 +248,15 @@ __device__ __forceinline__ void consumer_bar_sync() {          // the 3 consumer
   asm volatile("bar.sync 1, %0;" ::"n"(kHistWarps * 32) : "memory");
 }
 
+// (g,h) cell arithmetic: fp32 partial sums, or — quantized-gradient training — int32 partial sums whose bit
+// patterns live in the same float2 slots (exact: a cell sees at most rows_per_part * 127 < 2^31).
+template <bool QUANT>
+__device__ __forceinline__ float2 acc2(float2 a, float2 b) {
+  if (QUANT) return make_float2(__int_as_float(__float_as_int(a.x) + __float_as_int(b.x)), __int_as_float(__float_as_int(a.y) + __float_as_int(b.y)));
+  return make_float2(a.x + b.x, a.y + b.y);
+}
+
+template <bool QUANT>
 __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -361,7 +371,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
           }
         };
         fetch(0);
-        batch_prepare<K>(hbase, nb, nq, addrN, sN);
+        batch_prepare<K, QUANT>(hbase, nb, nq, addrN, sN);
         if (K < kStageRows) fetch(K);
 #pragma unroll
         for (int r = 0; r < kStageRows; r += K) {
@@ -371,20 +381,18 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
 #pragma unroll
           for (int i = 0; i < K; ++i) v[i] = lds64(addrC[i]);
           if (r + K < kStageRows) {
-            batch_prepare<K>(hbase, nb, nq, addrN, sN);            // batch r+K, in the shadow of the loads above
+            batch_prepare<K, QUANT>(hbase, nb, nq, addrN, sN);     // batch r+K, in the shadow of the loads above
             if (r + 2 * K < kStageRows) fetch(r + 2 * K);
           }
 #pragma unroll
-          for (int i = 0; i < K; ++i) sts64(addrC[i], make_float2(v[i].x + sC[i].x, v[i].y + sC[i].y));
+          for (int i = 0; i < K; ++i) sts64(addrC[i], acc2<QUANT>(v[i], sC[i]));
         }
       } else {
         for (int r = 0; r < cnt; ++r) {
           const uint32_t b = sbin[r * 32];
           const float2 q = sgh[r];
           const unsigned addr = hbase + (b << 8);
-          float2 v = lds64(addr);
-          v.x += q.x; v.y += q.y;
-          sts64(addr, v);
+          sts64(addr, acc2<QUANT>(lds64(addr), q));
         }
       }
       __syncwarp();
@@ -405,10 +413,19 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
         const float2 v0 = lds64(hbase0 + (b << 8));
         const float2 v1 = lds64(hbase0 + kWarpSmemBytes + (b << 8));
         const float2 v2 = lds64(hbase0 + 2 * kWarpSmemBytes + (b << 8));
-        const float gx = (v0.x + v1.x) + v2.x, hx = (v0.y + v1.y) + v2.y;
-        if (gx != 0.f || hx != 0.f) {
-          atomicAdd(dst + 2 * b, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(gx) * gs)));
-          atomicAdd(dst + 2 * b + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(hx) * hs)));
+        if (QUANT) {
+          const int gi = __float_as_int(v0.x) + __float_as_int(v1.x) + __float_as_int(v2.x);
+          const int hi = __float_as_int(v0.y) + __float_as_int(v1.y) + __float_as_int(v2.y);
+          if (gi != 0 || hi != 0) {
+            atomicAdd(dst + 2 * b, static_cast<unsigned long long>(static_cast<long long>(gi)));
+            atomicAdd(dst + 2 * b + 1, static_cast<unsigned long long>(static_cast<long long>(hi)));
+          }
+        } else {
+          const float gx = (v0.x + v1.x) + v2.x, hx = (v0.y + v1.y) + v2.y;
+          if (gx != 0.f || hx != 0.f) {
+            atomicAdd(dst + 2 * b, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(gx) * gs)));
+            atomicAdd(dst + 2 * b + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(hx) * hs)));
+          }
         }
       }
       consumer_bar_sync();            // the tables are free to be zeroed for the next item
@@ -416,7 +433,13 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
 #pragma unroll 4
       for (int b = 0; b < kBinsPerColumn; ++b) {
         const float2 v = lds64(hbase + (b << 8));
-        if (v.x != 0.f || v.y != 0.f) {
+        if (QUANT) {
+          const int gi = __float_as_int(v.x), hi = __float_as_int(v.y);
+          if (gi != 0 || hi != 0) {
+            atomicAdd(dst + 2 * b, static_cast<unsigned long long>(static_cast<long long>(gi)));
+            atomicAdd(dst + 2 * b + 1, static_cast<unsigned long long>(static_cast<long long>(hi)));
+          }
+        } else if (v.x != 0.f || v.y != 0.f) {
           atomicAdd(dst + 2 * b, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v.x) * gs)));
           atomicAdd(dst + 2 * b + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v.y) * hs)));
         }

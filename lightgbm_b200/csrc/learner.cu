@@ -78,6 +78,16 @@ class Learner {
     params_.min_sum_hessian = cfg.min_sum_hessian_in_leaf; params_.l1 = cfg.lambda_l1; params_.l2 = cfg.lambda_l2;
     params_.min_gain_to_split = cfg.min_gain_to_split; params_.max_delta_step = cfg.max_delta_step;
     params_.path_smooth = cfg.path_smooth;
+    params_.quant = cfg.use_quantized_grad ? 1 : 0;
+    params_.quant_bins = cfg.num_grad_quant_bins;
+    params_.quant_renew = cfg.quant_train_renew_leaf ? 1 : 0;
+    params_.quant_stochastic = cfg.stochastic_rounding ? 1 : 0;
+    params_.quant_const_hess = const_hess_ ? 1 : 0;
+    params_.quant_seed = cfg.seed;
+    if (params_.quant) {
+      REQUIRE(cfg.num_grad_quant_bins >= 2 && cfg.num_grad_quant_bins <= 127, "num_grad_quant_bins must be in [2, 127] (int8 gradients)");
+      REQUIRE(!(peers_.world > 1 && peers_.mode == 1), "use_quantized_grad is not supported in row-shard mode");
+    }
     InvalidateGraph();
     if (inited_ && leaves_changed) AllocTreeState();
   }
@@ -128,6 +138,7 @@ class Learner {
     gh_.alloc(N_); idx0_.alloc(N_); idx1_.alloc(N_); flags_.alloc((static_cast<size_t>(N_) + 31) / 32 * 4 + 256);
     grad_stage_.alloc(N_); hess_stage_.alloc(N_);
     const_hess_ = is_constant_hessian != 0; hess_fill_valid_ = false;
+    params_.quant_const_hess = const_hess_ ? 1 : 0;
     part_blocks_ = num_sms_ * 2;
     if (part_blocks_ > 1024) part_blocks_ = 1024;
     block_left_.alloc(part_blocks_);
@@ -141,7 +152,8 @@ class Learner {
     feature_used_.alloc(F_);
     have_feature_mask_ = false;
     bag_count_ = -1;
-    CUDA_CHECK(cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+    CUDA_CHECK(cudaFuncSetAttribute(k_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+    CUDA_CHECK(cudaFuncSetAttribute(k_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
     CUDA_CHECK(cudaFuncSetAttribute(k_hist2, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
     BuildTensorMap();
     inited_ = true;
@@ -203,6 +215,8 @@ class Learner {
     CUDA_CHECK(cudaMemcpyAsync(h_splits_, splits_.p, sizeof(SplitRec) * (NL - 1), cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaMemcpyAsync(h_leaves_, leaves_.p, sizeof(Leaf) * NL, cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaMemcpyAsync(h_ctl_, ctl_.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream_));
+    const bool renew = params_.quant && params_.quant_renew;
+    if (renew) CUDA_CHECK(cudaMemcpyAsync(h_renew_, renew_out_.p, sizeof(double) * NL, cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));     // the one host sync per tree
     if (profiling_) CollectHistTimes();
 
@@ -237,6 +251,12 @@ class Learner {
       out->leaf_depth[right] = out->leaf_depth[r.leaf] + 1;
       out->leaf_depth[r.leaf] += 1;
     }
+    if (renew) {
+      // Tree::SetLeafOutput for every leaf (gradient_discretizer.cpp:255-257)
+      for (int i = 0; i < n_leaves; ++i) out->leaf_value[i] = h_renew_[i];
+    }
+    if (params_.quant) { out->grad_scale = h_ctl_->q_gscale; out->hess_scale = h_ctl_->q_hscale; }
+    else { out->grad_scale = 0.0; out->hess_scale = 0.0; }
     last_num_leaves_ = n_leaves;
   }
 
@@ -538,6 +558,9 @@ class Learner {
     splittable_new_.alloc(2 * static_cast<size_t>(F_));
     block_best_.alloc(2 * static_cast<size_t>((F_ + kScanWarps - 1) / kScanWarps));
     leaf_value_dev_.alloc(NL);
+    renew_partial_.alloc(static_cast<size_t>(NL) * kRenewBlocks * 2); renew_out_.alloc(NL);
+    if (h_renew_) cudaFreeHost(h_renew_);
+    CUDA_CHECK(cudaMallocHost(&h_renew_, sizeof(double) * NL));
     if (h_splits_) { cudaFreeHost(h_splits_); cudaFreeHost(h_leaves_); cudaFreeHost(h_ctl_); }
     CUDA_CHECK(cudaMallocHost(&h_splits_, sizeof(SplitRec) * NL));
     CUDA_CHECK(cudaMallocHost(&h_leaves_, sizeof(Leaf) * NL));
@@ -594,9 +617,10 @@ class Learner {
   // reserved bit 3 selects the experimental split kernel k_hist2 (separate gradient / hessian consumer warps,
   // 6 consumers per SM).  Measured 12 % SLOWER than k_hist on 4M x 1024 (5.45 vs 4.85 ms): the kernel is bound by
   // shared-memory wavefronts, not by latency, and the split re-reads the staged bins — kept for the record.
-  void LaunchHist(const HistArgs& ha, bool chain = false) {
-    if (cfg_.reserved & 8) LaunchChain(chain, k_hist2, dim3(num_sms_), dim3(kHist2Threads), kHistSmemBytes, ha, tmap_);
-    else LaunchChain(chain, k_hist, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
+  void LaunchHist(const HistArgs& ha, bool chain = false, bool quant = false) {
+    if (quant) LaunchChain(chain, k_hist<true>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
+    else if (cfg_.reserved & 8) LaunchChain(chain, k_hist2, dim3(num_sms_), dim3(kHist2Threads), kHistSmemBytes, ha, tmap_);
+    else LaunchChain(chain, k_hist<false>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
   }
 
   // Launch of a kernel of the per-split chain.  With LGBMB200_Config.reserved bit 4 the launch carries a
@@ -625,6 +649,7 @@ class Learner {
     sa.splittable = splittable_.p; sa.splittable_new = splittable_new_.p; sa.cand = cand_.p; sa.block_best = block_best_.p;
     sa.peers = peers_;
     const bool row_mode = peers_.world > 1 && peers_.mode == 1;
+    (void)0;
     const int scan_blocks = ((row_mode ? peers_.f_cnt : F_) + kScanWarps - 1) / kScanWarps;
     SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p, block_best_.p, scan_blocks, splittable_.p, splittable_new_.p, peers_};
     const bool fuse_select = (cfg_.reserved & 32) != 0;
@@ -636,7 +661,15 @@ class Learner {
     prof_n_ = 0;
     Stamp(kProfStart);
 
+    const bool quant = params_.quant != 0;
+    REQUIRE(!(quant && row_mode), "use_quantized_grad is not supported in row-shard mode");
     k_prep<<<prep_blocks_, kPrepThreads, 0, stream_>>>(pa);
+    if (quant) {
+      // GradientDiscretizer::DiscretizeGradients: scales from the maxima k_prep just reduced, then int8 (g,h)
+      k_quant_scales<<<1, 32, 0, stream_>>>(pa);
+      k_quantize<<<prep_blocks_, kPrepThreads, 0, stream_>>>(pa);
+      launches_ += 2;
+    }
     k_root_init<<<1, 32, 0, stream_>>>(pa);
     CUDA_CHECK(cudaMemsetAsync(splittable_.p, 1, static_cast<size_t>(NL) * F_, stream_));
     launches_ += 2;
@@ -654,15 +687,24 @@ class Learner {
         launches_ += 2;
         if (it == NL - 1) break;   // the tree is full: no need to look for further splits
       }
-      LaunchHist(ha, it > 0);          // it == 0 follows a memset node: plain dependency
+      LaunchHist(ha, it > 0, quant);   // it == 0 follows a memset node: plain dependency
       Stamp(kProfHist);
       if (row_mode) { LaunchChain(true, k_hist_signal, dim3(1), dim3(32), 0, peers_, ctl_.p); ++launches_; }
-      if (row_mode) LaunchChain(true, k_scan<true>, dim3(std::max(scan_blocks, 1), 1), dim3(kScanWarps * 32), 0, sa);
-      else LaunchChain(true, k_scan<false>, dim3(std::max(scan_blocks, 1), 2), dim3(kScanWarps * 32), 0, sa);
+      if (row_mode) LaunchChain(true, k_scan<true, false>, dim3(std::max(scan_blocks, 1), 1), dim3(kScanWarps * 32), 0, sa);
+      else if (quant) LaunchChain(true, k_scan<false, true>, dim3(std::max(scan_blocks, 1), 2), dim3(kScanWarps * 32), 0, sa);
+      else LaunchChain(true, k_scan<false, false>, dim3(std::max(scan_blocks, 1), 2), dim3(kScanWarps * 32), 0, sa);
       Stamp(kProfScan);
       if (!fuse_select) LaunchChain(true, k_select, dim3(1), dim3(256), 0, se);
       Stamp(kProfSelect);
       launches_ += fuse_select ? 2 : 3;
+    }
+    if (quant && params_.quant_renew) {
+      // quant_train_renew_leaf: leaf outputs from the ORIGINAL gradients (g, h are still untouched: k_quantize
+      // only rewrote the packed gh array)
+      RenewArgs ra{g, h, leaves_.p, ctl_.p, idx0_.p, idx1_.p, renew_partial_.p, renew_out_.p, params_};
+      k_renew_leaf<<<dim3(kRenewBlocks, NL), 256, 0, stream_>>>(ra);
+      k_renew_leaf_finish<<<(NL + 127) / 128, 128, 0, stream_>>>(ra, kRenewBlocks);
+      launches_ += 2;
     }
     CUDA_CHECK(cudaGetLastError());
   }
@@ -736,6 +778,7 @@ class Learner {
     if (comm_local_) { cudaFree(comm_local_); comm_local_ = nullptr; }
     if (h_row_leaf_) { cudaFreeHost(h_row_leaf_); h_row_leaf_ = nullptr; }
     if (h_row_leaf8_) { cudaFreeHost(h_row_leaf8_); h_row_leaf8_ = nullptr; }
+    if (h_renew_) { cudaFreeHost(h_renew_); h_renew_ = nullptr; }
     if (t0_) { cudaEventDestroy(t0_); cudaEventDestroy(t1_); t0_ = nullptr; }
     if (stream_) { cudaStreamDestroy(stream_); stream_ = nullptr; }
   }
@@ -754,6 +797,9 @@ class Learner {
   DevBuf<uint8_t> bins_, binsT_, flags_, feature_used_, splittable_, splittable_new_;
   DevBuf<BlockBest> block_best_;
   DevBuf<float2> gh_;
+  static constexpr int kRenewBlocks = 64;
+  DevBuf<double> renew_partial_, renew_out_;
+  double* h_renew_ = nullptr;
   DevBuf<float> grad_stage_, hess_stage_;
   bool const_hess_ = false, hess_fill_valid_ = false;
   float hess_fill_ = 0.f;

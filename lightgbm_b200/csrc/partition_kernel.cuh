@@ -257,6 +257,9 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
     R.sum_g = s.rsg; R.sum_h = s.rsh; R.output = s.rout;
     R.best.gain = -INFINITY; R.best.feature = -1; R.best.real = 0x7fffffff; R.best.owner = 0;
     L.count = left_count; L.lcount = lleft; L.buf = child_buf; L.depth = parent_depth + 1;
+    // quantized training: SplitInfo::{left,right}_sum_gradient_and_hessian -> LeafSplits::Init (serial_tree_learner.cpp:880-905)
+    R.isum_g = L.isum_g - s.ilg; R.isum_h = L.isum_h - s.ilh;
+    L.isum_g = s.ilg; L.isum_h = s.ilh;
     L.sum_g = s.lsg; L.sum_h = s.lsh; L.output = s.lout;
     L.best.gain = -INFINITY; L.best.feature = -1; L.best.real = 0x7fffffff; L.best.owner = 0;
     // smaller / larger (serial_tree_learner.cpp:858): the parent's pool slot becomes the larger child's,
@@ -399,10 +402,19 @@ __global__ void __launch_bounds__(32) k_root_init(const PrepArgs a) {
   for (int i = 0; i < a.max_leaves; ++i) {
     Leaf& L = a.leaves[i];
     L.begin = 0; L.count = 0; L.buf = 0; L.depth = 0; L.slot = 0; L.lcount = 0;
-    L.sum_g = 0; L.sum_h = 0; L.output = 0;
+    L.sum_g = 0; L.sum_h = 0; L.output = 0; L.isum_g = 0; L.isum_h = 0;
     L.best.gain = -INFINITY; L.best.feature = -1; L.best.real = 0x7fffffff; L.best.owner = 0;
   }
   Leaf& R = a.leaves[0];
+  Ctl* c = a.ctl;
+  long long isg = 0, ish = 0;
+  if (a.params.quant) {
+    // k_quantize left the INTEGER root sums in the partials (exact in fp64).  LeafSplits::Init(int8 ...)
+    // (leaf_splits.hpp:117-140): sum_gradients_ = sum(int * scale); here int_sum * scale (one rounding).
+    isg = __double2ll_rn(sg); ish = __double2ll_rn(sh);
+    sg = static_cast<double>(isg) * c->q_gscale; sh = static_cast<double>(ish) * c->q_hscale;
+  }
+  R.isum_g = isg; R.isum_h = ish;
   R.count = n_root; R.lcount = n_local; R.sum_g = sg; R.sum_h = sh;
   // root output (serial_tree_learner.cpp:207-211): L1 + max_delta_step, no smoothing
   {
@@ -412,15 +424,143 @@ __global__ void __launch_bounds__(32) k_root_init(const PrepArgs a) {
     if (a.params.max_delta_step > 0 && fabs(ret) > a.params.max_delta_step) ret = ((ret > 0) - (ret < 0)) * a.params.max_delta_step;
     R.output = ret;
   }
-  Ctl* c = a.ctl;
   c->cur_valid = c->error ? 0 : 1; c->cur_owner = 0; c->part_blocks_done = 0; c->cur_leaf = 0; c->cur_begin = 0; c->cur_count = n_local; c->cur_buf = 0;
   c->smaller = 0; c->larger = -1; c->do_find = 1; c->num_leaves = 1;
   // BeforeFindBestSplit at the root: too few rows to ever split
   if (n_root < a.params.min_data_in_leaf * 2) c->do_find = 0;
   c->g_scale = pow2_scale(static_cast<double>(n_root) * mg);
   c->h_scale = pow2_scale(static_cast<double>(n_root) * mh);
+  if (a.params.quant) { c->g_scale = 1.0; c->h_scale = 1.0; }     // the pool holds the raw integer sums
   c->g_inv = 1.0 / c->g_scale; c->h_inv = 1.0 / c->h_scale;
   c->root_sum_g = sg; c->root_sum_h = sh; c->root_count = n_root; c->root_identity = a.bag ? 0 : 1;
+}
+
+// ---- quantized-gradient training: GradientDiscretizer::DiscretizeGradients (gradient_discretizer.cpp:68-160) ----
+// k_prep has left max|g|, max|h| over ALL rows in the partials.  k_quant_scales turns them into the tree's scales;
+// k_quantize overwrites gh[] with the int8 values (stored as two int32 bit patterns in the float2 slots, consumed by
+// k_hist<true>) and replaces the partials by the integer root sums (over the bag if there is one).
+__global__ void __launch_bounds__(32) k_quant_scales(const PrepArgs a) {
+  if (threadIdx.x != 0) return;
+  float mg = 0.f, mh = 0.f;
+  for (int b = 0; b < a.num_partials; ++b) { mg = fmaxf(mg, a.partials[b].gmax); mh = fmaxf(mh, a.partials[b].hmax); }
+  Ctl* c = a.ctl;
+  const double max_g = mg, max_h = mh;
+  c->q_gscale = max_g / static_cast<double>(a.params.quant_bins / 2);
+  c->q_hscale = a.params.quant_const_hess ? max_h : max_h / static_cast<double>(a.params.quant_bins);
+  c->q_ginv = 1.0f / c->q_gscale;        // the reference divides the float literal 1.0f by the double scale
+  c->q_hinv = 1.0f / c->q_hscale;
+  c->quant_iter += 1;
+}
+
+// counter-based uniform in [0,1) for stochastic rounding (splitmix64 finaliser over (seed, tree, row, stream))
+__device__ __forceinline__ double quant_uniform(unsigned long long seed, unsigned long long iter, unsigned row, unsigned stream) {
+  unsigned long long z = seed * 0x9E3779B97F4A7C15ull + iter * 0xBF58476D1CE4E5B9ull + (static_cast<unsigned long long>(row) << 1 | stream);
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<double>(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ int2 quantize_row(const PrepArgs& a, const Ctl* c, int i) {
+  const double g = a.grad[i];
+  double rg = 0.5, rh = 0.5;
+  if (a.params.quant_stochastic) {
+    rg = quant_uniform(static_cast<unsigned>(a.params.quant_seed), c->quant_iter, static_cast<unsigned>(i), 0u);
+    rh = quant_uniform(static_cast<unsigned>(a.params.quant_seed), c->quant_iter, static_cast<unsigned>(i), 1u);
+  }
+  // static_cast<int8_t>(double): truncation toward zero (gradient_discretizer.cpp:123-125, :146-148)
+  const int qg = g >= 0.0 ? static_cast<int>(g * c->q_ginv + rg) : static_cast<int>(g * c->q_ginv - rg);
+  const int qh = a.params.quant_const_hess ? 1 : static_cast<int>(static_cast<double>(a.hess[i]) * c->q_hinv + rh);
+  return make_int2(static_cast<int>(static_cast<signed char>(qg)), static_cast<int>(static_cast<signed char>(qh)));
+}
+
+__global__ void __launch_bounds__(kPrepThreads) k_quantize(const PrepArgs a) {
+  const Ctl* c = a.ctl;
+  const int N = a.num_data;
+  const int nb = gridDim.x;
+  int per = (N + nb - 1) / nb;
+  per = (per + kPrepThreads - 1) / kPrepThreads * kPrepThreads;
+  const int lo = min(N, static_cast<int>(blockIdx.x) * per), hi = min(N, lo + per);
+  long long sg = 0, sh = 0; int mg = 0, mh = 0;
+  for (int i = lo + threadIdx.x; i < hi; i += kPrepThreads) {
+    const int2 q = quantize_row(a, c, i);
+    a.gh[i] = make_float2(__int_as_float(q.x), __int_as_float(q.y));
+    mg = max(mg, abs(q.x)); mh = max(mh, abs(q.y));
+    if (a.bag == nullptr) { sg += q.x; sh += q.y; }
+  }
+  if (a.bag != nullptr) {
+    int perb = (a.bag_count + nb - 1) / nb;
+    perb = (perb + kPrepThreads - 1) / kPrepThreads * kPrepThreads;
+    const int blo = min(a.bag_count, static_cast<int>(blockIdx.x) * perb), bhi = min(a.bag_count, blo + perb);
+    for (int i = blo + threadIdx.x; i < bhi; i += kPrepThreads) {
+      const int2 q = quantize_row(a, c, a.bag[i]);       // recomputed: the row may belong to another block's range
+      sg += q.x; sh += q.y;
+    }
+  }
+  __shared__ long long s_g[kPrepThreads / 32], s_h[kPrepThreads / 32];
+  __shared__ int s_mg[kPrepThreads / 32], s_mh[kPrepThreads / 32];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    sg += __shfl_xor_sync(0xffffffffu, sg, d); sh += __shfl_xor_sync(0xffffffffu, sh, d);
+    mg = max(mg, __shfl_xor_sync(0xffffffffu, mg, d)); mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, d));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_g[warp] = sg; s_h[warp] = sh; s_mg[warp] = mg; s_mh[warp] = mh; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tg = 0, th = 0; int tmg = 0, tmh = 0;
+    for (int w = 0; w < kPrepThreads / 32; ++w) { tg += s_g[w]; th += s_h[w]; tmg = max(tmg, s_mg[w]); tmh = max(tmh, s_mh[w]); }
+    PartialSum p; p.g = static_cast<double>(tg); p.h = static_cast<double>(th); p.gmax = static_cast<float>(tmg); p.hmax = static_cast<float>(tmh);
+    a.partials[blockIdx.x] = p;
+  }
+}
+
+// Config::quant_train_renew_leaf — GradientDiscretizer::RenewIntGradTreeOutput (gradient_discretizer.cpp:236-259):
+// leaf outputs from the ORIGINAL gradients of the leaf's rows, <USE_L1, USE_MAX_OUTPUT, no smoothing>, parent_output 0.
+// Pass 1: per-(leaf, block) partial sums in a fixed order; pass 2 (k_renew_leaf_finish): fixed-order total + output.
+struct RenewArgs {
+  const float* grad; const float* hess;
+  const Leaf* leaves; const Ctl* ctl;
+  const int32_t* idx0; const int32_t* idx1;
+  double* partial;          // [max_leaves][gridDim.x][2]
+  double* out;              // [max_leaves]
+  Params params;
+};
+__global__ void __launch_bounds__(256) k_renew_leaf(const RenewArgs a) {
+  const int leaf = blockIdx.y;
+  double sg = 0.0, sh = 0.0;
+  if (leaf < a.ctl->num_leaves) {
+    const Leaf& L = a.leaves[leaf];
+    const int32_t* idx = (L.buf ? a.idx1 : a.idx0) + L.begin;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < L.lcount; i += gridDim.x * 256) {
+      const int r = idx[i];
+      sg += a.grad[r]; sh += a.hess[r];
+    }
+  }
+  __shared__ double s_g[8], s_h[8];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, d); sh += __shfl_xor_sync(0xffffffffu, sh, d); }
+  if ((threadIdx.x & 31) == 0) { s_g[threadIdx.x >> 5] = sg; s_h[threadIdx.x >> 5] = sh; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tg = 0, th = 0;
+    for (int w = 0; w < 8; ++w) { tg += s_g[w]; th += s_h[w]; }
+    double* p = a.partial + (static_cast<int64_t>(leaf) * gridDim.x + blockIdx.x) * 2;
+    p[0] = tg; p[1] = th;
+  }
+}
+__global__ void k_renew_leaf_finish(const RenewArgs a, int blocks) {
+  const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= a.params.num_leaves) return;
+  if (leaf >= a.ctl->num_leaves) { a.out[leaf] = 0.0; return; }
+  double sg = 0.0, sh = 0.0;
+  for (int b = 0; b < blocks; ++b) { const double* p = a.partial + (static_cast<int64_t>(leaf) * blocks + b) * 2; sg += p[0]; sh += p[1]; }
+  double ret = -sg;
+  if (a.params.l1 > 0.0) { double r = fabs(sg) - a.params.l1; if (r < 0) r = 0; ret = -((sg > 0) - (sg < 0)) * r; }
+  ret /= (sh + a.params.l2);
+  if (a.params.max_delta_step > 0 && fabs(ret) > a.params.max_delta_step) ret = ((ret > 0) - (ret < 0)) * a.params.max_delta_step;
+  a.out[leaf] = ret;
 }
 
 // row-shard: tell every peer that this rank's local histogram for the current iteration is complete

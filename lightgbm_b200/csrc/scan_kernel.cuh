@@ -218,7 +218,7 @@ __device__ __forceinline__ Cand find_best_threshold(const double (&g)[8], const 
   Cand out;
   out.gain = -INFINITY; out.feature = f; out.threshold = 0; out.default_left = 1;
   out.lsg = out.lsh = out.lout = out.rsg = out.rsh = out.rout = 0.0; out.left_count = out.right_count = 0; out.pad = 0;
-  out.real = m.real_index; out.owner = 0;
+  out.real = m.real_index; out.owner = 0; out.ilg = 0; out.ilh = 0;
   const double sum_h = sum_h_in + 2 * B200_KEPS;
   const double min_gain_shift = leaf_gain(gc, sum_g, sum_h, num_data, parent_output) + P.min_gain_to_split;
   int splittable = 0;
@@ -249,6 +249,167 @@ __device__ __forceinline__ Cand find_best_threshold(const double (&g)[8], const 
   }
   if (two_way) {
     const DirBest fw = scan_direction<false>(g, h, lane, m, P, gc, sum_g, sum_h, num_data, min_gain_shift, parent_output, zero, na, &splittable);
+    apply(fw, false);
+  } else if (m.missing == 2) {
+    out.default_left = 0;
+  }
+  *is_splittable = splittable;
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Quantized-gradient training: FindBestThresholdSequentiallyInt (feature_histogram.hpp:1059-1350).  The histogram
+// entries are exact integer sums; the reference packs (gradient << bits | hessian) into one integer with 16- or
+// 32-bit fields chosen per leaf so that nothing overflows, i.e. plain integer arithmetic on the two sums, done here
+// on separate int64 values.  Doubles appear only at the candidate evaluation: sum * grad_scale / hess_scale, counts
+// RoundInt(int_hessian * num_data / int_sum_hessian), kEpsilon added to the hessians at the gain call only.
+struct DirBestInt {
+  double gain;
+  long long ilg, ilh;
+  int threshold, pos;
+};
+
+template <bool REVERSE>
+__device__ __noinline__ DirBestInt scan_direction_int(const long long (&g)[8], const long long (&h)[8], int lane, const FeatMeta& m,
+                                                      const Params& P, const GainCfg& gc, long long tot_g, long long tot_h,
+                                                      double gscale, double hscale, int num_data, double min_gain_shift,
+                                                      double parent_output, bool skip_default, bool na_as_missing, int* any_splittable) {
+  const double cnt_factor = static_cast<double>(num_data) / static_cast<double>(static_cast<unsigned>(tot_h));
+  const int nslice = m.nslice, offset = m.offset;
+  int e_lo, e_hi;
+  if (REVERSE) { e_lo = 1 - offset; e_hi = nslice - 1 - (na_as_missing ? 1 : 0); }
+  else { e_lo = 0; e_hi = m.num_bin - 2 - offset; }
+  const int skip_e = skip_default ? (m.default_bin - offset) : -1000;
+
+  long long tg = 0, th = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = lane * 8 + k;
+    if (e >= e_lo && e <= e_hi && e != skip_e) { tg += g[k]; th += h[k]; }
+  }
+  long long og = tg, oh = th;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    if (REVERSE) {
+      const long long xg = __shfl_down_sync(0xffffffffu, og, d), xh = __shfl_down_sync(0xffffffffu, oh, d);
+      if (lane + d < 32) { og += xg; oh += xh; }
+    } else {
+      const long long xg = __shfl_up_sync(0xffffffffu, og, d), xh = __shfl_up_sync(0xffffffffu, oh, d);
+      if (lane >= d) { og += xg; oh += xh; }
+    }
+  }
+  {
+    const long long ig = REVERSE ? __shfl_down_sync(0xffffffffu, og, 1) : __shfl_up_sync(0xffffffffu, og, 1);
+    const long long ih = REVERSE ? __shfl_down_sync(0xffffffffu, oh, 1) : __shfl_up_sync(0xffffffffu, oh, 1);
+    const bool first = REVERSE ? (lane == 31) : (lane == 0);
+    og = first ? 0 : ig; oh = first ? 0 : ih;
+  }
+  long long ag = og, ah = oh;
+  if (!REVERSE && na_as_missing && offset == 1) {
+    // implicit bin 0 = total - sum(all slice entries) (feature_histogram.hpp:1196-1214)
+    long long ag_all = 0, ah_all = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (lane * 8 + k < nslice) { ag_all += g[k]; ah_all += h[k]; } }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { ag_all += __shfl_xor_sync(0xffffffffu, ag_all, d); ah_all += __shfl_xor_sync(0xffffffffu, ah_all, d); }
+    ag = (tot_g - ag_all) + og;
+    ah = (tot_h - ah_all) + oh;
+  }
+
+  DirBestInt best; best.gain = -INFINITY; best.ilg = 0; best.ilh = 0; best.threshold = 0; best.pos = 0x7fffffff;
+  int splittable = 0;
+
+  auto evaluate = [&](long long acc_g, long long acc_h, int threshold, int pos) {
+    const int acc_c = static_cast<int>(static_cast<double>(static_cast<unsigned>(acc_h)) * cnt_factor + 0.5);
+    const double acc_hd = static_cast<double>(static_cast<unsigned>(acc_h)) * hscale;
+    if (acc_c < P.min_data_in_leaf || acc_hd < P.min_sum_hessian) return;
+    const int other_c = num_data - acc_c;
+    if (other_c < P.min_data_in_leaf) return;
+    const long long oth_g = tot_g - acc_g, oth_h = tot_h - acc_h;
+    const double other_hd = static_cast<double>(static_cast<unsigned>(oth_h)) * hscale;
+    if (other_hd < P.min_sum_hessian) return;
+    const double acc_gd = static_cast<double>(acc_g) * gscale, other_gd = static_cast<double>(oth_g) * gscale;
+    const double cur = REVERSE ? split_gain(gc, other_gd, other_hd + B200_KEPS, other_c, acc_gd, acc_hd + B200_KEPS, acc_c, parent_output)
+                               : split_gain(gc, acc_gd, acc_hd + B200_KEPS, acc_c, other_gd, other_hd + B200_KEPS, other_c, parent_output);
+    if (cur <= min_gain_shift) return;
+    splittable = 1;
+    if (cur > best.gain) {
+      best.gain = cur; best.threshold = threshold; best.pos = pos;
+      if (REVERSE) { best.ilg = oth_g; best.ilh = oth_h; } else { best.ilg = acc_g; best.ilh = acc_h; }
+    }
+  };
+
+  if (!REVERSE && na_as_missing && offset == 1 && lane == 0) evaluate(ag, ah, 0, -1);
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const int k = REVERSE ? 7 - kk : kk;
+    const int e = lane * 8 + k;
+    if (e >= e_lo && e <= e_hi && e != skip_e) {
+      ag += g[k]; ah += h[k];
+      // an empty bin leaves the sums unchanged: the candidate is a bit-identical duplicate of the previous one,
+      // which wins the reference's strict '>' — skip it
+      if (g[k] != 0 || h[k] != 0) {
+        if (REVERSE) evaluate(ag, ah, e - 1 + offset, 255 - e);
+        else evaluate(ag, ah, e + offset, e);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const double og2 = __shfl_xor_sync(0xffffffffu, best.gain, d);
+    const int op = __shfl_xor_sync(0xffffffffu, best.pos, d);
+    const long long oilg = __shfl_xor_sync(0xffffffffu, best.ilg, d);
+    const long long oilh = __shfl_xor_sync(0xffffffffu, best.ilh, d);
+    const int ot = __shfl_xor_sync(0xffffffffu, best.threshold, d);
+    if (og2 > best.gain || (og2 == best.gain && op < best.pos)) {
+      best.gain = og2; best.pos = op; best.ilg = oilg; best.ilh = oilh; best.threshold = ot;
+    }
+  }
+  if (__any_sync(0xffffffffu, splittable)) *any_splittable = 1;
+  return best;
+}
+
+// FeatureHistogram::FindBestThresholdInt (:176-189) + BeforeNumericalInt (:209-228) + output (:1303-1346)
+__device__ __forceinline__ Cand find_best_threshold_int(const long long (&g)[8], const long long (&h)[8], int lane, int f,
+                                                        const FeatMeta& m, const Params& P, const GainCfg& gc,
+                                                        long long tot_g, long long tot_h, double gscale, double hscale,
+                                                        int num_data, double parent_output, int* is_splittable) {
+  Cand out;
+  out.gain = -INFINITY; out.feature = f; out.threshold = 0; out.default_left = 1;
+  out.lsg = out.lsh = out.lout = out.rsg = out.rsh = out.rout = 0.0; out.left_count = out.right_count = 0; out.pad = 0;
+  out.real = m.real_index; out.owner = 0; out.ilg = 0; out.ilh = 0;
+  const double sum_g = static_cast<double>(static_cast<int>(tot_g)) * gscale;
+  const double sum_h = static_cast<double>(static_cast<unsigned>(tot_h)) * hscale;
+  const double min_gain_shift = leaf_gain(gc, sum_g, sum_h, num_data, parent_output) + P.min_gain_to_split;
+  const double cnt_factor = static_cast<double>(num_data) / static_cast<double>(static_cast<unsigned>(tot_h));
+  int splittable = 0;
+
+  auto apply = [&](const DirBestInt& b, bool reverse) {
+    if (splittable && b.gain > out.gain + min_gain_shift) {
+      const long long irg = tot_g - b.ilg, irh = tot_h - b.ilh;
+      const double slg = static_cast<double>(b.ilg) * gscale, slh = static_cast<double>(static_cast<unsigned>(b.ilh)) * hscale;
+      const double srg = static_cast<double>(irg) * gscale, srh = static_cast<double>(static_cast<unsigned>(irh)) * hscale;
+      const int lc = static_cast<int>(static_cast<double>(static_cast<unsigned>(b.ilh)) * cnt_factor + 0.5);
+      const int rc = static_cast<int>(static_cast<double>(static_cast<unsigned>(irh)) * cnt_factor + 0.5);
+      out.threshold = b.threshold;
+      out.lout = leaf_output(gc, slg, slh, lc, parent_output);
+      out.left_count = lc; out.lsg = slg; out.lsh = slh;
+      out.rout = leaf_output(gc, srg, srh, rc, parent_output);
+      out.right_count = rc; out.rsg = srg; out.rsh = srh;
+      out.ilg = b.ilg; out.ilh = b.ilh;
+      out.gain = b.gain - min_gain_shift;
+      out.default_left = reverse ? 1 : 0;
+    }
+  };
+
+  const bool two_way = m.num_bin > 2 && m.missing != 0;
+  const bool zero = two_way && m.missing == 1, na = two_way && m.missing == 2;
+  {
+    const DirBestInt r = scan_direction_int<true>(g, h, lane, m, P, gc, tot_g, tot_h, gscale, hscale, num_data, min_gain_shift, parent_output, zero, na, &splittable);
+    apply(r, true);
+  }
+  if (two_way) {
+    const DirBestInt fw = scan_direction_int<false>(g, h, lane, m, P, gc, tot_g, tot_h, gscale, hscale, num_data, min_gain_shift, parent_output, zero, na, &splittable);
     apply(fw, false);
   } else if (m.missing == 2) {
     out.default_left = 0;
@@ -300,7 +461,7 @@ __device__ __forceinline__ Cand cand_none() {
   Cand out;
   out.gain = -INFINITY; out.feature = -1; out.threshold = 0; out.default_left = 1;
   out.lsg = out.lsh = out.lout = out.rsg = out.rsh = out.rout = 0.0; out.left_count = out.right_count = 0; out.pad = 0;
-  out.real = 0x7fffffff; out.owner = 0;
+  out.real = 0x7fffffff; out.owner = 0; out.ilg = 0; out.ilh = 0;
   return out;
 }
 
@@ -312,7 +473,7 @@ __device__ __forceinline__ Cand cand_none() {
 // (the reduce-scatter of DataParallelTreeLearner, data_parallel_tree_learner.cpp:283+, fused into the scan's
 // load phase; int64 fixed point => the sum is exact and order-independent).  The global slice is written back
 // into this rank's own pool so that later subtractions (parent - smaller) stay local.
-template <bool ROWS>
+template <bool ROWS, bool QUANT>
 __global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const __grid_constant__ ScanArgs a) {
   pdl_enter();
   Ctl* c = a.ctl;
@@ -390,8 +551,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const __
         for (int k = 0; k < 8; ++k) { if (lane * 8 + k != m.mfb) { og += ig[k]; oh += ih[k]; } }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) { og += __shfl_xor_sync(0xffffffffu, og, d); oh += __shfl_xor_sync(0xffffffffu, oh, d); }
-        const long long tg = __double2ll_rn(LS.sum_g * c->g_scale) - og;
-        const long long th = __double2ll_rn(LS.sum_h * c->h_scale) - oh;
+        const long long tg = (QUANT ? LS.isum_g : __double2ll_rn(LS.sum_g * c->g_scale)) - og;
+        const long long th = (QUANT ? LS.isum_h : __double2ll_rn(LS.sum_h * c->h_scale)) - oh;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { if (lane * 8 + k == m.mfb) { ig[k] = tg; ih[k] = th; } }
       }
@@ -415,9 +576,38 @@ __global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const __
     int new_flag = (which == 0) ? inherit_flag0 : 2;
     if (used && !(which == 1 && larger < 0)) {
       const GainCfg gc = make_gain_cfg(a.params);
+      int splittable = 0;
+      if (QUANT) {
+        // integer histograms: the pool holds the raw sums of the discretized gradients (scale 1)
+        long long qg[8], qh[8];
+        long long tot_g, tot_h; double po; int cnt;
+        if (which == 0) {
+          const Leaf& LS = a.leaves[smaller];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { qg[k] = ig[k]; qh[k] = ih[k]; }
+          tot_g = LS.isum_g; tot_h = LS.isum_h; cnt = LS.count;
+          po = (c->num_leaves == 1)
+              ? leaf_output(GainCfg{1, 1, 0, a.params.l1, a.params.l2, a.params.max_delta_step, a.params.path_smooth}, LS.sum_g, LS.sum_h, LS.count, 0.0)
+              : LS.output;
+        } else {
+          const Leaf& LL = a.leaves[larger];
+          long long* hl = a.pool + static_cast<int64_t>(LL.slot) * a.slot_stride + slice;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int e = lane * 8 + k;
+            if (e < m.nslice) {
+              longlong2 v = *reinterpret_cast<const longlong2*>(hl + 2 * e);
+              v.x -= ig[k]; v.y -= ih[k];
+              *reinterpret_cast<longlong2*>(hl + 2 * e) = v;
+              qg[k] = v.x; qh[k] = v.y;
+            } else { qg[k] = 0; qh[k] = 0; }
+          }
+          tot_g = LL.isum_g; tot_h = LL.isum_h; cnt = LL.count; po = LL.output;
+        }
+        out = find_best_threshold_int(qg, qh, lane, f, m, a.params, gc, tot_g, tot_h, c->q_gscale, c->q_hscale, cnt, po, &splittable);
+      } else {
       const double g_inv = c->g_inv, h_inv = c->h_inv;
       double g[8], h[8];
-      int splittable = 0;
       double sum_g, sum_h, po; int cnt;
       if (which == 0) {
         const Leaf& LS = a.leaves[smaller];
@@ -445,6 +635,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, ROWS ? 1 : 2) k_scan(const __
         sum_g = LL.sum_g; sum_h = LL.sum_h; cnt = LL.count; po = LL.output;
       }
       out = find_best_threshold(g, h, lane, f, m, a.params, gc, sum_g, sum_h, cnt, po, &splittable);
+      }
       new_flag = splittable;
     }
     if (lane == 0) {

@@ -28,6 +28,13 @@ struct FeatMeta {
 struct Params {
   int32_t num_leaves, max_depth, min_data_in_leaf, pad;
   double min_sum_hessian, l1, l2, min_gain_to_split, max_delta_step, path_smooth;
+  // quantized-gradient training (reference gradient_discretizer.cpp, config.h:626-651)
+  int32_t quant;               // use_quantized_grad
+  int32_t quant_bins;          // num_grad_quant_bins
+  int32_t quant_renew;         // quant_train_renew_leaf
+  int32_t quant_stochastic;    // stochastic_rounding
+  int32_t quant_const_hess;    // is_constant_hessian passed to Init
+  int32_t quant_seed;
 };
 
 // The best split found for one (leaf[, feature]) — reference split_info.hpp:22-56
@@ -42,6 +49,7 @@ struct Cand {
   int32_t real;                // real (global) feature index: the cross-feature / cross-rank tie-break key
   int32_t owner;               // rank that owns `feature` (feature-shard mode); 0 on a single GPU
   int32_t pad;
+  long long ilg, ilh;          // quantized training: exact integer left sums (SplitInfo::left_sum_gradient_and_hessian)
 };
 
 // LeafSplits + DataPartition entry + HistogramPool slot of one leaf
@@ -52,6 +60,7 @@ struct Leaf {
   int32_t slot;                // histogram pool slot
   int32_t lcount;              // rows of this leaf held by THIS rank (== count except in row-shard mode)
   double sum_g, sum_h, output; // leaf_splits.hpp: sum_gradients_, sum_hessians_, weight_
+  long long isum_g, isum_h;    // quantized training: int_sum_gradients_and_hessians_ (leaf_splits.hpp:66-74), unpacked
   Cand best;                   // best_split_per_leaf_[leaf]
 };
 
@@ -70,6 +79,9 @@ struct Ctl {
   // fixed-point scales of the int64 histogram (power of two), set once per tree
   double g_scale, h_scale, g_inv, h_inv;
   double root_sum_g, root_sum_h;
+  // quantized training: GradientDiscretizer::grad_scale() / hess_scale() of this tree and their inverses
+  double q_gscale, q_hscale, q_ginv, q_hinv;
+  unsigned long long quant_iter;   // trees discretized so far (stochastic rounding stream id)
   int32_t root_count;          // rows in the root (bag size or num_data)
   int32_t root_identity;       // 1: root index list is 0..N-1 (no bagging) => histogram skips the index load
   // ---- multi-GPU (feature-shard) state; persistent across trees

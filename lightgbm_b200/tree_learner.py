@@ -22,7 +22,9 @@ class _CConfig(C.Structure):
     _fields_ = [("num_leaves", C.c_int32), ("max_depth", C.c_int32), ("min_data_in_leaf", C.c_int32),
                 ("gpu_device_id", C.c_int32), ("min_sum_hessian_in_leaf", C.c_double), ("lambda_l1", C.c_double),
                 ("lambda_l2", C.c_double), ("min_gain_to_split", C.c_double), ("max_delta_step", C.c_double),
-                ("path_smooth", C.c_double), ("use_cuda_graph", C.c_int32), ("reserved", C.c_int32)]
+                ("path_smooth", C.c_double), ("use_cuda_graph", C.c_int32), ("reserved", C.c_int32),
+                ("use_quantized_grad", C.c_int32), ("num_grad_quant_bins", C.c_int32), ("quant_train_renew_leaf", C.c_int32),
+                ("stochastic_rounding", C.c_int32), ("seed", C.c_int32), ("pad_", C.c_int32)]
 
 
 class _CLayout(C.Structure):
@@ -48,7 +50,8 @@ assert SPLIT_DTYPE.itemsize == C.sizeof(_CSplit)
 class _CTree(C.Structure):
     _fields_ = [("num_leaves", C.c_int32), ("splits", C.c_void_p), ("leaf_value", C.c_void_p),
                 ("leaf_weight", C.c_void_p), ("leaf_count", C.c_void_p), ("leaf_depth", C.c_void_p),
-                ("root_sum_gradient", C.c_double), ("root_sum_hessian", C.c_double)]
+                ("root_sum_gradient", C.c_double), ("root_sum_hessian", C.c_double),
+                ("grad_scale", C.c_double), ("hess_scale", C.c_double)]
 
 
 @dataclass
@@ -66,11 +69,18 @@ class Config:
     gpu_device_id: int = -1
     use_cuda_graph: bool = True
     reserved: int = int(os.environ.get("LGBMB200_RESERVED", "0"))   # experiment switches, see include/lgbm_b200.h
+    use_quantized_grad: bool = False      # reference config.h:626-651
+    num_grad_quant_bins: int = 4
+    quant_train_renew_leaf: bool = False
+    stochastic_rounding: bool = True
+    seed: int = 0
 
     def to_c(self) -> _CConfig:
         return _CConfig(self.num_leaves, self.max_depth, self.min_data_in_leaf, self.gpu_device_id,
                         self.min_sum_hessian_in_leaf, self.lambda_l1, self.lambda_l2, self.min_gain_to_split,
-                        self.max_delta_step, self.path_smooth, 1 if self.use_cuda_graph else 0, int(self.reserved))
+                        self.max_delta_step, self.path_smooth, 1 if self.use_cuda_graph else 0, int(self.reserved),
+                        1 if self.use_quantized_grad else 0, int(self.num_grad_quant_bins),
+                        1 if self.quant_train_renew_leaf else 0, 1 if self.stochastic_rounding else 0, int(self.seed), 0)
 
 
 @dataclass
@@ -273,11 +283,13 @@ class B200TreeLearner:
         splits = np.zeros(nl - 1, dtype=SPLIT_DTYPE)
         lv, lw = np.zeros(nl), np.zeros(nl)
         lc, ld = np.zeros(nl, np.int32), np.zeros(nl, np.int32)
-        t = _CTree(0, _p(splits), _p(lv), _p(lw), _p(lc), _p(ld), 0.0, 0.0)
+        t = _CTree(0, _p(splits), _p(lv), _p(lw), _p(lc), _p(ld), 0.0, 0.0, 0.0, 0.0)
         check(lib().LGBMB200_LearnerTrain(self.handle, gp, hp, C.c_int32(gd), C.byref(t)))
         n = t.num_leaves
-        return Tree(n, splits[:n - 1].copy(), lv[:n].copy(), lw[:n].copy(), lc[:n].copy(), ld[:n].copy(),
+        tree = Tree(n, splits[:n - 1].copy(), lv[:n].copy(), lw[:n].copy(), lc[:n].copy(), ld[:n].copy(),
                     t.root_sum_gradient, t.root_sum_hessian)
+        tree.grad_scale, tree.hess_scale = t.grad_scale, t.hess_scale     # use_quantized_grad: this tree's scales
+        return tree
 
     # void TreeLearner::AddPredictionToScore(const Tree* tree, double* out_score)
     def add_prediction_to_score(self, tree: Tree, out_score) -> None:
