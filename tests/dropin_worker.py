@@ -13,6 +13,8 @@ from oracle import refapi  # noqa: E402
 def main():
     device, n, f, iters, case = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
     rng = np.random.default_rng(17)
+    quant = case.endswith("_quant")        # Config::use_quantized_grad through the real C API
+    case = case.replace("_quant", "")
     if case == "identity":
         X = rng.integers(0, 255, (n, f)).astype(np.float32)
         y = ((X[:, :6] / 127.0 - 1) @ rng.normal(size=6) + 0.3 * rng.normal(size=n)).astype(np.float32)
@@ -30,6 +32,9 @@ def main():
     ds = refapi.RefDataset(X, y, dsp)
     bp = dict(dsp, objective=obj, num_leaves=31, learning_rate=0.1, min_data_in_leaf=20, device_type=device,
               force_row_wise="true", deterministic="true", num_threads=1 if device == "cpu" else 4)
+    if quant:
+        bp.update(use_quantized_grad="true", stochastic_rounding="false", num_grad_quant_bins=4 if case == "identity" else 8,
+                  quant_train_renew_leaf="false" if case == "identity" else "true")
     bst = refapi.RefBooster(ds, bp)
     for _ in range(iters):
         bst.update()

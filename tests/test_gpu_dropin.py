@@ -40,3 +40,20 @@ def test_lgbm_capi_device_cuda_matches_reference_cpu(case, n, f):
     assert g0["leaf_count"] == c0["leaf_count"] or g0["split_feature"] != c0["split_feature"]
     # the reference's own CPU<->GPU criterion (test_dual.py:35-36): predictions agree
     np.testing.assert_allclose(gpu["pred"], cpu["pred"], rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.skipif(not (os.path.exists(DROPIN) and os.path.exists(REFLIB)), reason="drop-in / reference library not built")
+@pytest.mark.parametrize("case,n,f", [("identity_quant", 20000, 12), ("mixed_quant", 20000, 10)])
+def test_lgbm_capi_quantized_training_matches_reference_cpu(case, n, f):
+    """use_quantized_grad=true, stochastic_rounding=false through the real LGBM_* API: integer histograms are exact, so
+    the first tree of the drop-in (device_type=cuda -> B200TreeLearner) must be the reference CPU learner's tree."""
+    iters = 4
+    gpu = run(DROPIN, "cuda", n, f, iters, case)
+    cpu = run(REFLIB, "cpu", n, f, iters, case)
+    assert gpu["num_trees"] == cpu["num_trees"] == iters
+    g0, c0 = gpu["trees"][0], cpu["trees"][0]
+    assert g0["split_feature"] == c0["split_feature"] and g0["leaf_count"] == c0["leaf_count"]
+    np.testing.assert_allclose(g0["threshold"], c0["threshold"], rtol=1e-12)
+    np.testing.assert_allclose(g0["split_gain"], c0["split_gain"], rtol=1e-6)      # stored as float32 text
+    np.testing.assert_allclose(g0["leaf_value"], c0["leaf_value"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gpu["pred"], cpu["pred"], rtol=2e-3, atol=2e-3)
