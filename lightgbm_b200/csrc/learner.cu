@@ -19,6 +19,7 @@
 
 #include "../../include/lgbm_b200.h"
 #include "hist_kernel.cuh"
+#include "hist_q_kernel.cuh"
 #include "partition_kernel.cuh"
 #include "scan_kernel.cuh"
 #include "types.cuh"
@@ -84,6 +85,7 @@ class Learner {
     params_.quant_stochastic = cfg.stochastic_rounding ? 1 : 0;
     params_.quant_const_hess = const_hess_ ? 1 : 0;
     params_.quant_seed = cfg.seed;
+    if (params_.quant && inited_ && ghq_.n < static_cast<size_t>(N_)) ghq_.alloc(N_);
     if (params_.quant) {
       REQUIRE(cfg.num_grad_quant_bins >= 2 && cfg.num_grad_quant_bins <= 127, "num_grad_quant_bins must be in [2, 127] (int8 gradients)");
       REQUIRE(!(peers_.world > 1 && peers_.mode == 1), "use_quantized_grad is not supported in row-shard mode");
@@ -139,6 +141,7 @@ class Learner {
     grad_stage_.alloc(N_); hess_stage_.alloc(N_);
     const_hess_ = is_constant_hessian != 0; hess_fill_valid_ = false;
     params_.quant_const_hess = const_hess_ ? 1 : 0;
+    if (params_.quant) ghq_.alloc(N_); else ghq_.release();
     part_blocks_ = num_sms_ * 2;
     if (part_blocks_ > 1024) part_blocks_ = 1024;
     block_left_.alloc(part_blocks_);
@@ -154,6 +157,8 @@ class Learner {
     bag_count_ = -1;
     CUDA_CHECK(cudaFuncSetAttribute(k_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
     CUDA_CHECK(cudaFuncSetAttribute(k_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+    CUDA_CHECK(cudaFuncSetAttribute(k_hist_q, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmemBytes));
+    CUDA_CHECK(cudaFuncSetAttribute(k_hist_q, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_CHECK(cudaFuncSetAttribute(k_hist2, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
     BuildTensorMap();
     inited_ = true;
@@ -577,6 +582,7 @@ class Learner {
     pa.bag = bag_count_ >= 0 ? bag_.p : nullptr; pa.bag_count = bag_count_ >= 0 ? bag_count_ : 0;
     pa.num_data = N_; pa.partials = partials_.p; pa.leaves = leaves_.p; pa.ctl = ctl_.p; pa.params = params_;
     pa.max_leaves = params_.num_leaves; pa.num_partials = prep_blocks_; pa.peers = peers_;
+    pa.ghq = PackedQuantHist() ? ghq_.p : nullptr;
     return pa;
   }
   HistArgs MakeHistArgs() {
@@ -617,8 +623,15 @@ class Learner {
   // reserved bit 3 selects the experimental split kernel k_hist2 (separate gradient / hessian consumer warps,
   // 6 consumers per SM).  Measured 12 % SLOWER than k_hist on 4M x 1024 (5.45 vs 4.85 ms): the kernel is bound by
   // shared-memory wavefronts, not by latency, and the split re-reads the staged bins — kept for the record.
+  // quantized training: packed 16:16 cells whenever a flush interval of at least 4096 rows keeps both fields in
+  // range (num_grad_quant_bins <= 15; reserved bit 6 forces the int32x2-cell kernel for A/B runs)
+  bool PackedQuantHist() const { return params_.quant && params_.quant_bins <= 15 && !(cfg_.reserved & 64); }
+
   void LaunchHist(const HistArgs& ha, bool chain = false, bool quant = false) {
-    if (quant) LaunchChain(chain, k_hist<true>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
+    if (quant && PackedQuantHist()) {
+      HistQArgs qa{ha, ghq_.p, ((65535 / params_.quant_bins) / kStageRows) * kStageRows};
+      LaunchChain(chain, k_hist_q, dim3(num_sms_ * 2), dim3(kHistThreads), kQSmemBytes, qa, tmap_);
+    } else if (quant) LaunchChain(chain, k_hist<true>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
     else if (cfg_.reserved & 8) LaunchChain(chain, k_hist2, dim3(num_sms_), dim3(kHist2Threads), kHistSmemBytes, ha, tmap_);
     else LaunchChain(chain, k_hist<false>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
   }
@@ -799,6 +812,7 @@ class Learner {
   DevBuf<float2> gh_;
   static constexpr int kRenewBlocks = 64;
   DevBuf<double> renew_partial_, renew_out_;
+  DevBuf<int32_t> ghq_;            // quantized training: packed (g << 16) + h per row
   double* h_renew_ = nullptr;
   DevBuf<float> grad_stage_, hess_stage_;
   bool const_hess_ = false, hess_fill_valid_ = false;

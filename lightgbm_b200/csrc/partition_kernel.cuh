@@ -315,6 +315,7 @@ struct PrepArgs {
   int32_t max_leaves;
   int32_t num_partials;
   CommPeers peers;
+  int32_t* ghq;             // quantized training: packed (g << 16) + h per row for k_hist_q, or nullptr
 };
 
 constexpr int kPrepThreads = 256;
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_quantize(const PrepArgs a) {
   for (int i = lo + threadIdx.x; i < hi; i += kPrepThreads) {
     const int2 q = quantize_row(a, c, i);
     a.gh[i] = make_float2(__int_as_float(q.x), __int_as_float(q.y));
+    if (a.ghq != nullptr) a.ghq[i] = q.x * 65536 + q.y;
     mg = max(mg, abs(q.x)); mh = max(mh, abs(q.y));
     if (a.bag == nullptr) { sg += q.x; sh += q.y; }
   }

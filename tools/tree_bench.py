@@ -11,7 +11,10 @@ trees = int(os.environ.get("TB_TREES", 3))
 rng = np.random.default_rng(0)
 bins = rng.integers(0, 255, (n, f), dtype=np.uint8)
 y = ((bins[:, :32] / 127.0 - 1) @ rng.normal(size=32) + 0.5 * rng.normal(size=n)).astype(np.float32)
-B = lgb.B200Booster(lgb.Layout.identity(bins), y, lgb.Config(num_leaves=leaves, use_cuda_graph=os.environ.get("TB_GRAPH", "1") == "1"), learning_rate=0.1)
+qb = int(os.environ.get("TB_QUANT", 0))          # > 0: use_quantized_grad with that many num_grad_quant_bins
+cfg = lgb.Config(num_leaves=leaves, use_cuda_graph=os.environ.get("TB_GRAPH", "1") == "1", use_quantized_grad=qb > 0,
+                 num_grad_quant_bins=max(qb, 2), stochastic_rounding=os.environ.get("TB_STOCH", "0") == "1")
+B = lgb.B200Booster(lgb.Layout.identity(bins), y, cfg, learning_rate=0.1)
 ms, h = [], hashlib.sha1()
 for _ in range(trees):
     B.learner.timer_start()
@@ -19,5 +22,8 @@ for _ in range(trees):
     ms.append(B.learner.timer_stop())
     h.update(t.splits.tobytes()); h.update(t.leaf_value.tobytes())
 warm = ms[min(2, len(ms) - 1):]
-print(f"reserved={lgb.Config().reserved} rows={n} cols={f} leaves={leaves} device_ms_per_tree mean={np.mean(warm):.3f} min={np.min(warm):.3f} "
+if os.environ.get("TB_PROFILE"):
+    B.learner.set_profiling(True); B.learner.hist_stats(reset=True); B.update(); B.learner.set_profiling(False)
+    print("by_kind_ms", {k: round(v, 3) for k, v in B.learner.profile_by_kind().items()}, "l2", B.l2())
+print(f"quant_bins={qb} reserved={lgb.Config().reserved} rows={n} cols={f} leaves={leaves} device_ms_per_tree mean={np.mean(warm):.3f} min={np.min(warm):.3f} "
       f"trees_sha1={h.hexdigest()[:16]}")
