@@ -167,6 +167,8 @@ def run_reference(args, wl, rank, world):
     while True:
         bp = dict(dsp, objective="regression", num_leaves=wl["leaves"], learning_rate=0.1, min_data_in_leaf=20,
                   device_type="cpu", num_threads=threads)
+        if getattr(args, "quantized", 0):
+            bp.update(use_quantized_grad="true", num_grad_quant_bins=args.quantized)
         bst = refapi.RefBooster(ds, bp)
         t0 = time.time()
         bst.update()
@@ -202,6 +204,8 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=500_000, help="row sample for the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--quantized", type=int, default=0, metavar="Q",
+                    help="NOT the headline: train with use_quantized_grad=true, num_grad_quant_bins=Q (both arms)")
     ap.add_argument("--no-replicate", action="store_true",
                     help="N>1: keep one copy of the partition columns across the box (the split's owner pushes go-left bits)")
     args = ap.parse_args()
@@ -211,7 +215,8 @@ def main():
     if args.rows:
         wl["rows"] = args.rows
     config = {"workload": f"{args.workload}: {wl['rows']} rows x {wl['cols']} dense features, 255 bins, {wl['leaves']} leaves, "
-                          f"L2 regression, min_data_in_leaf=20, lr=0.1",
+                          f"L2 regression, min_data_in_leaf=20, lr=0.1" +
+                          (f", use_quantized_grad num_grad_quant_bins={args.quantized} (NOT the BASELINE configuration)" if args.quantized else ""),
               "parallelism": (f"feature-shard x{world}" + ("" if args.no_replicate else ", partition columns replicated on every GPU"))
               if world > 1 else "single GPU",
               "l2_flush": "inputs larger than L2 (bin matrix 10.24 GB >> 126 MB)" if wl["rows"] * wl["cols"] > 2e9 else
@@ -248,7 +253,8 @@ def main():
     y = gen_label(rows, cols, wl["seed"], first32)
     lay = lgb.Layout.identity(bins)
     lay.feat_real_index = np.arange(lo, hi, dtype=np.int32)
-    cfg = lgb.Config(num_leaves=leaves, min_data_in_leaf=20, gpu_device_id=local, use_cuda_graph=True)
+    cfg = lgb.Config(num_leaves=leaves, min_data_in_leaf=20, gpu_device_id=local, use_cuda_graph=True,
+                     use_quantized_grad=args.quantized > 0, num_grad_quant_bins=max(args.quantized, 2), stochastic_rounding=True)
     L = D.make_sharded_learner(lay, cfg, rank, world, replicate_columns=not args.no_replicate,
                                is_constant_hessian=True)      # unweighted L2: IsConstantHessian()
     B = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=True, learner=L)
@@ -342,7 +348,8 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": "iters/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "fp32 partial sums -> int64 fixed-point histograms, f64 gain scan", "data": "synthetic",
+            "dtype": ("int8 gradients -> packed int16:int16 histogram cells -> int64 pool, f64 gain scan" if args.quantized else
+                      "fp32 partial sums -> int64 fixed-point histograms, f64 gain scan"), "data": "synthetic",
             "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "wall_ms_per_step": wall * 1e3 / args.steps, "final_train_l2": final_l2}
     print(json.dumps(line), flush=True)
