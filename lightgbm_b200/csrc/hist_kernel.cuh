@@ -73,8 +73,6 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
 }
-constexpr int kIdxPrefetchStages = 8;
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -322,9 +320,6 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
           continue;
         }
         // row ids: lane -> (g,h) of row p0+lane; lane pair -> 32-byte bin segment of rows p0+lane/2 and +16
-        // the row ids of a stage are one 128-byte line of the leaf's index list: pull the line of a later stage into
-        // L1 now, so that the three dependent id loads below hit L1 instead of paying an L2 round trip per stage
-        if (ip != nullptr && lane == 0 && p0 + kIdxPrefetchStages * kStageRows < r1) prefetch_l1(ip + p0 + kIdxPrefetchStages * kStageRows);
         const int pa = p0 + (lane >> 1), pb = pa + 16, pg = p0 + lane;
         int ra = -1, rb = -1, rg = -1;
         if (pa < r1) ra = ip ? __ldg(ip + pa) : pa;
@@ -547,9 +542,6 @@ __global__ void __launch_bounds__(kHist2Threads, 1) k_hist2(const HistArgs a, co
           continue;
         }
         // row ids: lane -> (g,h) of row p0+lane; lane pair -> 32-byte bin segment of rows p0+lane/2 and +16
-        // the row ids of a stage are one 128-byte line of the leaf's index list: pull the line of a later stage into
-        // L1 now, so that the three dependent id loads below hit L1 instead of paying an L2 round trip per stage
-        if (ip != nullptr && lane == 0 && p0 + kIdxPrefetchStages * kStageRows < r1) prefetch_l1(ip + p0 + kIdxPrefetchStages * kStageRows);
         const int pa = p0 + (lane >> 1), pb = pa + 16, pg = p0 + lane;
         int ra = -1, rb = -1, rg = -1;
         if (pa < r1) ra = ip ? __ldg(ip + pa) : pa;

@@ -96,9 +96,6 @@ __global__ void __launch_bounds__(kHistThreads, 2) k_hist_q(const HistQArgs qa, 
           if (++slot == kQStages) { slot = 0; phase ^= 1; }
           continue;
         }
-        // the row ids of a stage are one 128-byte line of the leaf's index list: pull the line of a later stage into
-        // L1 now, so that the three dependent id loads below hit L1 instead of paying an L2 round trip per stage
-        if (ip != nullptr && lane == 0 && p0 + kIdxPrefetchStages * kStageRows < r1) prefetch_l1(ip + p0 + kIdxPrefetchStages * kStageRows);
         const int pa = p0 + (lane >> 1), pb = pa + 16, pg = p0 + lane;
         int ra = -1, rb = -1, rg = -1;
         if (pa < r1) ra = ip ? __ldg(ip + pa) : pa;
