@@ -593,6 +593,7 @@ class Learner {
     ha.explicit_n = -1; ha.explicit_slot = 0; ha.explicit_idx = nullptr;
     ha.use_tma = have_tmap_ ? 1 : 0;
     ha.map_mode = (cfg_.reserved & 4) ? 0 : 1;
+    ha.l2_prefetch = (cfg_.reserved & 128) ? 0 : 16;
     return ha;
   }
 
