@@ -58,6 +58,10 @@ struct HistArgs {
   int32_t num_colgroups;          // ceil(num_columns / 32)
   int32_t min_rows_per_item;      // do not split a column group over more warps than n / this
   int32_t use_tma;                // 1: contiguous (root, un-bagged) stages are staged by TMA tile copies
+  const int32_t* ghqo0;           // leaf-ordered packed quantized words (k_hist_q), or nullptr
+  const int32_t* ghqo1;
+  const float2* gho0;             // leaf-ordered (g,h) parallel to idx0 / idx1 (written by k_part_scatter), or nullptr
+  const float2* gho1;
   int32_t l2_prefetch;            // > 0: gathered passes prefetch the bin sectors of the stage this many stages ahead into L2
   int32_t map_mode;               // 0: items dealt column-group-major; 1: one CTA = (column group, 3 row parts), adjacent CTAs = adjacent column groups
   // explicit mode (stand-alone ConstructHistogram hook): explicit_n >= 0
@@ -183,6 +187,8 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, un
 struct HistWork {
   int n, begin, slot;
   const int32_t* idx;
+  const float2* gh_ord;          // non-root leaf: (g,h) in leaf order (position-indexed), else nullptr => gather by row id
+  const int32_t* ghq_ord;        // same for the packed quantized word (k_hist_q)
   int CG, splits, per, items, total_warps;
   int mode, rounds_total;        // mode 1: rounds_total = CG * ceil(splits/3) virtual CTAs
 };
@@ -190,6 +196,7 @@ struct HistWork {
 __device__ __forceinline__ bool hist_work_setup(const HistArgs& a, HistWork* w) {
   if (a.explicit_n >= 0) {
     w->n = a.explicit_n; w->begin = 0; w->slot = a.explicit_slot; w->idx = a.explicit_idx;
+    w->gh_ord = nullptr; w->ghq_ord = nullptr;
   } else {
     const Ctl* c = a.ctl;
     if (!c->cur_valid || !c->do_find) return false;
@@ -197,6 +204,9 @@ __device__ __forceinline__ bool hist_work_setup(const HistArgs& a, HistWork* w) 
     w->n = L.lcount; w->begin = L.begin; w->slot = L.slot;
     // the root of an un-bagged tree is the identity list: skip the index load altogether
     w->idx = (c->num_leaves == 1 && c->root_identity) ? nullptr : (L.buf ? a.idx1 : a.idx0);
+    // every non-root segment was written by its parent's scatter, together with its (g,h) copy
+    w->gh_ord = (c->num_leaves > 1 && a.gho0 != nullptr) ? (L.buf ? a.gho1 : a.gho0) + L.begin : nullptr;
+    w->ghq_ord = (c->num_leaves > 1 && a.ghqo0 != nullptr) ? (L.buf ? a.ghqo1 : a.ghqo0) + L.begin : nullptr;
   }
   if (w->n <= 0) return false;
   w->total_warps = gridDim.x * kHistWarps;
@@ -342,12 +352,12 @@ __global__ void __launch_bounds__(kHistThreads, 1) k_hist(const HistArgs a, cons
         int ra = -1, rb = -1, rg = -1;
         if (pa < r1) ra = ip ? __ldg(ip + pa) : pa;
         if (pb < r1) rb = ip ? __ldg(ip + pb) : pb;
-        if (pg < r1) rg = ip ? __ldg(ip + pg) : pg;
+        if (pg < r1) rg = (w.gh_ord != nullptr) ? pg : (ip ? __ldg(ip + pg) : pg);       // leaf-ordered copy: the position IS the index
         mbar_wait_parked(empty + slot, phase ^ 1);           // the consumer released this ring slot
         unsigned char* sb = ring + slot * kStageBytes;
         if (ra >= 0) cp_async16(sb + (lane >> 1) * kColGroup + half, colbase + static_cast<int64_t>(ra) * a.pitch + half);
         if (rb >= 0) cp_async16(sb + (16 + (lane >> 1)) * kColGroup + half, colbase + static_cast<int64_t>(rb) * a.pitch + half);
-        if (rg >= 0) cp_async8(sb + kStageBinBytes + lane * 8, a.gh + rg);
+        if (rg >= 0) cp_async8(sb + kStageBinBytes + lane * 8, (w.gh_ord != nullptr ? w.gh_ord : a.gh) + rg);
         mbar_arrive_on_cp_async(full + slot);
         if (++slot == kStages) { slot = 0; phase ^= 1; }
       }
@@ -579,12 +589,12 @@ __global__ void __launch_bounds__(kHist2Threads, 1) k_hist2(const HistArgs a, co
         int ra = -1, rb = -1, rg = -1;
         if (pa < r1) ra = ip ? __ldg(ip + pa) : pa;
         if (pb < r1) rb = ip ? __ldg(ip + pb) : pb;
-        if (pg < r1) rg = ip ? __ldg(ip + pg) : pg;
+        if (pg < r1) rg = (w.gh_ord != nullptr) ? pg : (ip ? __ldg(ip + pg) : pg);       // leaf-ordered copy: the position IS the index
         mbar_wait_parked(empty + slot, phase ^ 1);           // the consumer released this ring slot
         unsigned char* sb = ring + slot * kStageBytes;
         if (ra >= 0) cp_async16(sb + (lane >> 1) * kColGroup + half, colbase + static_cast<int64_t>(ra) * a.pitch + half);
         if (rb >= 0) cp_async16(sb + (16 + (lane >> 1)) * kColGroup + half, colbase + static_cast<int64_t>(rb) * a.pitch + half);
-        if (rg >= 0) cp_async8(sb + kStageBinBytes + lane * 8, a.gh + rg);
+        if (rg >= 0) cp_async8(sb + kStageBinBytes + lane * 8, (w.gh_ord != nullptr ? w.gh_ord : a.gh) + rg);
         mbar_arrive_on_cp_async(full + slot);
         if (++slot == kStages) { slot = 0; phase ^= 1; }
       }

@@ -115,12 +115,12 @@ __global__ void __launch_bounds__(kHistThreads, 2) k_hist_q(const HistQArgs qa, 
         int ra = -1, rb = -1, rg = -1;
         if (pa < r1) ra = ip ? __ldg(ip + pa) : pa;
         if (pb < r1) rb = ip ? __ldg(ip + pb) : pb;
-        if (pg < r1) rg = ip ? __ldg(ip + pg) : pg;
+        if (pg < r1) rg = (w.ghq_ord != nullptr) ? pg : (ip ? __ldg(ip + pg) : pg);
         mbar_wait_parked(empty + slot, phase ^ 1);
         unsigned char* sb = ring + slot * kQStageBytes;
         if (ra >= 0) cp_async16(sb + (lane >> 1) * kColGroup + half, colbase + static_cast<int64_t>(ra) * a.pitch + half);
         if (rb >= 0) cp_async16(sb + (16 + (lane >> 1)) * kColGroup + half, colbase + static_cast<int64_t>(rb) * a.pitch + half);
-        if (rg >= 0) cp_async4(sb + kStageBinBytes + lane * 4, qa.ghq + rg);
+        if (rg >= 0) cp_async4(sb + kStageBinBytes + lane * 4, (w.ghq_ord != nullptr ? w.ghq_ord : qa.ghq) + rg);
         mbar_arrive_on_cp_async(full + slot);
         if (++slot == kQStages) { slot = 0; phase ^= 1; }
       }

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/lgbm_b200.h"
@@ -85,7 +86,7 @@ class Learner {
     params_.quant_stochastic = cfg.stochastic_rounding ? 1 : 0;
     params_.quant_const_hess = const_hess_ ? 1 : 0;
     params_.quant_seed = cfg.seed;
-    if (params_.quant && inited_ && ghq_.n < static_cast<size_t>(N_)) ghq_.alloc(N_);
+    if (params_.quant && inited_ && ghq_.n < static_cast<size_t>(N_)) { ghq_.alloc(N_); ghqo0_.alloc(N_); ghqo1_.alloc(N_); }
     if (params_.quant) {
       REQUIRE(cfg.num_grad_quant_bins >= 2 && cfg.num_grad_quant_bins <= 127, "num_grad_quant_bins must be in [2, 127] (int8 gradients)");
       REQUIRE(!(peers_.world > 1 && peers_.mode == 1), "use_quantized_grad is not supported in row-shard mode");
@@ -137,11 +138,11 @@ class Learner {
     } else {
       binsT_.release();
     }
-    gh_.alloc(N_); idx0_.alloc(N_); idx1_.alloc(N_); flags_.alloc((static_cast<size_t>(N_) + 31) / 32 * 4 + 256);
+    gh_.alloc(N_); gho0_.alloc(N_); gho1_.alloc(N_); idx0_.alloc(N_); idx1_.alloc(N_); flags_.alloc((static_cast<size_t>(N_) + 31) / 32 * 4 + 256);
     grad_stage_.alloc(N_); hess_stage_.alloc(N_);
     const_hess_ = is_constant_hessian != 0; hess_fill_valid_ = false;
     params_.quant_const_hess = const_hess_ ? 1 : 0;
-    if (params_.quant) ghq_.alloc(N_); else ghq_.release();
+    if (params_.quant) { ghq_.alloc(N_); ghqo0_.alloc(N_); ghqo1_.alloc(N_); } else { ghq_.release(); ghqo0_.release(); ghqo1_.release(); }
     part_blocks_ = num_sms_ * 2;
     if (part_blocks_ > 1024) part_blocks_ = 1024;
     block_left_.alloc(part_blocks_);
@@ -593,7 +594,10 @@ class Learner {
     ha.explicit_n = -1; ha.explicit_slot = 0; ha.explicit_idx = nullptr;
     ha.use_tma = have_tmap_ ? 1 : 0;
     ha.map_mode = (cfg_.reserved & 4) ? 0 : 1;
-    ha.l2_prefetch = (cfg_.reserved & 128) ? 0 : 16;
+    // distance tuned on 4M x 1024 (tools/tree_bench.py); LGBMB200_PF overrides it for experiments
+    static const int pf_stages = std::getenv("LGBMB200_PF") ? std::atoi(std::getenv("LGBMB200_PF")) : 16;
+    ha.l2_prefetch = (cfg_.reserved & 128) ? 0 : pf_stages;
+    ha.gho0 = nullptr; ha.gho1 = nullptr; ha.ghqo0 = nullptr; ha.ghqo1 = nullptr;      // set by EnqueueTree
     return ha;
   }
 
@@ -672,6 +676,11 @@ class Learner {
     pt.bins = bins_.p; pt.binsT = peers_.mode == 2 ? binsT_full_.p : binsT_.p; pt.num_data = N_; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flag_words = reinterpret_cast<uint32_t*>(flags_.p);
     pt.block_left = block_left_.p; pt.leaves = leaves_.p; pt.ctl = ctl_.p; pt.splits = splits_.p; pt.params = params_;
     pt.peers = peers_;
+    const bool ordered = !(cfg_.reserved & 256);
+    const bool packed = PackedQuantHist();
+    pt.gh = gh_.p; pt.gho0 = (ordered && !packed) ? gho0_.p : nullptr; pt.gho1 = (ordered && !packed) ? gho1_.p : nullptr;
+    pt.ghq = ghq_.p; pt.ghqo0 = (ordered && packed) ? ghqo0_.p : nullptr; pt.ghqo1 = (ordered && packed) ? ghqo1_.p : nullptr;
+    ha.gho0 = pt.gho0; ha.gho1 = pt.gho1; ha.ghqo0 = pt.ghqo0; ha.ghqo1 = pt.ghqo1;
     prof_n_ = 0;
     Stamp(kProfStart);
 
@@ -810,7 +819,8 @@ class Learner {
   DevBuf<FeatMeta> gmeta_;
   DevBuf<uint8_t> bins_, binsT_, flags_, feature_used_, splittable_, splittable_new_;
   DevBuf<BlockBest> block_best_;
-  DevBuf<float2> gh_;
+  DevBuf<float2> gh_, gho0_, gho1_;     // (g,h) by row id; leaf-ordered copies parallel to idx0_/idx1_
+  DevBuf<int32_t> ghqo0_, ghqo1_;
   static constexpr int kRenewBlocks = 64;
   DevBuf<double> renew_partial_, renew_out_;
   DevBuf<int32_t> ghq_;            // quantized training: packed (g << 16) + h per row
