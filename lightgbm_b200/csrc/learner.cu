@@ -595,7 +595,7 @@ class Learner {
     ha.use_tma = have_tmap_ ? 1 : 0;
     ha.map_mode = (cfg_.reserved & 4) ? 0 : 1;
     // distance tuned on 4M x 1024 (tools/tree_bench.py); LGBMB200_PF overrides it for experiments
-    static const int pf_stages = std::getenv("LGBMB200_PF") ? std::atoi(std::getenv("LGBMB200_PF")) : 16;
+    static const int pf_stages = std::getenv("LGBMB200_PF") ? std::atoi(std::getenv("LGBMB200_PF")) : 8;
     ha.l2_prefetch = (cfg_.reserved & 128) ? 0 : pf_stages;
     ha.gho0 = nullptr; ha.gho1 = nullptr; ha.ghqo0 = nullptr; ha.ghqo1 = nullptr;      // set by EnqueueTree
     return ha;
