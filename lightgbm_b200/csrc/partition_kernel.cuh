@@ -199,6 +199,10 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
   __syncthreads();
   const int total_left = s_total;
   int left_run = s_before;          // lefts before the current tile (whole leaf)
+  // only the smaller child gets a histogram pass (the larger one is parent - smaller), so only its rows need the
+  // leaf-ordered (g,h) copy; row-shard decides smaller/larger on GLOBAL counts after this kernel's exchange: copy both
+  const bool copy_both = a.peers.world > 1 && a.peers.mode == 1;
+  const bool left_smaller = total_left < n - total_left;        // same rule as the bookkeeping below (:858)
 
   int lo, hi;
   part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
@@ -215,8 +219,9 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
     }
 #pragma unroll
     for (int k = 0; k < kPartUnroll; ++k) {
-      gv[k] = (gho != nullptr && row[k] >= 0) ? __ldg(a.gh + row[k]) : make_float2(0.f, 0.f);
-      qv[k] = (ghqo != nullptr && row[k] >= 0) ? __ldg(a.ghq + row[k]) : 0;
+      const bool mine = copy_both || ((((word[k] >> lane) & 1u) != 0u) == left_smaller);
+      gv[k] = (gho != nullptr && row[k] >= 0 && mine) ? __ldg(a.gh + row[k]) : make_float2(0.f, 0.f);
+      qv[k] = (ghqo != nullptr && row[k] >= 0 && mine) ? __ldg(a.ghq + row[k]) : 0;
     }
     __syncthreads();
     int run = left_run;
@@ -230,8 +235,9 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
         const int lefts_before_me = run + wbefore + __popc(word[k] & ((1u << lane) - 1u));
         const int pos = ((word[k] >> lane) & 1u) ? lefts_before_me : total_left + (i - lefts_before_me);
         dst[pos] = row[k];
-        if (gho != nullptr) gho[pos] = gv[k];
-        if (ghqo != nullptr) ghqo[pos] = qv[k];
+        const bool mine = copy_both || ((((word[k] >> lane) & 1u) != 0u) == left_smaller);
+        if (gho != nullptr && mine) gho[pos] = gv[k];
+        if (ghqo != nullptr && mine) ghqo[pos] = qv[k];
       }
       run += tile_left;
     }
