@@ -59,14 +59,15 @@ def main():
     lo, hi = D.shard_columns(f, world)[rank]
     shard = full.column_slice(lo, hi) if hi > lo else D.empty_shard(n, rank)
     cfg = lgb.Config(num_leaves=leaves, gpu_device_id=int(os.environ.get("LOCAL_RANK", rank)),
-                     use_cuda_graph=not os.environ.get("NO_GRAPH"))
+                     use_cuda_graph=not os.environ.get("NO_GRAPH"),
+                     use_quantized_grad=mode.startswith("gpuquant"), num_grad_quant_bins=4, stochastic_rounding=False)
     if mode == "rows":
         r0, r1 = D.shard_rows(n, world)[rank]
         shard = lgb.Layout.identity(bins[r0:r1])
         L = D.make_row_sharded_learner(shard, cfg, rank, world)
         gl, hl = g[r0:r1], h[r0:r1]
     else:
-        L = D.make_sharded_learner(shard, cfg, rank, world, replicate_columns=(mode != "gpupush"))
+        L = D.make_sharded_learner(shard, cfg, rank, world, replicate_columns=(mode not in ("gpupush", "gpuquantpush")))
         gl, hl = g, h
     trees = []
     for it in range(3):

@@ -66,7 +66,7 @@ def _gpu_count():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["gpu", "gpupush"])      # replicated partition columns / owner pushes the go-left bits
+@pytest.mark.parametrize("mode", ["gpu", "gpupush", "gpuquant", "gpuquantpush"])   # replicated columns / owner pushes the go-left bits; + quantized gradients
 @pytest.mark.parametrize("n,f,leaves", [(30000, 96, 31), (20000, 40, 15)])
 def test_feature_shard_world2_matches_single_gpu(n, f, leaves, mode):
     if _gpu_count() < 2:
