@@ -64,3 +64,32 @@ def test_product_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                     txt = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert not bad.search(txt), f"{os.path.join(dirpath, f)} references the oracle"
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The Python mirror structs (tree_learner.py) must have the size and field offsets of include/lgbm_b200.h as a C
+    compiler lays them out — a drift here corrupts every call silently."""
+    import shutil
+    import subprocess
+    from lightgbm_b200 import tree_learner as tl
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    structs = {"LGBMB200_Config": tl._CConfig, "LGBMB200_Tree": tl._CTree, "LGBMB200_Split": tl._CSplit, "LGBMB200_Layout": tl._CLayout}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "lgbm_b200.h")}"', "int main(void) {"]
+    for cname, py in structs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in py._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call([gcc, "-std=c11", "-o", str(exe), str(src)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for line in out:
+        parts = line.split()
+        py = structs[parts[0]]
+        assert ctypes.sizeof(py) == int(parts[1]), parts[0]
+        assert [getattr(py, f).offset for f, _ in py._fields_] == [int(x) for x in parts[2:]], parts[0]

@@ -47,3 +47,27 @@ def test_model_text_parser_split_leaf_recovery():
     assert t.num_leaves == 3
     assert t.split_leaf().tolist() == [0, 0]          # node 1 is the left child of node 0 => it split leaf 0
     assert t.default_left.tolist() == [1, 0]
+
+
+def test_packed_cell_arithmetic_of_the_quantized_histogram():
+    """k_hist_q keeps (sum g << 16) + sum h in one int32 and adds one precomputed word per row.  Property the kernel
+    relies on: for |g| <= Q/2, 0 <= h <= Q and at most floor(65535/Q) rows, H = P & 0xffff and G = (P - H) >> 16 recover
+    the two sums exactly (worst cases included), and one more row of the maximum hessian may break it."""
+    rng = np.random.default_rng(0)
+    for Q in (2, 4, 5, 8, 15):
+        R = (65535 // Q) // 32 * 32
+        for trial in range(4):
+            if trial == 0:
+                g = np.full(R, Q // 2, np.int64); h = np.full(R, Q, np.int64)          # both fields at their maximum
+            elif trial == 1:
+                g = np.full(R, -(Q // 2), np.int64); h = np.zeros(R, np.int64)          # most negative gradient field
+            else:
+                g = rng.integers(-(Q // 2), Q // 2 + 1, R); h = rng.integers(0, Q + 1, R)
+            words = (g * 65536 + h).astype(np.int64)
+            P = int(np.sum(words))
+            assert -2 ** 31 <= P < 2 ** 31                                              # fits the int32 cell
+            H = P & 0xffff
+            G = (P - H) >> 16
+            assert H == int(h.sum()) and G == int(g.sum())
+        # the bound is tight for the hessian field: R' = floor(65535/Q) + 1 rows of h = Q overflow 16 bits
+        assert (65535 // Q + 1) * Q > 65535
