@@ -93,28 +93,11 @@ __device__ __forceinline__ void sts64(unsigned addr, float2 v) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y));
 }
 
-// K rows of the lane's column.  All K cells are loaded BEFORE any store, so rows that hit the same bin see the
-// same old value v; the new value of row i is v + (q_i + sum of the q_j, j < i, with b_j == b_i).  Those
-// partial sums do not depend on the loads and are formed while the LDS are in flight, so the critical path
-// per batch is LDS -> FADD -> STS and K independent LDS.64 are in flight per warp (with 3 warps per SM the
-// shared-memory pipe is latency-bound, so K is the lever).  Stores are issued in row order: the last store
-// to a cell carries the complete sum.  Fixed evaluation order => bitwise run-to-run determinism.
-template <int K>
-__device__ __forceinline__ void rmw_batch(unsigned hbase, const uint32_t (&b)[K], const float2 (&q)[K]) {
-  unsigned addr[K];
-  float2 v[K], s[K];
-#pragma unroll
-  for (int i = 0; i < K; ++i) { addr[i] = hbase + (b[i] << 8); v[i] = lds64(addr[i]); }
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    s[i] = q[i];
-#pragma unroll
-    for (int j = 0; j < i; ++j) if (b[j] == b[i]) { s[i].x += q[j].x; s[i].y += q[j].y; }
-  }
-#pragma unroll
-  for (int i = 0; i < K; ++i) sts64(addr[i], make_float2(v[i].x + s[i].x, v[i].y + s[i].y));
-}
-
+// Batches of K rows of the lane's column: all K cells are loaded BEFORE any store, so rows that hit the same bin see
+// the same old value v; the new value of row i is v + (q_i + sum of the q_j, j < i, with b_j == b_i).  Those partial
+// sums do not depend on the loads and are formed while the LDS are in flight, so the critical path per batch is
+// LDS -> FADD -> STS with K independent LDS.64 in flight per warp.  Stores are issued in row order: the last store to
+// a cell carries the complete sum.  Fixed evaluation order => bitwise run-to-run determinism.
 // The same batch update split in two so that the caller can software-pipeline it: batch_prepare (pure ALU: cell
 // addresses + the duplicate-combined increments) of batch k+1 is placed in the shadow of batch k's LDS latency.
 template <bool QUANT> __device__ __forceinline__ float2 acc2(float2 a, float2 b);

@@ -667,7 +667,6 @@ class Learner {
     sa.splittable = splittable_.p; sa.splittable_new = splittable_new_.p; sa.cand = cand_.p; sa.block_best = block_best_.p;
     sa.peers = peers_;
     const bool row_mode = peers_.world > 1 && peers_.mode == 1;
-    (void)0;
     const int scan_blocks = ((row_mode ? peers_.f_cnt : F_) + kScanWarps - 1) / kScanWarps;
     SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p, block_best_.p, scan_blocks, splittable_.p, splittable_new_.p, peers_};
     const bool fuse_select = (cfg_.reserved & 32) != 0;
