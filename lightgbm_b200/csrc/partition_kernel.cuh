@@ -469,8 +469,10 @@ __global__ void __launch_bounds__(32) k_quant_scales(const PrepArgs a) {
   const double max_g = mg, max_h = mh;
   c->q_gscale = max_g / static_cast<double>(a.params.quant_bins / 2);
   c->q_hscale = a.params.quant_const_hess ? max_h : max_h / static_cast<double>(a.params.quant_bins);
-  c->q_ginv = 1.0f / c->q_gscale;        // the reference divides the float literal 1.0f by the double scale
-  c->q_hinv = 1.0f / c->q_hscale;
+  // the reference divides the float literal 1.0f by the double scale; all-zero gradients (scale 0) would make that
+  // inf and the discretized values NaN casts: map them to 0 instead (no split is found, as it should be)
+  c->q_ginv = c->q_gscale > 0.0 ? 1.0f / c->q_gscale : 0.0;
+  c->q_hinv = c->q_hscale > 0.0 ? 1.0f / c->q_hscale : 0.0;
   c->quant_iter += 1;
 }
 

@@ -231,7 +231,9 @@ void orc_discretize(const float* grad, const float* hess, int32_t n, OrcQuant* Q
   }
   Q->grad_scale = max_g / (double)(Q->num_grad_quant_bins / 2);
   Q->hess_scale = Q->is_constant_hessian ? max_h : max_h / (double)Q->num_grad_quant_bins;
-  const double inv_g = 1.0f / Q->grad_scale, inv_h = 1.0f / Q->hess_scale;
+  /* all-zero gradients: the reference would divide by zero here; both this restatement and the CUDA path map the
+   * degenerate case to all-zero integers */
+  const double inv_g = Q->grad_scale > 0.0 ? 1.0f / Q->grad_scale : 0.0, inv_h = Q->hess_scale > 0.0 ? 1.0f / Q->hess_scale : 0.0;
   for (int32_t i = 0; i < n; ++i) {
     const double g = grad[i];
     const double rg = random_g ? random_g[i] : 0.5;
