@@ -122,9 +122,38 @@ def quantized_cases():
              quant=dict(num_grad_quant_bins=4))
 
 
+def example_cases():
+    """The reference's own example datasets (examples/regression, examples/binary_classification: 7000 x 28 real-valued
+    features, the data behind tests/python_package_test/test_consistency.py) with the learner settings of their
+    train.conf (num_leaves=31, min_data_in_leaf=100/50, min_sum_hessian_in_leaf=5.0, max_bin=255): real-data bins, ties
+    and a most-frequent-bin pattern no synthetic generator produces.  Only the binned matrix travels in the fixture."""
+    ex = "/root/reference/examples"
+    reg = np.loadtxt(os.path.join(ex, "regression", "regression.train"))
+    y, X = reg[:, 0], reg[:, 1:]
+    run_case("example_regression", X, y.mean() - y, np.ones(len(y)), dict(max_bin=255),
+             dict(num_leaves=31, min_data_in_leaf=100, min_sum_hessian_in_leaf=5.0))
+    run_case("example_regression_quant", X, y.mean() - y, np.ones(len(y)), dict(max_bin=255),
+             dict(num_leaves=31, min_data_in_leaf=100, min_sum_hessian_in_leaf=5.0), quant=dict(num_grad_quant_bins=4))
+    bi = np.loadtxt(os.path.join(ex, "binary_classification", "binary.train"))
+    yb, Xb = bi[:, 0], bi[:, 1:]
+    p = np.full(len(yb), yb.mean())
+    run_case("example_binary", Xb, p - yb, p * (1 - p), dict(max_bin=255),
+             dict(num_leaves=63, min_data_in_leaf=50, min_sum_hessian_in_leaf=5.0))
+    # second-iteration-like gradients (hessians vary per row) with quantization and leaf renewal
+    rng = np.random.default_rng(7)
+    s = 0.4 * (Xb[:, 0] - Xb[:, 0].mean()) + 0.1 * rng.normal(size=len(yb))
+    p2 = 1 / (1 + np.exp(-s))
+    run_case("example_binary_quant", Xb, p2 - yb, p2 * (1 - p2), dict(max_bin=255),
+             dict(num_leaves=31, min_data_in_leaf=50, min_sum_hessian_in_leaf=5.0, lambda_l2=0.5),
+             quant=dict(num_grad_quant_bins=8, quant_train_renew_leaf=True))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "quant":
         quantized_cases()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "examples":
+        example_cases()
         return
     rng = np.random.default_rng(2024)
     nan = np.nan
@@ -179,6 +208,7 @@ def main():
     run_case("efb_bundled", X, -yv, np.ones(n), dict(enable_bundle="true", device_type="cuda", max_bin=63),
              dict(num_leaves=31, min_data_in_leaf=10))
     quantized_cases()
+    example_cases()
 
 
 if __name__ == "__main__":
