@@ -60,7 +60,8 @@ typedef struct {
                                        bit 5: k_select folded into the last block of k_scan;
                                        bit 6: quantized training keeps int32x2 histogram cells (no packed 16:16 kernel);
                                        bit 7: no L2 prefetch of gathered rows in the histogram producers;
-                                       bit 8: no leaf-ordered (g,h) copies (producers gather 8 B per row per column group) */
+                                       bit 8: no leaf-ordered (g,h) copies (producers gather 8 B per row per column group);
+                                       bit 9: EXPERIMENTAL, not yet run on hardware: gathered histogram stages by TMA tile::gather4 */
   /* ---- quantized-gradient training (reference config.h:626-651; gradient_discretizer.cpp) */
   int32_t use_quantized_grad;       /* 1: discretize (g,h) to int8 per tree, integer histograms, integer split scan */
   int32_t num_grad_quant_bins;      /* config.h:638, default 4 */

@@ -20,6 +20,7 @@
 
 #include "../../include/lgbm_b200.h"
 #include "hist_kernel.cuh"
+#include "hist_g4_kernel.cuh"
 #include "hist_q_kernel.cuh"
 #include "partition_kernel.cuh"
 #include "scan_kernel.cuh"
@@ -158,6 +159,8 @@ class Learner {
     bag_count_ = -1;
     CUDA_CHECK(cudaFuncSetAttribute(k_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
     CUDA_CHECK(cudaFuncSetAttribute(k_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+    CUDA_CHECK(cudaFuncSetAttribute(k_hist_g4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+    CUDA_CHECK(cudaFuncSetAttribute(k_hist_g4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
     CUDA_CHECK(cudaFuncSetAttribute(k_hist_q, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmemBytes));
     CUDA_CHECK(cudaFuncSetAttribute(k_hist_q, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CUDA_CHECK(cudaFuncSetAttribute(k_hist2, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
@@ -623,6 +626,16 @@ class Learner {
                                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     have_tmap_ = (r == CUDA_SUCCESS);
+    // second map for the experimental tile::gather4 path: box = {32 columns, 1 row}, four rows per instruction
+    have_tmap_g4_ = false;
+    std::memset(&tmap_g4_, 0, sizeof(tmap_g4_));
+    if (have_tmap_ && (cfg_.reserved & 512)) {
+      const cuuint32_t box1[2] = {kColGroup, 1};
+      const CUresult r4 = reinterpret_cast<EncodeTiled>(fn)(&tmap_g4_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, bins_.p, gdim, gstride, box1, estride,
+                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      have_tmap_g4_ = (r4 == CUDA_SUCCESS);
+    }
   }
 
   // reserved bit 3 selects the experimental split kernel k_hist2 (separate gradient / hessian consumer warps,
@@ -636,6 +649,10 @@ class Learner {
     if (quant && PackedQuantHist()) {
       HistQArgs qa{ha, ghq_.p, ((65535 / params_.quant_bins) / kStageRows) * kStageRows};
       LaunchChain(chain, k_hist_q, dim3(num_sms_ * 2), dim3(kHistThreads), kQSmemBytes, qa, tmap_);
+    } else if ((cfg_.reserved & 512) && have_tmap_g4_) {
+      // EXPERIMENTAL (not yet run on hardware): gathered stages through TMA tile::gather4, see hist_g4_kernel.cuh
+      if (quant) LaunchChain(chain, k_hist_g4<true>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_, tmap_g4_);
+      else LaunchChain(chain, k_hist_g4<false>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_, tmap_g4_);
     } else if (quant) LaunchChain(chain, k_hist<true>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
     else if (cfg_.reserved & 8) LaunchChain(chain, k_hist2, dim3(num_sms_), dim3(kHist2Threads), kHistSmemBytes, ha, tmap_);
     else LaunchChain(chain, k_hist<false>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
@@ -836,7 +853,8 @@ class Learner {
   DevBuf<PartialSum> partials_;
   CommPeers peers_{};
   CUtensorMap tmap_;
-  bool have_tmap_ = false;
+  bool have_tmap_ = false, have_tmap_g4_ = false;
+  CUtensorMap tmap_g4_;
   void* comm_local_ = nullptr;
   int64_t comm_stride_ = 0;
   std::vector<void*> comm_opened_;
