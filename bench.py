@@ -38,23 +38,29 @@ WORKLOADS = {
 }
 
 
-def gen_bins(rows, cols, seed, col_lo=0, col_hi=None, threads=None):
+GEN_CHUNK = 65536
+
+
+def gen_bins(rows, cols, seed, col_lo=0, col_hi=None, threads=None, row_lo=0, row_hi=None):
     """Seeded synthetic bin matrix: one Philox stream per (64K-row chunk, 128-column block), so the
-    matrix — and any column slice of it — is identical whatever the thread count or the number of ranks, and a rank
-    only generates the column blocks it owns."""
+    matrix — and any column slice or 64K-aligned row range of it — is identical whatever the thread count or the number
+    of ranks, and a rank only generates the column blocks it owns."""
     col_hi = cols if col_hi is None else col_hi
-    out = np.empty((rows, col_hi - col_lo), dtype=np.uint8)
-    chunk, cblock = 65536, 128
-    jobs = [(s, b) for s in range(0, rows, chunk) for b in range(col_lo // cblock, (col_hi + cblock - 1) // cblock)]
+    row_hi = rows if row_hi is None else min(rows, row_hi)
+    assert row_lo % GEN_CHUNK == 0
+    out = np.empty((row_hi - row_lo, col_hi - col_lo), dtype=np.uint8)
+    chunk, cblock = GEN_CHUNK, 128
+    jobs = [(s, b) for s in range(row_lo, row_hi, chunk) for b in range(col_lo // cblock, (col_hi + cblock - 1) // cblock)]
 
     def work(job):
         s, b = job
-        e = min(rows, s + chunk)
+        e = min(rows, s + chunk)        # the chunk's extent in the FULL matrix fixes the stream length
         c0, c1 = b * cblock, min(cols, (b + 1) * cblock)
         rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, b, s // chunk]))
         blk = rng.integers(0, 255, (e - s, c1 - c0), dtype=np.uint8)
         lo, hi = max(c0, col_lo), min(c1, col_hi)
-        out[s:e, lo - col_lo:hi - col_lo] = blk[:, lo - c0:hi - c0]
+        e2 = min(e, row_hi)
+        out[s - row_lo:e2 - row_lo, lo - col_lo:hi - col_lo] = blk[:e2 - s, lo - c0:hi - c0]
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 8)) as ex:
         list(ex.map(work, jobs))
@@ -140,57 +146,185 @@ def ncu_traffic():
 
 
 # ----------------------------------------------------------------------------------------------------
-def run_reference(args, wl, rank, world):
-    """The reference's own CPU learner (unmodified, built into oracle/_ref by oracle/Makefile.ref) on the
-    host cores, on a bounded row sample of the same workload; it/s is scaled by sample_rows/rows
-    (histogram work is linear in rows; this favours the CPU since per-split overheads do not scale)."""
+# Reference arms.  Both run the UNMODIFIED reference through its own C API (oracle/refapi.py), never this repo's code:
+#   --impl reference       the reference's OpenMP CPU learner (oracle/_ref/lib_lightgbm.so, built by oracle/Makefile.ref)
+#   --impl reference_cuda  the reference's own CUDA learner compiled for sm_100 (oracle/_ref/cuda/lib_lightgbm.so, built by
+#                          oracle/Makefile.refcuda): the rival on the same box
+# They train on the FULL workload that config.workload prints (the matrix is streamed into the reference Dataset in
+# row blocks, so the 41 GB fp32 copy of C3 never exists); `value` and `ms_per_step` are what was measured, unscaled.
+REF_BLOCK_ROWS = 4 * GEN_CHUNK
+
+
+def _ref_params(wl, threads, device="cpu", quantized=0):
+    dsp = dict(max_bin=255, min_data_in_bin=1, enable_bundle="false", feature_pre_filter="false", verbosity=-1,
+               num_threads=threads, device_type=device)
+    if device == "cuda":
+        dsp.update(gpu_device_id=0, num_gpu=1)
+    bp = dict(dsp, objective="regression", num_leaves=wl["leaves"], learning_rate=0.1, min_data_in_leaf=20)
+    if quantized:
+        bp.update(use_quantized_grad="true", num_grad_quant_bins=quantized)
+    return dsp, bp
+
+
+def _ref_dataset(refapi, wl, rows, dsp, threads):
+    """Reference Dataset over rows [0, rows) of the workload, streamed in REF_BLOCK_ROWS blocks."""
+    first32 = np.empty((rows, 32), dtype=np.uint8)
+
+    def block(lo, hi):
+        b = gen_bins(wl["rows"], wl["cols"], wl["seed"], threads=min(32, threads), row_lo=lo, row_hi=hi)
+        first32[lo:hi] = b[:, :32]
+        out = np.empty(b.shape, dtype=np.float32)
+        nt = max(1, min(16, threads))
+        per = (len(b) + nt - 1) // nt
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=nt) as ex:       # numpy casts release the GIL
+            list(ex.map(lambda t: np.copyto(out[t * per:(t + 1) * per], b[t * per:(t + 1) * per], casting="unsafe"), range(nt)))
+        return out
+    t0 = time.time()
+    ds = refapi.RefDatasetStreamed(block, rows, wl["cols"], None, dsp, block_rows=REF_BLOCK_ROWS)
+    y = gen_label(wl["rows"], wl["cols"], wl["seed"], first32) if rows == wl["rows"] else \
+        gen_label_rows(wl, first32)
+    ds.set_label(y)
+    return ds, time.time() - t0
+
+
+def gen_label_rows(wl, first32):
+    """Labels of the first len(first32) rows of the workload (the noise stream is row-ordered, so a prefix is a prefix)."""
+    rng = np.random.Generator(np.random.Philox(key=wl["seed"] + 1000))
+    w = rng.normal(size=32)
+    noise = rng.normal(size=wl["rows"]).astype(np.float32)[:len(first32)]
+    return ((first32.astype(np.float32) / 127.0 - 1.0) @ w.astype(np.float32) + 0.5 * noise).astype(np.float32)
+
+
+def _time_iters(bst, warmup, steps):
+    for _ in range(warmup):
+        bst.update()
+    t0 = time.time()
+    for _ in range(steps):
+        bst.update()
+    return (time.time() - t0) / max(steps, 1)
+
+
+def _calibrate_threads(refapi, ds, wl, cores, device, quantized):
+    """Shared GPU boxes advertise more logical CPUs than a tenant gets; OpenMP spin-waits then collapse (measured in
+    round 1: 49 s/iter at 128 threads vs ~16 usable cores).  Time one iteration on a small Dataset at cores, cores/2,
+    cores/4 threads and keep the fastest: the reference gets the best thread count the box offers."""
+    if device != "cpu":
+        return cores
+    best, best_dt, t = cores, None, cores
+    while t >= 4:
+        _, bp = _ref_params(wl, t, device, quantized)
+        b = refapi.RefBooster(ds, bp)
+        dt = _time_iters(b, 1, 2)
+        b.free()
+        if best_dt is None or dt < best_dt:
+            best, best_dt = t, dt
+        t //= 2
+        if t < cores // 4:
+            break
+    return best
+
+
+def host_mem_available():
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 1 << 62
+    try:
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        if lim != "max":
+            cur = int(open("/sys/fs/cgroup/memory.current").read().strip())
+            avail = min(avail, int(lim) - cur)
+    except Exception:
+        pass
+    return avail
+
+
+def run_reference(args, wl, rank, world, device="cpu"):
+    """Full-workload reference arm; returns None on ranks != 0."""
     if rank != 0:
         return None
+    if device == "cuda":
+        os.environ["LGBM_REF_LIB"] = os.path.join(ROOT, "oracle", "_ref", "cuda", "lib_lightgbm.so")
     from oracle import refapi
-    rows = min(wl["rows"], args.ref_rows)
+    if not os.path.exists(refapi.REF_LIB):
+        return {"unavailable": f"{refapi.REF_LIB} not built (oracle/Makefile.ref{'cuda' if device == 'cuda' else ''})"}
     cores = effective_cores()
-    bins = gen_bins(rows, wl["cols"], wl["seed"])
-    y = gen_label(rows, wl["cols"], wl["seed"], bins[:, :32])
-    X = bins.astype(np.float32)
-    dsp = dict(max_bin=255, min_data_in_bin=1, enable_bundle="false", feature_pre_filter="false", verbosity=-1,
-               num_threads=cores)
-    t0 = time.time()
-    ds = refapi.RefDataset(X, y, dsp)
-    t_ds = time.time() - t0
-    del X
-    # histogram layout: neither force_col_wise nor force_row_wise is set, so the reference times both layouts itself
-    # at Booster creation and keeps the faster one (Dataset::GetShareStates, dataset.cpp:655-727) — its stock
-    # behaviour.  Thread count: all the host threads it can use, but shared GPU boxes advertise more logical CPUs
-    # than a tenant gets; OpenMP spin-waits then collapse (measured: 49 s/iter at 128 threads vs ~16 usable cores),
-    # so the count is halved while the first iteration is implausibly slow.
-    threads = cores
-    while True:
-        bp = dict(dsp, objective="regression", num_leaves=wl["leaves"], learning_rate=0.1, min_data_in_leaf=20,
-                  device_type="cpu", num_threads=threads)
-        if getattr(args, "quantized", 0):
-            bp.update(use_quantized_grad="true", num_grad_quant_bins=args.quantized)
-        bst = refapi.RefBooster(ds, bp)
-        t0 = time.time()
-        bst.update()
-        t_first = time.time() - t0
-        if t_first < 8.0 or threads <= 8:
-            break
-        bst.free()
-        threads //= 2
-    for _ in range(max(args.warmup - 1, 0)):
-        bst.update()
-    t0 = time.time()
-    for _ in range(args.steps):
-        bst.update()
-    dt = (time.time() - t0) / args.steps
+    rows = wl["rows"]
+    need = 3.2 * rows * wl["cols"] + (2 << 30)      # column-wise + row-wise bin copies + one fp32 block, bytes
+    note = ""
+    if host_mem_available() < need:
+        rows = max(REF_BLOCK_ROWS, int(host_mem_available() / (3.2 * wl["cols"])) // GEN_CHUNK * GEN_CHUNK)
+        note = f"; host memory allows only {rows} rows"
+    dsp, _ = _ref_params(wl, cores, device, args.quantized)
+    cal_ds, _ = _ref_dataset(refapi, wl, min(rows, REF_BLOCK_ROWS), dsp, cores)
+    threads = _calibrate_threads(refapi, cal_ds, wl, cores, device, args.quantized)
+    cal_ds.free()
+    dsp, bp = _ref_params(wl, threads, device, args.quantized)
+    ds, t_ds = _ref_dataset(refapi, wl, rows, dsp, cores)
+    bst = refapi.RefBooster(ds, bp)
+    dt = _time_iters(bst, args.warmup, args.steps)
+    trees = bst.trees()
     bst.free()
-    cores = threads
-    best_mode = "col/row-wise chosen by the reference's own auto-timing"
-    scale = rows / wl["rows"]
-    value = (1.0 / dt) * scale
-    sample = f"{rows} of {wl['rows']} rows x {wl['cols']} cols, {wl['leaves']} leaves, {best_mode}, " \
-             f"{cores} threads; it/s scaled by {scale:g}; dataset construction {t_ds:.1f}s excluded"
-    return dict(value=value, ms_per_step=dt * 1e3 / scale, cores=cores, sample=sample)
+    ds.free()
+    kind = ("the reference's own CUDA learner (src/treelearner/cuda, -DUSE_CUDA, sm_100), boosting on the GPU" if device == "cuda"
+            else "the reference's OpenMP CPU learner, col/row-wise chosen by its own auto-timing")
+    sample = f"all {rows} rows x {wl['cols']} cols, {wl['leaves']} leaves, {kind}, {threads} host threads; " \
+             f"dataset construction {t_ds:.1f}s excluded{note}"
+    return dict(value=1.0 / dt, ms_per_step=dt * 1e3, cores=threads, sample=sample, rows=rows,
+                first_tree=ref_tree_signature(trees[args.warmup]) if len(trees) > args.warmup else None)
+
+
+def tree_signature(t):
+    """Structure hash of one tree (split leaf / feature / threshold bin / default_left / child counts, in split order):
+    equal hashes across N = 1, 2, 4, 8 prove that every configuration grew the same tree."""
+    import hashlib
+    h = hashlib.sha1()
+    for k in ("leaf", "feature", "threshold", "default_left", "left_count", "right_count"):
+        h.update(np.ascontiguousarray(t.splits[k]).tobytes())
+    hv = hashlib.sha1(np.ascontiguousarray(t.leaf_value).tobytes()).hexdigest()[:16]
+    return {"num_leaves": int(t.num_leaves), "root_feature": int(t.splits["feature"][0]) if t.num_leaves > 1 else -1,
+            "root_threshold_bin": int(t.splits["threshold"][0]) if t.num_leaves > 1 else 0,
+            "structure_sha1": h.hexdigest()[:16], "leaf_values_sha1": hv}
+
+
+def ref_tree_signature(t):
+    return {"num_leaves": int(t.num_leaves), "root_feature": int(t.split_feature[0]) if t.num_leaves > 1 else -1,
+            "root_threshold": float(t.threshold[0]) if t.num_leaves > 1 else 0.0}
+
+
+def run_reference_fit(args, wl):
+    """Bounded CPU baseline for the b200 arm's `cpu_baseline` key (about 10-30 s of CPU work): the reference CPU
+    learner timed on TWO row samples of the workload, t(rows) = a + b*rows fitted through them and evaluated at the
+    full row count.  The per-split work that does not depend on the row count (the scan of 2 x T bins, the per-thread
+    histogram merge) lands in `a` and is NOT multiplied up.  An estimate, labelled as such: the measured full-size
+    number is `bench.py --impl reference`."""
+    from oracle import refapi
+    if not os.path.exists(refapi.REF_LIB):
+        return None
+    cores = effective_cores()
+    s1, s2 = 2 * GEN_CHUNK, 8 * GEN_CHUNK
+    s2 = min(s2, wl["rows"] // GEN_CHUNK * GEN_CHUNK) or wl["rows"]
+    s1 = min(s1, s2 // 2)
+    dsp, _ = _ref_params(wl, cores, "cpu", args.quantized)
+    ds2, t_ds = _ref_dataset(refapi, wl, s2, dsp, cores)
+    threads = _calibrate_threads(refapi, ds2, wl, cores, "cpu", args.quantized)
+    dsp, bp = _ref_params(wl, threads, "cpu", args.quantized)
+    b2 = refapi.RefBooster(ds2, bp)
+    t2 = _time_iters(b2, 1, 3)
+    b2.free(); ds2.free()
+    ds1, _ = _ref_dataset(refapi, wl, s1, dsp, cores)
+    b1 = refapi.RefBooster(ds1, bp)
+    t1 = _time_iters(b1, 1, 3)
+    b1.free(); ds1.free()
+    slope = max((t2 - t1) / (s2 - s1), 0.0)
+    icpt = max(t1 - slope * s1, 0.0)
+    est = icpt + slope * wl["rows"]
+    sample = (f"ESTIMATE from two row samples of the workload ({s1} rows: {t1 * 1e3:.0f} ms/iter, {s2} rows: {t2 * 1e3:.0f} ms/iter, "
+              f"{wl['cols']} cols, {wl['leaves']} leaves, {threads} threads): t = {icpt * 1e3:.0f} ms + {slope * 1e9:.1f} ns/row "
+              f"evaluated at {wl['rows']} rows; the measured full-size run is `bench.py --impl reference`")
+    return {"value": 1.0 / est, "unit": "iters/sec", "cores": threads, "kind": "reference", "sample": sample}
 
 
 def main():
@@ -198,10 +332,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference_cuda"])
     ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "C3"), choices=list(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override rows (debug only; makes the number INVALID)")
-    ap.add_argument("--ref-rows", type=int, default=500_000, help="row sample for the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--quantized", type=int, default=0, metavar="Q",
@@ -214,6 +347,7 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.rows:
         wl["rows"] = args.rows
+    metric = METRIC if args.workload == "C3" else f"boosting iters/sec, {wl['rows']} x {wl['cols']} synthetic, 255 bins, {wl['leaves']} leaves"
     config = {"workload": f"{args.workload}: {wl['rows']} rows x {wl['cols']} dense features, 255 bins, {wl['leaves']} leaves, "
                           f"L2 regression, min_data_in_leaf=20, lr=0.1" +
                           (f", use_quantized_grad num_grad_quant_bins={args.quantized} (NOT the BASELINE configuration)" if args.quantized else ""),
@@ -222,16 +356,24 @@ def main():
               "l2_flush": "inputs larger than L2 (bin matrix 10.24 GB >> 126 MB)" if wl["rows"] * wl["cols"] > 2e9 else
                           "bin matrix larger than L2 per GPU"}
 
-    if args.impl == "reference":
-        r = run_reference(args, wl, rank, world)
+    if args.impl in ("reference", "reference_cuda"):
+        dev = "cuda" if args.impl == "reference_cuda" else "cpu"
+        r = run_reference(args, wl, rank, world, dev)
         if rank == 0:
-            line = {"metric": METRIC, "impl": "reference", "value": r["value"], "unit": "iters/sec", "n_gpus": args.gpus,
+            if "unavailable" in r:
+                print(json.dumps({"impl": args.impl, "unavailable": r["unavailable"]}), flush=True)
+                return
+            if r["rows"] != wl["rows"]:       # never print a workload that was not the one trained on
+                config["workload"] = config["workload"].replace(f"{wl['rows']} rows", f"{r['rows']} rows (SAMPLE of {wl['rows']})")
+            line = {"metric": metric, "impl": args.impl, "value": r["value"], "unit": "iters/sec", "n_gpus": args.gpus,
                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                    "scaling": "strong", "vs_baseline": None, "dtype": "f64 histograms (fp32 grad/hess)", "data": "synthetic",
-                    "config": config,
+                    "scaling": "strong", "vs_baseline": None,
+                    "dtype": "f64 histograms (fp32 grad/hess)" if dev == "cpu" else "fp32 shared-memory atomics -> f64 histograms (gpu_use_dp=false)",
+                    "data": "synthetic", "config": config,
                     "cpu_baseline": {"value": r["value"], "unit": "iters/sec", "cores": r["cores"], "kind": "reference",
                                      "sample": r["sample"]},
-                    "e2e": {"value": r["value"], "unit": "iters/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                    "e2e": {"value": r["value"], "unit": "iters/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "first_timed_tree": r["first_tree"]}
             print(json.dumps(line), flush=True)
         return
 
@@ -280,8 +422,11 @@ def main():
     with ClockSampler(local) as clk:
         L.timer_start()
         t0 = time.time()
+        first_tree = None
         for _ in range(args.steps):
-            B.update()
+            t = B.update()
+            if first_tree is None:
+                first_tree = t
         ms_total = L.timer_stop()
         barrier()
         wall = time.time() - t0
@@ -342,16 +487,15 @@ def main():
             dist.barrier(); dist.destroy_process_group()
         return
     if not args.no_cpu_baseline and world == 1:
-        a2 = argparse.Namespace(**vars(args)); a2.steps = 2; a2.warmup = 1
-        r = run_reference(a2, wl, rank, world)
-        cpu = {"value": r["value"], "unit": "iters/sec", "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
+        cpu = run_reference_fit(args, wl)
 
-    line = {"metric": METRIC, "value": value, "unit": "iters/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": metric, "value": value, "unit": "iters/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": ("int8 gradients -> packed int16:int16 histogram cells -> int64 pool, f64 gain scan" if args.quantized else
                       "fp32 partial sums -> int64 fixed-point histograms, f64 gain scan"), "data": "synthetic",
             "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "wall_ms_per_step": wall * 1e3 / args.steps, "final_train_l2": final_l2}
+            "cpu_baseline": cpu, "wall_ms_per_step": wall * 1e3 / args.steps, "final_train_l2": final_l2,
+            "first_timed_tree": tree_signature(first_tree)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

@@ -71,6 +71,11 @@ class RefDataset:
                                           C.c_int(len(lab)), C.c_int(C_API_DTYPE_FLOAT32)))
         self.num_data = X.shape[0]
 
+    def set_label(self, label: np.ndarray):
+        lab = np.ascontiguousarray(label, dtype=np.float32)
+        _check(lib().LGBM_DatasetSetField(self.handle, b"label", lab.ctypes.data_as(C.c_void_p),
+                                          C.c_int(len(lab)), C.c_int(C_API_DTYPE_FLOAT32)))
+
     def layout(self) -> "Layout":
         lib()
         n, c, f, tf = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
@@ -266,3 +271,35 @@ class RefBooster:
         if self.handle:
             lib().LGBM_BoosterFree(self.handle)
             self.handle = None
+
+
+class RefDatasetStreamed(RefDataset):
+    """The reference's own streaming ingestion (c_api.h LGBM_DatasetCreateByReference + LGBM_DatasetPushRows): bin
+    mappers come from a sample Dataset built with LGBM_DatasetCreateFromMat on the first `sample_rows` rows, then the
+    full matrix is pushed in row blocks, so the fp32 copy of a 10M x 1024 matrix (41 GB) never exists.
+    `block_fn(lo, hi)` returns the float32 [hi-lo, ncol] block of rows lo..hi; the next block is produced on a
+    helper thread while the current one is being pushed."""
+
+    def __init__(self, block_fn, nrow: int, ncol: int, label: np.ndarray | None, params: dict, block_rows: int = 250_000,
+                 sample_rows: int = 65_536):
+        from concurrent.futures import ThreadPoolExecutor
+        L = lib()
+        first = np.ascontiguousarray(block_fn(0, min(nrow, block_rows)), dtype=np.float32)
+        sample = RefDataset(first[:min(len(first), sample_rows)], None, params)
+        self.handle = C.c_void_p()
+        _check(L.LGBM_DatasetCreateByReference(sample.handle, C.c_int64(nrow), C.byref(self.handle)))
+        with ThreadPoolExecutor(max_workers=1) as ex:
+            lo, blk = 0, first
+            while lo < nrow:
+                hi = min(nrow, lo + block_rows)
+                nxt = ex.submit(block_fn, hi, min(nrow, hi + block_rows)) if hi < nrow else None
+                blk = np.ascontiguousarray(blk, dtype=np.float32)
+                _check(L.LGBM_DatasetPushRows(self.handle, blk.ctypes.data_as(C.c_void_p), C.c_int(C_API_DTYPE_FLOAT32),
+                                              C.c_int32(hi - lo), C.c_int32(ncol), C.c_int32(lo)))
+                lo = hi
+                blk = nxt.result() if nxt is not None else None
+        del first
+        sample.free()
+        if label is not None:
+            self.set_label(label)
+        self.num_data = nrow
