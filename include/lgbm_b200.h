@@ -51,17 +51,9 @@ typedef struct {
   double  max_delta_step;
   double  path_smooth;
   int32_t use_cuda_graph;           /* 1: replay the whole per-tree launch sequence as one CUDA graph */
-  int32_t reserved;                 /* bit 0: do NOT keep the column-major copy of the bin matrix used by the
-                                       partition kernels (saves num_data*num_columns bytes of HBM);
-                                       bit 1: do NOT stage contiguous (root) histogram passes with TMA tile copies;
-                                       bit 2: legacy column-group-major work mapping in the histogram kernel;
-                                       bit 3: experimental split gradient/hessian histogram kernel (slower; A/B only);
-                                       bit 4: programmatic dependent launch between the kernels of the per-split chain;
-                                       bit 5: k_select folded into the last block of k_scan;
-                                       bit 6: quantized training keeps int32x2 histogram cells (no packed 16:16 kernel);
-                                       bit 7: no L2 prefetch of gathered rows in the histogram producers;
-                                       bit 8: no leaf-ordered (g,h) copies (producers gather 8 B per row per column group);
-                                       bit 9: EXPERIMENTAL, not yet run on hardware: gathered histogram stages by TMA tile::gather4 */
+  int32_t reserved;                 /* bit 0: do NOT keep the column-major copy of the bin matrix used by the partition
+                                       kernels (saves num_data*num_columns bytes of HBM); other bits must be 0 (developer A/B
+                                       switches live in the LGBMB200_DEBUG environment variable, see learner.cu) */
   /* ---- quantized-gradient training (reference config.h:626-651; gradient_discretizer.cpp) */
   int32_t use_quantized_grad;       /* 1: discretize (g,h) to int8 per tree, integer histograms, integer split scan */
   int32_t num_grad_quant_bins;      /* config.h:638, default 4 */

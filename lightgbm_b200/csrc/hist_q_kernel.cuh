@@ -16,7 +16,7 @@
 // (RED.ADD.64 of the two unpacked fields) after at most R rows.  The hessian field is unsigned, the gradient field
 // signed: P = G * 65536 + H  =>  H = P & 0xffff, G = (P - H) >> 16.
 #pragma once
-#include "hist_kernel.cuh"
+#include "hist_common.cuh"
 
 namespace b200 {
 

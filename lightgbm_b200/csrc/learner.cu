@@ -19,8 +19,7 @@
 #include <vector>
 
 #include "../../include/lgbm_b200.h"
-#include "hist_kernel.cuh"
-#include "hist_g4_kernel.cuh"
+#include "hist_atom_kernel.cuh"
 #include "hist_q_kernel.cuh"
 #include "partition_kernel.cuh"
 #include "scan_kernel.cuh"
@@ -72,6 +71,15 @@ class Learner {
   explicit Learner(const LGBMB200_Config& cfg) { SetConfig(cfg); }
   ~Learner() { Destroy(); }
 
+  // Developer A/B switches (not part of the boundary): LGBMB200_DEBUG is a bit mask read once per process.
+  //   1: no column-major copy for the partition   2: no TMA staging   16: programmatic dependent launch on the chain
+  //   32: k_select folded into k_scan's last block   64: quantized training never uses the packed-cell kernel
+  //   256: no leaf-ordered (g,h) copies
+  static int DebugBits() {
+    static const int bits = std::getenv("LGBMB200_DEBUG") ? std::atoi(std::getenv("LGBMB200_DEBUG")) : 0;
+    return bits;
+  }
+
   void SetConfig(const LGBMB200_Config& cfg) {
     REQUIRE(cfg.num_leaves >= 2, "num_leaves must be >= 2");
     const bool leaves_changed = cfg.num_leaves != cfg_.num_leaves;
@@ -108,7 +116,7 @@ class Learner {
     InvalidateGraph();
 
     N_ = lay.num_data; C_ = lay.num_columns; F_ = lay.num_features;
-    Cpad_ = (C_ + kColGroup - 1) / kColGroup * kColGroup;
+    Cpad_ = (C_ + 2 * kColGroup - 1) / (2 * kColGroup) * (2 * kColGroup);     // whole column-group PAIRS: 64-byte rows = whole DRAM atoms
     pitch_ = Cpad_;
     std::vector<FeatMeta> fm(F_);
     for (int f = 0; f < F_; ++f) {
@@ -128,7 +136,7 @@ class Learner {
     CUDA_CHECK(cudaMemcpy2D(bins_.p, pitch_, bins_host, C_, C_, N_, cudaMemcpyHostToDevice));
 
     // column-major copy for the partition kernels (+C*N bytes; LGBMB200_Config.reserved bit 0 disables it)
-    if (!(cfg_.reserved & 1)) {
+    if (!(cfg_.reserved & 1) && !(DebugBits() & 1)) {
       // a pageable H2D cudaMemcpy may return before its DMA has landed, and stream_ is a non-blocking stream:
       // make the matrix resident before the first kernel reads it
       CUDA_CHECK(cudaDeviceSynchronize());
@@ -139,7 +147,7 @@ class Learner {
     } else {
       binsT_.release();
     }
-    gh_.alloc(N_); gho0_.alloc(N_); gho1_.alloc(N_); idx0_.alloc(N_); idx1_.alloc(N_); flags_.alloc((static_cast<size_t>(N_) + 31) / 32 * 4 + 256);
+    gq_.alloc(N_); gqo0_.alloc(N_); gqo1_.alloc(N_); idx0_.alloc(N_); idx1_.alloc(N_); flags_.alloc((static_cast<size_t>(N_) + 31) / 32 * 4 + 256);
     grad_stage_.alloc(N_); hess_stage_.alloc(N_);
     const_hess_ = is_constant_hessian != 0; hess_fill_valid_ = false;
     params_.quant_const_hess = const_hess_ ? 1 : 0;
@@ -157,13 +165,10 @@ class Learner {
     feature_used_.alloc(F_);
     have_feature_mask_ = false;
     bag_count_ = -1;
-    CUDA_CHECK(cudaFuncSetAttribute(k_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
-    CUDA_CHECK(cudaFuncSetAttribute(k_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
-    CUDA_CHECK(cudaFuncSetAttribute(k_hist_g4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
-    CUDA_CHECK(cudaFuncSetAttribute(k_hist_g4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
+    CUDA_CHECK(cudaFuncSetAttribute(k_hist_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AShape<true>::kSmem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_hist_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AShape<false>::kSmem));
     CUDA_CHECK(cudaFuncSetAttribute(k_hist_q, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmemBytes));
     CUDA_CHECK(cudaFuncSetAttribute(k_hist_q, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CUDA_CHECK(cudaFuncSetAttribute(k_hist2, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmemBytes));
     BuildTensorMap();
     inited_ = true;
     AllocTreeState();
@@ -379,6 +384,7 @@ class Learner {
     pa.peers.world = 1;            // stand-alone hook: local histogram only, no exchange
     k_prep<<<prep_blocks_, kPrepThreads, 0, stream_>>>(pa);
     k_root_init<<<1, 32, 0, stream_>>>(pa);
+    k_quant_rows<<<prep_blocks_, kPrepThreads, 0, stream_>>>(pa);
     const int32_t* didx = nullptr;
     int n = N_;
     if (idx_host != nullptr) {
@@ -387,14 +393,14 @@ class Learner {
       didx = idx1_.p; n = n_idx;
     }
     CUDA_CHECK(cudaMemsetAsync(pool_.p, 0, sizeof(long long) * slot_stride_, stream_));
-    HistArgs ha = MakeHistArgs();
+    HistAArgs ha = MakeHistArgs();
     ha.explicit_n = n; ha.explicit_slot = 0; ha.explicit_idx = didx;
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, stream_));
-    LaunchHist(ha);
+    LaunchHist(ha, HistQArgs{});
     CUDA_CHECK(cudaEventRecord(e1, stream_));
-    launches_ += 3;
+    launches_ += 4;
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(h_ctl_, ctl_.p, sizeof(Ctl), cudaMemcpyDeviceToHost, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -459,7 +465,7 @@ class Learner {
   }
   void CommShareColumns(const uint8_t* column_handles) {
     REQUIRE(peers_.world > 1 && peers_.mode != 1, "CommConnect (feature-shard) first");
-    REQUIRE(binsT_.p != nullptr, "the column-major copy is disabled (reserved bit 0)");
+    REQUIRE(binsT_.p != nullptr, "the column-major copy is disabled (LGBMB200_Config.reserved bit 0)");
     CUDA_CHECK(cudaStreamSynchronize(stream_));        // my own transpose has finished
     const int W = peers_.world;
     std::vector<int32_t> nf(W), nc(W), col_off(W + 1, 0), f_off(W + 1, 0);
@@ -582,35 +588,52 @@ class Learner {
 
   PrepArgs MakePrepArgs(const float* g, const float* h) {
     PrepArgs pa;
-    pa.grad = g; pa.hess = h; pa.gh = gh_.p; pa.idx0 = idx0_.p;
+    pa.grad = g; pa.hess = h; pa.gq = gq_.p; pa.idx0 = idx0_.p;
     pa.bag = bag_count_ >= 0 ? bag_.p : nullptr; pa.bag_count = bag_count_ >= 0 ? bag_count_ : 0;
     pa.num_data = N_; pa.partials = partials_.p; pa.leaves = leaves_.p; pa.ctl = ctl_.p; pa.params = params_;
     pa.max_leaves = params_.num_leaves; pa.num_partials = prep_blocks_; pa.peers = peers_;
     pa.ghq = PackedQuantHist() ? ghq_.p : nullptr;
     return pa;
   }
-  HistArgs MakeHistArgs() {
-    HistArgs ha;
-    ha.bins = bins_.p; ha.pitch = pitch_; ha.gh = gh_.p; ha.idx0 = idx0_.p; ha.idx1 = idx1_.p;
+  HistAArgs MakeHistArgs() {
+    HistAArgs ha;
+    ha.bins = bins_.p; ha.pitch = pitch_; ha.gq = gq_.p; ha.gqo0 = nullptr; ha.gqo1 = nullptr;      // gqo*: set by EnqueueTree
+    ha.idx0 = idx0_.p; ha.idx1 = idx1_.p;
+    ha.leaves = leaves_.p; ha.ctl = ctl_.p; ha.pool = reinterpret_cast<unsigned long long*>(pool_.p);
+    ha.slot_stride = slot_stride_; ha.num_colgroups = Cpad_ / kColGroup;
+    static const int min_rows = std::getenv("LGBMB200_MIN_ROWS") ? std::atoi(std::getenv("LGBMB200_MIN_ROWS")) : 2048;
+    ha.min_rows_per_cta = std::max(32, min_rows);
+    ha.explicit_n = -1; ha.explicit_slot = 0; ha.explicit_idx = nullptr;
+    ha.use_tma = have_tmap_ ? 1 : 0;
+    // L2 prefetch distance of the gathered passes, in stages of one producer warp (LGBMB200_PF overrides it)
+    static const int pf_stages = std::getenv("LGBMB200_PF") ? std::atoi(std::getenv("LGBMB200_PF")) : 4;
+    ha.l2_prefetch = pf_stages;
+    return ha;
+  }
+  // the packed-cell kernel of quantized training keeps the round-1 work mapping (hist_common.cuh)
+  HistQArgs MakeHistQArgs() {
+    HistQArgs qa;
+    HistArgs& ha = qa.h;
+    ha.bins = bins_.p; ha.pitch = pitch_; ha.idx0 = idx0_.p; ha.idx1 = idx1_.p;
     ha.leaves = leaves_.p; ha.ctl = ctl_.p; ha.pool = reinterpret_cast<unsigned long long*>(pool_.p);
     ha.slot_stride = slot_stride_; ha.num_colgroups = Cpad_ / kColGroup; ha.min_rows_per_item = 64;
     ha.explicit_n = -1; ha.explicit_slot = 0; ha.explicit_idx = nullptr;
     ha.use_tma = have_tmap_ ? 1 : 0;
-    ha.map_mode = (cfg_.reserved & 4) ? 0 : 1;
-    // distance tuned on 4M x 1024 (tools/tree_bench.py); LGBMB200_PF overrides it for experiments
-    static const int pf_stages = std::getenv("LGBMB200_PF") ? std::atoi(std::getenv("LGBMB200_PF")) : 8;
-    ha.l2_prefetch = (cfg_.reserved & 128) ? 0 : pf_stages;
-    ha.gho0 = nullptr; ha.gho1 = nullptr; ha.ghqo0 = nullptr; ha.ghqo1 = nullptr;      // set by EnqueueTree
-    return ha;
+    ha.map_mode = 1;
+    ha.l2_prefetch = 8;
+    ha.ghqo0 = nullptr; ha.ghqo1 = nullptr;
+    qa.ghq = ghq_.p;
+    qa.flush_rows = ((65535 / std::max(1, params_.quant_bins)) / kStageRows) * kStageRows;
+    return qa;
   }
 
   // 2-D tensor map over the row-major bin matrix {Cpad, N} with a {32 columns, 32 rows} box, for the TMA tile
   // loads of contiguous (root) stages.  cuTensorMapEncodeTiled is fetched from the driver at run time, so the
-  // library keeps depending on libcudart only.  LGBMB200_Config.reserved bit 1 turns TMA staging off.
+  // library keeps depending on libcudart only.  LGBMB200_DEBUG bit 2 turns TMA staging off.
   void BuildTensorMap() {
     have_tmap_ = false;
     std::memset(&tmap_, 0, sizeof(tmap_));
-    if (cfg_.reserved & 2) return;
+    if (DebugBits() & 2) return;
     typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -626,39 +649,31 @@ class Learner {
                                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     have_tmap_ = (r == CUDA_SUCCESS);
-    // second map for the experimental tile::gather4 path: box = {32 columns, 1 row}, four rows per instruction
-    have_tmap_g4_ = false;
-    std::memset(&tmap_g4_, 0, sizeof(tmap_g4_));
-    if (have_tmap_ && (cfg_.reserved & 512)) {
-      const cuuint32_t box1[2] = {kColGroup, 1};
-      const CUresult r4 = reinterpret_cast<EncodeTiled>(fn)(&tmap_g4_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, bins_.p, gdim, gstride, box1, estride,
+    // the constant-hessian histogram kernel stages two column groups per row: box = {64 columns, 32 rows}
+    std::memset(&tmap2_, 0, sizeof(tmap2_));
+    if (have_tmap_) {
+      const cuuint32_t box2[2] = {2 * kColGroup, kStageRows};
+      const CUresult r2 = reinterpret_cast<EncodeTiled>(fn)(&tmap2_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, bins_.p, gdim, gstride, box2, estride,
                                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      have_tmap_g4_ = (r4 == CUDA_SUCCESS);
+      have_tmap_ = (r2 == CUDA_SUCCESS);
     }
   }
 
-  // reserved bit 3 selects the experimental split kernel k_hist2 (separate gradient / hessian consumer warps,
-  // 6 consumers per SM).  Measured 12 % SLOWER than k_hist on 4M x 1024 (5.45 vs 4.85 ms): the kernel is bound by
-  // shared-memory wavefronts, not by latency, and the split re-reads the staged bins — kept for the record.
   // quantized training: packed 16:16 cells whenever a flush interval of at least 4096 rows keeps both fields in
-  // range (num_grad_quant_bins <= 15; reserved bit 6 forces the int32x2-cell kernel for A/B runs)
-  bool PackedQuantHist() const { return params_.quant && params_.quant_bins <= 15 && !(cfg_.reserved & 64); }
+  // range (num_grad_quant_bins <= 15; LGBMB200_DEBUG bit 64 forces the general kernel for A/B runs)
+  bool PackedQuantHist() const { return params_.quant && params_.quant_bins <= 15 && !(DebugBits() & 64); }
+  // constant hessian (Init's flag): the count-and-scale kernel; quantized training discretizes the hessian to 1 then too,
+  // but keeps the general kernel (its pool holds raw integer sums)
+  bool ConstHessHist() const { return const_hess_ && !params_.quant; }
 
-  void LaunchHist(const HistArgs& ha, bool chain = false, bool quant = false) {
-    if (quant && PackedQuantHist()) {
-      HistQArgs qa{ha, ghq_.p, ((65535 / params_.quant_bins) / kStageRows) * kStageRows};
-      LaunchChain(chain, k_hist_q, dim3(num_sms_ * 2), dim3(kHistThreads), kQSmemBytes, qa, tmap_);
-    } else if ((cfg_.reserved & 512) && have_tmap_g4_) {
-      // EXPERIMENTAL (not yet run on hardware): gathered stages through TMA tile::gather4, see hist_g4_kernel.cuh
-      if (quant) LaunchChain(chain, k_hist_g4<true>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_, tmap_g4_);
-      else LaunchChain(chain, k_hist_g4<false>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_, tmap_g4_);
-    } else if (quant) LaunchChain(chain, k_hist<true>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
-    else if (cfg_.reserved & 8) LaunchChain(chain, k_hist2, dim3(num_sms_), dim3(kHist2Threads), kHistSmemBytes, ha, tmap_);
-    else LaunchChain(chain, k_hist<false>, dim3(num_sms_), dim3(kHistThreads), kHistSmemBytes, ha, tmap_);
+  void LaunchHist(const HistAArgs& ha, const HistQArgs& qa, bool chain = false) {
+    if (PackedQuantHist()) LaunchChain(chain, k_hist_q, dim3(num_sms_ * 2), dim3(kHistThreads), kQSmemBytes, qa, tmap_);
+    else if (ConstHessHist()) LaunchChain(chain, k_hist_a<true>, dim3(num_sms_), dim3(kAThreads), AShape<true>::kSmem, ha, tmap2_);
+    else LaunchChain(chain, k_hist_a<false>, dim3(num_sms_), dim3(kAThreads), AShape<false>::kSmem, ha, tmap_);
   }
 
-  // Launch of a kernel of the per-split chain.  With LGBMB200_Config.reserved bit 4 the launch carries a
+  // Launch of a kernel of the per-split chain.  With LGBMB200_DEBUG bit 16 the launch carries a
   // programmatic-dependent-launch edge to its predecessor (see pdl_enter() in comm.cuh); inside stream capture
   // this becomes a programmatic graph edge.  Profiling mode (an event after every launch) keeps plain launches.
   template <typename... KArgs, typename... Args>
@@ -669,7 +684,7 @@ class Learner {
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
-    lc.numAttrs = (chain && (cfg_.reserved & 16) && !profiling_) ? 1 : 0;
+    lc.numAttrs = (chain && (DebugBits() & 16) && !profiling_) ? 1 : 0;
     CUDA_CHECK(cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...));
   }
 
@@ -677,7 +692,8 @@ class Learner {
   void EnqueueTree(const float* g, const float* h) {
     const int NL = params_.num_leaves;
     PrepArgs pa = MakePrepArgs(g, h);
-    HistArgs ha = MakeHistArgs();
+    HistAArgs ha = MakeHistArgs();
+    HistQArgs qa = MakeHistQArgs();
     ScanArgs sa;
     sa.feat = feat_.p; sa.feature_used = have_feature_mask_ ? feature_used_.p : nullptr; sa.num_features = F_;
     sa.params = params_; sa.leaves = leaves_.p; sa.ctl = ctl_.p; sa.pool = pool_.p; sa.slot_stride = slot_stride_;
@@ -686,17 +702,17 @@ class Learner {
     const bool row_mode = peers_.world > 1 && peers_.mode == 1;
     const int scan_blocks = ((row_mode ? peers_.f_cnt : F_) + kScanWarps - 1) / kScanWarps;
     SelectArgs se{feat_.p, F_, NL, leaves_.p, ctl_.p, cand_.p, block_best_.p, scan_blocks, splittable_.p, splittable_new_.p, peers_};
-    const bool fuse_select = (cfg_.reserved & 32) != 0;
+    const bool fuse_select = (DebugBits() & 32) != 0;
     sa.fuse_select = fuse_select ? 1 : 0; sa.sel = se;
     PartArgs pt;
     pt.bins = bins_.p; pt.binsT = peers_.mode == 2 ? binsT_full_.p : binsT_.p; pt.num_data = N_; pt.pitch = pitch_; pt.idx0 = idx0_.p; pt.idx1 = idx1_.p; pt.flag_words = reinterpret_cast<uint32_t*>(flags_.p);
     pt.block_left = block_left_.p; pt.leaves = leaves_.p; pt.ctl = ctl_.p; pt.splits = splits_.p; pt.params = params_;
     pt.peers = peers_;
-    const bool ordered = !(cfg_.reserved & 256);
+    const bool ordered = !(DebugBits() & 256);
     const bool packed = PackedQuantHist();
-    pt.gh = gh_.p; pt.gho0 = (ordered && !packed) ? gho0_.p : nullptr; pt.gho1 = (ordered && !packed) ? gho1_.p : nullptr;
+    pt.gh = gq_.p; pt.gho0 = (ordered && !packed) ? gqo0_.p : nullptr; pt.gho1 = (ordered && !packed) ? gqo1_.p : nullptr;
     pt.ghq = ghq_.p; pt.ghqo0 = (ordered && packed) ? ghqo0_.p : nullptr; pt.ghqo1 = (ordered && packed) ? ghqo1_.p : nullptr;
-    ha.gho0 = pt.gho0; ha.gho1 = pt.gho1; ha.ghqo0 = pt.ghqo0; ha.ghqo1 = pt.ghqo1;
+    ha.gqo0 = pt.gho0; ha.gqo1 = pt.gho1; qa.h.ghqo0 = pt.ghqo0; qa.h.ghqo1 = pt.ghqo1;
     prof_n_ = 0;
     Stamp(kProfStart);
 
@@ -710,6 +726,7 @@ class Learner {
       launches_ += 2;
     }
     k_root_init<<<1, 32, 0, stream_>>>(pa);
+    if (!quant) { k_quant_rows<<<prep_blocks_, kPrepThreads, 0, stream_>>>(pa); ++launches_; }     // per-tree fixed point of (g, h)
     CUDA_CHECK(cudaMemsetAsync(splittable_.p, 1, static_cast<size_t>(NL) * F_, stream_));
     launches_ += 2;
     Stamp(kProfPrep);
@@ -726,7 +743,7 @@ class Learner {
         launches_ += 2;
         if (it == NL - 1) break;   // the tree is full: no need to look for further splits
       }
-      LaunchHist(ha, it > 0, quant);   // it == 0 follows a memset node: plain dependency
+      LaunchHist(ha, qa, it > 0);   // it == 0 follows a memset node: plain dependency
       Stamp(kProfHist);
       if (row_mode) { LaunchChain(true, k_hist_signal, dim3(1), dim3(32), 0, peers_, ctl_.p); ++launches_; }
       if (row_mode) LaunchChain(true, k_scan<true, false>, dim3(std::max(scan_blocks, 1), 1), dim3(kScanWarps * 32), 0, sa);
@@ -835,7 +852,7 @@ class Learner {
   DevBuf<FeatMeta> gmeta_;
   DevBuf<uint8_t> bins_, binsT_, flags_, feature_used_, splittable_, splittable_new_;
   DevBuf<BlockBest> block_best_;
-  DevBuf<float2> gh_, gho0_, gho1_;     // (g,h) by row id; leaf-ordered copies parallel to idx0_/idx1_
+  DevBuf<int2> gq_, gqo0_, gqo1_;       // per-tree fixed-point (g,h) by row id; leaf-ordered copies parallel to idx0_/idx1_
   DevBuf<int32_t> ghqo0_, ghqo1_;
   static constexpr int kRenewBlocks = 64;
   DevBuf<double> renew_partial_, renew_out_;
@@ -853,8 +870,8 @@ class Learner {
   DevBuf<PartialSum> partials_;
   CommPeers peers_{};
   CUtensorMap tmap_;
-  bool have_tmap_ = false, have_tmap_g4_ = false;
-  CUtensorMap tmap_g4_;
+  bool have_tmap_ = false;
+  CUtensorMap tmap2_;
   void* comm_local_ = nullptr;
   int64_t comm_stride_ = 0;
   std::vector<void*> comm_opened_;

@@ -36,10 +36,10 @@ struct PartArgs {
   Ctl* ctl;
   SplitRec* splits;        // [num_leaves-1] output records
   Params params;
-  // leaf-ordered copies of the per-row (g,h) [and of the packed quantized word], parallel to idx0 / idx1: the
-  // scatter writes them next to the row ids, so that the histogram producers of a non-root leaf stream (g,h)
-  // contiguously instead of gathering 8 bytes per row per column group (nullptr: off)
-  const float2* gh; float2* gho0; float2* gho1;
+  // leaf-ordered copies of the per-row fixed-point (g,h) [and of the packed quantized word], parallel to idx0 / idx1:
+  // the scatter writes them next to the row ids, so that the histogram producers of a non-root leaf stream (g,h)
+  // contiguously instead of gathering 8 bytes per row per column-group set (nullptr: off)
+  const int2* gh; int2* gho0; int2* gho1;
   const int32_t* ghq; int32_t* ghqo0; int32_t* ghqo1;
 };
 
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
   const int n = c->cur_count, begin = c->cur_begin;
   const int32_t* src = (c->cur_buf ? a.idx1 : a.idx0) + begin;
   int32_t* dst = (c->cur_buf ? a.idx0 : a.idx1) + begin;
-  float2* gho = a.gho0 ? (c->cur_buf ? a.gho0 : a.gho1) + begin : nullptr;
+  int2* gho = a.gho0 ? (c->cur_buf ? a.gho0 : a.gho1) + begin : nullptr;
   int32_t* ghqo = a.ghqo0 ? (c->cur_buf ? a.ghqo0 : a.ghqo1) + begin : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* fw = a.flag_words;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
   part_block_range(n, gridDim.x, blockIdx.x, &lo, &hi);
   for (int base = lo; base < hi; base += kPartThreads * kPartUnroll) {
     unsigned word[kPartUnroll]; int row[kPartUnroll];
-    float2 gv[kPartUnroll]; int qv[kPartUnroll];
+    int2 gv[kPartUnroll]; int qv[kPartUnroll];
 #pragma unroll
     for (int k = 0; k < kPartUnroll; ++k) {
       const int i = base + k * kPartThreads + tid;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
 #pragma unroll
     for (int k = 0; k < kPartUnroll; ++k) {
       const bool mine = copy_both || ((((word[k] >> lane) & 1u) != 0u) == left_smaller);
-      gv[k] = (gho != nullptr && row[k] >= 0 && mine) ? __ldg(a.gh + row[k]) : make_float2(0.f, 0.f);
+      gv[k] = (gho != nullptr && row[k] >= 0 && mine) ? __ldg(a.gh + row[k]) : make_int2(0, 0);
       qv[k] = (ghqo != nullptr && row[k] >= 0 && mine) ? __ldg(a.ghq + row[k]) : 0;
     }
     __syncthreads();
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) k_transpose_bins(const uint8_t* __restric
 struct PrepArgs {
   const float* grad;
   const float* hess;
-  float2* gh;
+  int2* gq;                 // [num_data] fixed-point (g, h) of this tree (k_quant_rows; quantized training: k_quantize)
   int32_t* idx0;
   const int32_t* bag;       // device bag indices or nullptr
   int32_t bag_count;
@@ -351,7 +351,6 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep(const PrepArgs a) {
   double sg = 0.0, sh = 0.0; float mg = 0.f, mh = 0.f;
   for (int i = lo + threadIdx.x; i < hi; i += kPrepThreads) {
     const float g = a.grad[i], h = a.hess[i];
-    a.gh[i] = make_float2(g, h);
     mg = fmaxf(mg, fabsf(g)); mh = fmaxf(mh, fabsf(h));
     if (a.bag == nullptr) { sg += g; sh += h; a.idx0[i] = i; }
   }
@@ -383,10 +382,11 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep(const PrepArgs a) {
 }
 
 __device__ __forceinline__ double pow2_scale(double bound) {
-  // largest power of two s with bound * s < 2^61 (bound = rows * max|value|)
+  // largest power of two s with bound * s < 2^30 (bound = max|value| over the rows): every row's value becomes a
+  // 30-bit integer (hist_atom_kernel.cuh), and a sum over up to 2^31 rows stays below 2^61
   if (!(bound > 0.0)) return 1.0;
   int e; frexp(bound, &e);            // bound < 2^e
-  int k = 61 - e;
+  int k = 30 - e;
   if (k > 1000) k = 1000;
   if (k < -1000) k = -1000;
   return ldexp(1.0, k);
@@ -450,16 +450,27 @@ __global__ void __launch_bounds__(32) k_root_init(const PrepArgs a) {
   c->smaller = 0; c->larger = -1; c->do_find = 1; c->num_leaves = 1;
   // BeforeFindBestSplit at the root: too few rows to ever split
   if (n_root < a.params.min_data_in_leaf * 2) c->do_find = 0;
-  c->g_scale = pow2_scale(static_cast<double>(n_root) * mg);
-  c->h_scale = pow2_scale(static_cast<double>(n_root) * mh);
+  c->g_scale = pow2_scale(static_cast<double>(mg));
+  c->h_scale = pow2_scale(static_cast<double>(mh));
   if (a.params.quant) { c->g_scale = 1.0; c->h_scale = 1.0; }     // the pool holds the raw integer sums
   c->g_inv = 1.0 / c->g_scale; c->h_inv = 1.0 / c->h_scale;
   c->root_sum_g = sg; c->root_sum_h = sh; c->root_count = n_root; c->root_identity = a.bag ? 0 : 1;
+  // constant hessian (Init(..., is_constant_hessian)): the per-row fixed-point hessian the histogram kernel scales its
+  // row counts with (the reference counts and multiplies by hessians[0] the same way, dataset.cpp:1430-1437)
+  c->h_const_q = a.params.quant ? 1 : llrint(static_cast<double>(a.hess[0]) * c->h_scale);
+}
+
+// Per-tree fixed point: q = rint(value * scale), scale = the power of two k_root_init just chose (|q| < 2^30).
+__global__ void __launch_bounds__(kPrepThreads) k_quant_rows(const PrepArgs a) {
+  const Ctl* c = a.ctl;
+  const double gs = c->g_scale, hs = c->h_scale;       // powers of two: the products are exact, one rounding to integer
+  for (int i = blockIdx.x * kPrepThreads + threadIdx.x; i < a.num_data; i += gridDim.x * kPrepThreads)
+    a.gq[i] = make_int2(__double2int_rn(static_cast<double>(a.grad[i]) * gs), __double2int_rn(static_cast<double>(a.hess[i]) * hs));
 }
 
 // ---- quantized-gradient training: GradientDiscretizer::DiscretizeGradients (gradient_discretizer.cpp:68-160) ----
 // k_prep has left max|g|, max|h| over ALL rows in the partials.  k_quant_scales turns them into the tree's scales;
-// k_quantize overwrites gh[] with the int8 values (stored as two int32 bit patterns in the float2 slots, consumed by
+// k_quantize writes the int8 values into gq[] (consumed by
 // k_hist<true>) and replaces the partials by the integer root sums (over the bag if there is one).
 __global__ void __launch_bounds__(32) k_quant_scales(const PrepArgs a) {
   if (threadIdx.x != 0) return;
@@ -509,7 +520,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_quantize(const PrepArgs a) {
   long long sg = 0, sh = 0; int mg = 0, mh = 0;
   for (int i = lo + threadIdx.x; i < hi; i += kPrepThreads) {
     const int2 q = quantize_row(a, c, i);
-    a.gh[i] = make_float2(__int_as_float(q.x), __int_as_float(q.y));
+    a.gq[i] = q;
     if (a.ghq != nullptr) a.ghq[i] = q.x * 65536 + q.y;
     mg = max(mg, abs(q.x)); mh = max(mh, abs(q.y));
     if (a.bag == nullptr) { sg += q.x; sh += q.y; }

@@ -79,6 +79,7 @@ struct Ctl {
   // fixed-point scales of the int64 histogram (power of two), set once per tree
   double g_scale, h_scale, g_inv, h_inv;
   double root_sum_g, root_sum_h;
+  long long h_const_q;         // constant-hessian training: rint(hessians[0] * h_scale), the per-row fixed-point hessian
   // quantized training: GradientDiscretizer::grad_scale() / hess_scale() of this tree and their inverses
   double q_gscale, q_hscale, q_ginv, q_hinv;
   unsigned long long quant_iter;   // trees discretized so far (stochastic rounding stream id)

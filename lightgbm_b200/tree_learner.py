@@ -68,7 +68,7 @@ class Config:
     path_smooth: float = 0.0
     gpu_device_id: int = -1
     use_cuda_graph: bool = True
-    reserved: int = int(os.environ.get("LGBMB200_RESERVED", "0"))   # experiment switches, see include/lgbm_b200.h
+    reserved: int = 0                     # bit 0: no column-major partition copy (include/lgbm_b200.h)
     use_quantized_grad: bool = False      # reference config.h:626-651
     num_grad_quant_bins: int = 4
     quant_train_renew_leaf: bool = False

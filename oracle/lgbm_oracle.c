@@ -74,6 +74,9 @@ void orc_construct_histogram(const OrcLayout* L, const uint8_t* bins, const int3
   memset(hist, 0, sizeof(double) * (size_t)C * 256 * 2);
   /* column-major loop order == the col-wise CPU path (dataset.cpp:1390-1440): for each group the rows
    * are visited in leaf order and added in fp64 (dense_bin.hpp:109-137). */
+  /* columns are independent and every cell keeps its row order, so threading over columns (only worth it for the
+   * benchmark-scale parity tests) cannot change a single bit of the result */
+#pragma omp parallel for schedule(dynamic, 4) if ((int64_t)n * C > (1 << 24))
   for (int c = 0; c < C; ++c) {
     double* h = hist + (size_t)c * 512;
     for (int32_t i = 0; i < n; ++i) {
@@ -92,7 +95,7 @@ typedef struct { double gain; int threshold; int left_count; double slg, slh; in
 static void scan_one_direction(const double* d, int num_bin, int offset, int default_bin, const OrcParams* P,
                                const GainCfg* gc, double sum_gradient, double sum_hessian, int32_t num_data,
                                double min_gain_shift, double parent_output, int reverse, int skip_default,
-                               int na_as_missing, int* is_splittable, OrcSplit* out) {
+                               int na_as_missing, int* is_splittable, OrcSplit* out, double* top2) {
   double best_slg = NAN, best_slh = NAN, best_gain = K_MIN_SCORE;
   int32_t best_left_count = 0;
   int best_threshold = num_bin;
@@ -117,6 +120,7 @@ static void scan_one_direction(const double* d, int num_bin, int offset, int def
                          leaf_gain(gc, srg, srh, right_count, parent_output);
       if (cur <= min_gain_shift) continue;
       *is_splittable = 1;
+      if (cur > top2[0]) { top2[1] = top2[0]; top2[0] = cur; } else if (cur > top2[1]) top2[1] = cur;   /* checker only */
       if (cur > best_gain) {
         best_left_count = left_count; best_slg = slg; best_slh = slh;
         best_threshold = t - 1 + offset; best_gain = cur;
@@ -152,6 +156,7 @@ static void scan_one_direction(const double* d, int num_bin, int offset, int def
                          leaf_gain(gc, srg, srh, right_count, parent_output);
       if (cur <= min_gain_shift) continue;
       *is_splittable = 1;
+      if (cur > top2[0]) { top2[1] = top2[0]; top2[0] = cur; } else if (cur > top2[1]) top2[1] = cur;   /* checker only */
       if (cur > best_gain) {
         best_left_count = left_count; best_slg = slg; best_slh = slh;
         best_threshold = t + offset; best_gain = cur;
@@ -200,20 +205,22 @@ int orc_find_best_threshold(const OrcLayout* L, const OrcParams* P, int f, doubl
   /* BeforeNumerical (:177-196) */
   int is_splittable = 0;
   const double min_gain_shift = leaf_gain(&gc, sum_gradient, sum_hessian, num_data, parent_output) + P->min_gain_to_split;
+  double top2[2] = {K_MIN_SCORE, K_MIN_SCORE};   /* the two largest candidate gains of this feature (parity checker's margin rule) */
 
   /* direction dispatch FuncForNumricalL3 (:396-441) */
   if (num_bin > 2 && missing != ORC_MISSING_NONE) {
     if (missing == ORC_MISSING_ZERO) {
-      scan_one_direction(d, num_bin, offset, default_bin, P, &gc, sum_gradient, sum_hessian, num_data, min_gain_shift, parent_output, 1, 1, 0, &is_splittable, out);
-      scan_one_direction(d, num_bin, offset, default_bin, P, &gc, sum_gradient, sum_hessian, num_data, min_gain_shift, parent_output, 0, 1, 0, &is_splittable, out);
+      scan_one_direction(d, num_bin, offset, default_bin, P, &gc, sum_gradient, sum_hessian, num_data, min_gain_shift, parent_output, 1, 1, 0, &is_splittable, out, top2);
+      scan_one_direction(d, num_bin, offset, default_bin, P, &gc, sum_gradient, sum_hessian, num_data, min_gain_shift, parent_output, 0, 1, 0, &is_splittable, out, top2);
     } else {
-      scan_one_direction(d, num_bin, offset, default_bin, P, &gc, sum_gradient, sum_hessian, num_data, min_gain_shift, parent_output, 1, 0, 1, &is_splittable, out);
-      scan_one_direction(d, num_bin, offset, default_bin, P, &gc, sum_gradient, sum_hessian, num_data, min_gain_shift, parent_output, 0, 0, 1, &is_splittable, out);
+      scan_one_direction(d, num_bin, offset, default_bin, P, &gc, sum_gradient, sum_hessian, num_data, min_gain_shift, parent_output, 1, 0, 1, &is_splittable, out, top2);
+      scan_one_direction(d, num_bin, offset, default_bin, P, &gc, sum_gradient, sum_hessian, num_data, min_gain_shift, parent_output, 0, 0, 1, &is_splittable, out, top2);
     }
   } else {
-    scan_one_direction(d, num_bin, offset, default_bin, P, &gc, sum_gradient, sum_hessian, num_data, min_gain_shift, parent_output, 1, 0, 0, &is_splittable, out);
+    scan_one_direction(d, num_bin, offset, default_bin, P, &gc, sum_gradient, sum_hessian, num_data, min_gain_shift, parent_output, 1, 0, 0, &is_splittable, out, top2);
     if (missing == ORC_MISSING_NAN) out->default_left = 0;
   }
+  out->second_gain = top2[1] > K_MIN_SCORE ? top2[1] - min_gain_shift : K_MIN_SCORE;
   return is_splittable;
 }
 
@@ -467,7 +474,7 @@ static int train_impl(const OrcLayout* L, const uint8_t* bins, const float* grad
   int32_t n_root;
   if (bag_indices) { n_root = bag_count; memcpy(T->indices, bag_indices, sizeof(int32_t) * (size_t)bag_count); }
   else { n_root = L->num_data; for (int32_t i = 0; i < n_root; ++i) T->indices[i] = i; }
-  for (int i = 0; i < NL; ++i) { best[i].feature = -1; best[i].gain = K_MIN_SCORE; T->leaf_begin[i] = 0; T->leaf_count[i] = 0; T->leaf_depth[i] = 0; }
+  for (int i = 0; i < NL; ++i) { best[i].feature = -1; best[i].gain = K_MIN_SCORE; best[i].second_gain = K_MIN_SCORE; T->leaf_begin[i] = 0; T->leaf_count[i] = 0; T->leaf_depth[i] = 0; }
   T->leaf_count[0] = n_root;
   double sg = 0.0, sh = 0.0;
   if (!Q) {
@@ -535,6 +542,7 @@ static int train_impl(const OrcLayout* L, const uint8_t* bins, const float* grad
 
       OrcSplit bs, bl; bs.feature = -1; bs.gain = K_MIN_SCORE; bl = bs;
       int bs_real = 0, bl_real = 0;
+      double bs2 = K_MIN_SCORE, bl2 = K_MIN_SCORE;   /* runner-up candidate gain per leaf (checker only) */
       for (int f = 0; f < F; ++f) {
         if (!used[f]) continue;
         OrcSplit s; memset(&s, 0, sizeof(s));
@@ -543,6 +551,9 @@ static int train_impl(const OrcLayout* L, const uint8_t* bins, const float* grad
         else sp_small[f] = (uint8_t)orc_find_best_threshold_int(L, P, f, h_small, 1, leaf_ig[smaller], leaf_ih[smaller], Q->grad_scale, Q->hess_scale,
                                                               T->leaf_count[smaller], po_small, &s, &ilg, &ilh);
         s.leaf = smaller;
+        if (Q) s.second_gain = K_MIN_SCORE;
+        if (split_better(&s, L->feat_real_index[f], &bs, bs_real)) { if (bs.feature >= 0 && bs.gain > bs2) bs2 = bs.gain; if (s.second_gain > bs2) bs2 = s.second_gain; }
+        else if (s.gain > bs2) bs2 = s.gain;
         if (split_better(&s, L->feat_real_index[f], &bs, bs_real)) { bs = s; bs_real = L->feat_real_index[f]; best_ilg[smaller] = ilg; best_ilh[smaller] = ilh; }
         if (larger < 0) continue;
         /* FeatureHistogram::Subtract (feature_histogram.hpp:96-145) on the feature's slice */
@@ -558,11 +569,14 @@ static int train_impl(const OrcLayout* L, const uint8_t* bins, const float* grad
         else sp_large[f] = (uint8_t)orc_find_best_threshold_int(L, P, f, h_large, 0, leaf_ig[larger], leaf_ih[larger], Q->grad_scale, Q->hess_scale,
                                                               T->leaf_count[larger], po_large, &l, &ilg, &ilh);
         l.leaf = larger;
+        if (Q) l.second_gain = K_MIN_SCORE;
+        if (split_better(&l, L->feat_real_index[f], &bl, bl_real)) { if (bl.feature >= 0 && bl.gain > bl2) bl2 = bl.gain; if (l.second_gain > bl2) bl2 = l.second_gain; }
+        else if (l.gain > bl2) bl2 = l.gain;
         if (split_better(&l, L->feat_real_index[f], &bl, bl_real)) { bl = l; bl_real = L->feat_real_index[f]; best_ilg[larger] = ilg; best_ilh[larger] = ilh; }
       }
       free(used);
-      bs.leaf = smaller; best[smaller] = bs;
-      if (larger >= 0) { bl.leaf = larger; best[larger] = bl; }
+      bs.leaf = smaller; bs.second_gain = bs2; best[smaller] = bs;
+      if (larger >= 0) { bl.leaf = larger; bl.second_gain = bl2; best[larger] = bl; }
     }
 
     /* ArgMax over best_split_per_leaf_ (array_args.h:45-60) — all num_leaves slots, operator> */
@@ -574,6 +588,8 @@ static int train_impl(const OrcLayout* L, const uint8_t* bins, const float* grad
     }
     OrcSplit* s = &best[best_leaf];
     if (s->gain <= 0.0) break;  /* serial_tree_learner.cpp:232 (gain <= 0 -> stop) */
+    /* checker only: the best candidate NOT taken at this step = max(runner-up inside the chosen leaf, other leaves' bests) */
+    for (int i = 0; i < NL; ++i) if (i != best_leaf && best[i].feature >= 0 && best[i].gain > s->second_gain) s->second_gain = best[i].gain;
 
     /* SplitInner (:769-925) */
     const int next_leaf = T->num_leaves;

@@ -68,6 +68,11 @@ typedef struct {
   double  gain;            /* best_gain - min_gain_shift                                        */
   double  left_sum_gradient, left_sum_hessian, left_output;
   double  right_sum_gradient, right_sum_hessian, right_output;
+  double  second_gain;     /* NOT a reference field: the largest gain among the candidates NOT taken when this split was
+                              chosen (other thresholds, other features, other leaves), minus the same min_gain_shift.
+                              The parity tests accept a divergence of the CUDA path only where gain - second_gain is
+                              below the stated tolerance (SURVEY.md 8d margin rule).  -inf when there was no runner-up;
+                              not tracked (= -inf) on the quantized path, which must match exactly. */
 } OrcSplit;
 
 typedef struct {

@@ -30,13 +30,15 @@ class _OrcSplit(C.Structure):
     _fields_ = [("leaf", C.c_int32), ("feature", C.c_int32), ("threshold", C.c_int32), ("default_left", C.c_int32),
                 ("left_count", C.c_int32), ("right_count", C.c_int32), ("gain", C.c_double),
                 ("left_sum_gradient", C.c_double), ("left_sum_hessian", C.c_double), ("left_output", C.c_double),
-                ("right_sum_gradient", C.c_double), ("right_sum_hessian", C.c_double), ("right_output", C.c_double)]
+                ("right_sum_gradient", C.c_double), ("right_sum_hessian", C.c_double), ("right_output", C.c_double),
+                ("second_gain", C.c_double)]
 
 
 SPLIT_DTYPE = np.dtype([("leaf", "i4"), ("feature", "i4"), ("threshold", "i4"), ("default_left", "i4"),
                         ("left_count", "i4"), ("right_count", "i4"), ("gain", "f8"),
                         ("left_sum_gradient", "f8"), ("left_sum_hessian", "f8"), ("left_output", "f8"),
-                        ("right_sum_gradient", "f8"), ("right_sum_hessian", "f8"), ("right_output", "f8")], align=True)
+                        ("right_sum_gradient", "f8"), ("right_sum_hessian", "f8"), ("right_output", "f8"),
+                        ("second_gain", "f8")], align=True)
 assert SPLIT_DTYPE.itemsize == C.sizeof(_OrcSplit)
 
 

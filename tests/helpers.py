@@ -25,11 +25,19 @@ def logistic_grad(y01, score=0.0):
     return g, h
 
 
+MARGIN_TOL = 1e-5      # stated tolerance of the split-sequence comparison
+DIVERGENCES = []       # (test-visible) log of accepted near-tie divergences: (split index, relative margin)
+
+
 def compare_trees(gpu, orc, rtol=1e-5, min_prefix=None):
     """gpu: lightgbm_b200.Tree, orc: oracle_py.OracleTree.  Returns (#splits that matched exactly, diverged?).
-    Structural fields must match exactly; float fields within rtol.  A divergence is tolerated only when it
-    is a near tie (the two gains agree within rtol), per the reference's own CPU<->GPU tolerance
-    (tests/python_package_test/test_dual.py:35-36)."""
+
+    Every split must match the oracle's: structural fields exactly, float fields within rtol*10.  The ONLY tolerated
+    divergence is the margin rule of SURVEY.md §8d: at the first differing split the ORACLE's own best-vs-runner-up
+    margin (gain - second_gain, recorded by oracle/lgbm_oracle.c for every split) must be below MARGIN_TOL relative,
+    i.e. the reference's choice was itself a numerical coin flip; the comparison then stops (the trees legitimately
+    differ from there on) and the divergence is logged in DIVERGENCES.  A mismatch at a split whose margin is larger
+    fails the test."""
     ns = min(gpu.num_leaves, orc.num_leaves) - 1
     matched = 0
     for i in range(ns):
@@ -37,8 +45,17 @@ def compare_trees(gpu, orc, rtol=1e-5, min_prefix=None):
         same = (a["leaf"] == b["leaf"] and a["feature"] == b["feature"] and a["threshold"] == b["threshold"]
                 and a["default_left"] == b["default_left"])
         if not same:
+            names = b.dtype.names or ()
+            second = float(b["second_gain"]) if "second_gain" in names else float("-inf")
+            margin = (float(b["gain"]) - second) / max(abs(float(b["gain"])), 1e-300)
+            assert margin < MARGIN_TOL, (f"split {i}: structural mismatch where the oracle's margin is {margin:.3e} "
+                                         f"(>= {MARGIN_TOL}): gpu={a} oracle={b}")
             rel = abs(a["gain"] - b["gain"]) / max(abs(b["gain"]), 1e-300)
-            assert rel < rtol * 10, f"split {i}: structural mismatch that is not a near tie: gpu={a} oracle={b}"
+            assert rel < rtol * 10, f"split {i}: near-tie divergence but the gains differ by {rel:.3e}: gpu={a} oracle={b}"
+            DIVERGENCES.append((i, margin))
+            print(f"[compare_trees] accepted near-tie divergence at split {i}/{ns}: oracle margin {margin:.3e}")
+            if min_prefix is not None:
+                assert matched >= min_prefix
             return matched, True
         assert a["left_count"] == b["left_count"] and a["right_count"] == b["right_count"], f"split {i} counts {a} {b}"
         for k in ("gain", "left_sum_gradient", "left_sum_hessian", "right_sum_gradient", "right_sum_hessian",

@@ -36,7 +36,8 @@ def test_cuda_path_on_golden_fixture(built_lib, name):
         np.testing.assert_allclose(t.leaf_value, o.leaf_value, rtol=1e-11 if not q["renew_leaf"] else 1e-9, atol=1e-15)
         assert golden_io.check_against_reference(t, g, exact_values=False) == o.num_leaves - 1
     n_ref = golden_io.check_against_reference(t, g, exact_values=False)
-    assert matched >= min(3, o.num_leaves - 1) and n_ref >= min(3, o.num_leaves - 1)
+    # the oracle reproduces the reference bit for bit, so a full match against it is a full match against the reference
+    assert diverged or (matched == o.num_leaves - 1 and n_ref == o.num_leaves - 1)
     if g.kat_y is not None and name != "kat_missing_none":
         lb, lc, idx = L.get_partition(t.num_leaves)
         pred = golden_io.row_predictions(t, lb, lc, idx, lay.num_data)

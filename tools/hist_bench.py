@@ -9,10 +9,10 @@ rng = np.random.default_rng(0)
 bins = rng.integers(0, 255, (n, f), dtype=np.uint8)
 g = rng.normal(size=n).astype(np.float32); h = np.ones(n, np.float32)
 cfg = lgb.Config(num_leaves=4, use_cuda_graph=False)
-_orig = cfg.to_c
-cfg.to_c = lambda: (lambda c: (setattr(c, "reserved", int(os.environ.get("HB_RESERVED", 0))), c)[1])(_orig())
+const_h = os.environ.get("HB_CONST", "1") == "1"        # 1: constant-hessian (count-and-scale) kernel, 0: general hessians
 L = lgb.B200TreeLearner(cfg)
-L.init(lgb.Layout.identity(bins))
+L.init(lgb.Layout.identity(bins), is_constant_hessian=const_h)
+print("constant_hessian", const_h)
 from lightgbm_b200.tree_learner import DeviceArray
 dg = DeviceArray(n * 4).upload(g); dh = DeviceArray(n * 4).upload(h)
 for label, idx in (("root", None), ("gather50", np.sort(rng.choice(n, n // 2, replace=False)).astype(np.int32)),

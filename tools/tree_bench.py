@@ -1,6 +1,6 @@
 """Trains a few trees on an N x F synthetic matrix (ncu captures of the non-histogram kernels, A/B of launch
 options).  Prints the device time per tree (CUDA events on the learner's stream) and a hash of the split records so
-that two runs with different LGBMB200_RESERVED bits can be checked for identical trees."""
+that two runs with different LGBMB200_DEBUG bits can be checked for identical trees."""
 import hashlib, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -25,5 +25,5 @@ warm = ms[min(2, len(ms) - 1):]
 if os.environ.get("TB_PROFILE"):
     B.learner.set_profiling(True); B.learner.hist_stats(reset=True); B.update(); B.learner.set_profiling(False)
     print("by_kind_ms", {k: round(v, 3) for k, v in B.learner.profile_by_kind().items()}, "l2", B.l2())
-print(f"quant_bins={qb} reserved={lgb.Config().reserved} rows={n} cols={f} leaves={leaves} device_ms_per_tree mean={np.mean(warm):.3f} min={np.min(warm):.3f} "
+print(f"quant_bins={qb} debug={os.environ.get('LGBMB200_DEBUG', '0')} rows={n} cols={f} leaves={leaves} device_ms_per_tree mean={np.mean(warm):.3f} min={np.min(warm):.3f} "
       f"trees_sha1={h.hexdigest()[:16]}")
