@@ -130,6 +130,10 @@ LGBMB200_EXPORT int LGBMB200_LearnerInit(LGBMB200_LearnerHandle h, const LGBMB20
 /* TreeLearner::ResetConfig(const Config*) — reference tree_learner.h:56 */
 LGBMB200_EXPORT int LGBMB200_LearnerResetConfig(LGBMB200_LearnerHandle h, const LGBMB200_Config* config);
 
+/* TreeLearner::ResetIsConstantHessian(bool) — reference tree_learner.h:49 (GBDT::ResetTrainingData may swap the
+ * objective): switches between the count-and-scale histogram kernel and the general one. */
+LGBMB200_EXPORT int LGBMB200_LearnerSetConstantHessian(LGBMB200_LearnerHandle h, int32_t is_constant_hessian);
+
 /* ColSampler by-tree mask (reference src/treelearner/col_sampler.hpp; serial_tree_learner.cpp:297):
  * feature_used[num_features] bytes on the host, or NULL for "all features". */
 LGBMB200_EXPORT int LGBMB200_LearnerSetFeatureMask(LGBMB200_LearnerHandle h, const uint8_t* feature_used);

@@ -5,6 +5,9 @@
 #include <LightGBM/bin.h>
 #include <LightGBM/utils/log.h>
 
+#include <LightGBM/utils/openmp_wrapper.h>
+
+#include <algorithm>
 #include <cmath>
 
 namespace LightGBM {
@@ -37,12 +40,23 @@ void B200TreeLearner::Check(int ret) const {
   if (ret != 0) Log::Fatal("lgbm_b200: %s", LGBMB200_GetLastError());
 }
 
-B200TreeLearner::B200TreeLearner(const Config* config) : config_(config), col_sampler_(config) {
-  // features of the reference learner that this hot-path library does not cover
+// Config fields that change the reference learner's split choice but are outside this hot-path library (SURVEY.md §8,
+// DESIGN.md §7): refuse them loudly instead of silently training a different model than device_type=cpu would.
+void B200TreeLearner::CheckSupported(const Config* config) {
   if (!config->monotone_constraints.empty()) Log::Fatal("lgbm_b200: monotone constraints are not supported");
   if (config->extra_trees) Log::Fatal("lgbm_b200: extra_trees is not supported");
   if (config->feature_fraction_bynode < 1.0) Log::Fatal("lgbm_b200: feature_fraction_bynode is not supported");
   if (config->cegb_tradeoff < 1.0 || config->cegb_penalty_split > 0.0) Log::Fatal("lgbm_b200: CEGB is not supported");
+  for (double v : config->feature_contri)
+    if (v != 1.0) Log::Fatal("lgbm_b200: feature_contri (per-feature gain penalty, feature_histogram.hpp:174) is not supported");
+  if (!config->interaction_constraints.empty()) Log::Fatal("lgbm_b200: interaction_constraints are not supported");
+  if (config->linear_tree) Log::Fatal("lgbm_b200: linear_tree is not supported");
+  if (config->num_machines > 1) Log::Fatal("lgbm_b200: num_machines > 1 is not supported (multi-GPU runs inside one machine)");
+  if (config->max_bin > 255) Log::Fatal("lgbm_b200: max_bin > 255 is not supported");
+}
+
+B200TreeLearner::B200TreeLearner(const Config* config) : config_(config), col_sampler_(config) {
+  CheckSupported(config);
   LGBMB200_Config c = ToB200Config(config);
   Check(LGBMB200_LearnerCreate(&c, &handle_));
 }
@@ -71,15 +85,40 @@ void B200TreeLearner::Init(const Dataset* train_data, bool is_constant_hessian) 
     miss[f] = static_cast<int32_t>(bm->missing_type());
     real[f] = train_data->RealFeatureIndex(f);
   }
-  // stored group values, row-major [num_data x num_groups] (what FeatureGroup::PushData wrote)
-  std::vector<uint8_t> bins(static_cast<size_t>(num_data_) * C);
-  for (int g = 0; g < C; ++g) {
+  // stored group values, row-major [num_data x num_groups] (what FeatureGroup::PushData wrote).  Row blocks are
+  // dealt to OpenMP threads; every thread owns one iterator per group, so a 256-row x C tile is written while it is
+  // cache-resident (one thread walking a whole column would touch a new cache line of the matrix per byte).
+  for (int g = 0; g < C; ++g)
     if (train_data->FeatureGroupNumBin(g) > 256) Log::Fatal("lgbm_b200: a feature group has more than 256 bins (use max_bin <= 255)");
-    std::unique_ptr<BinIterator> it(train_data->FeatureGroupIterator(g));
-    if (!it) Log::Fatal("lgbm_b200: cannot iterate feature group %d", g);
-    it->Reset(0);
-    for (int i = 0; i < num_data_; ++i) bins[static_cast<size_t>(i) * C + g] = static_cast<uint8_t>(it->RawGet(i));
+  std::vector<uint8_t> bins(static_cast<size_t>(num_data_) * C);
+  constexpr int kTileRows = 256;
+  const int num_tiles = (num_data_ + kTileRows - 1) / kTileRows;
+  bool iter_failed = false;
+#pragma omp parallel num_threads(OMP_NUM_THREADS())
+  {
+    std::vector<std::unique_ptr<BinIterator>> its(C);
+    for (int g = 0; g < C; ++g) {
+      its[g].reset(train_data->FeatureGroupIterator(g));
+      if (!its[g]) {
+#pragma omp critical
+        iter_failed = true;
+      } else {
+        its[g]->Reset(0);
+      }
+    }
+#pragma omp barrier
+    if (!iter_failed) {
+#pragma omp for schedule(static)
+      for (int tile = 0; tile < num_tiles; ++tile) {
+        const int r0 = tile * kTileRows, r1 = std::min(num_data_, r0 + kTileRows);
+        for (int g = 0; g < C; ++g) {
+          BinIterator* it = its[g].get();
+          for (int i = r0; i < r1; ++i) bins[static_cast<size_t>(i) * C + g] = static_cast<uint8_t>(it->RawGet(i));
+        }
+      }
+    }
   }
+  if (iter_failed) Log::Fatal("lgbm_b200: cannot iterate a feature group");
   LGBMB200_Layout lay;
   lay.num_data = num_data_; lay.num_columns = C; lay.num_features = num_features_;
   lay.feat_column = col.data(); lay.feat_lo = lo.data(); lay.feat_num_bin = nbin.data();
@@ -93,7 +132,12 @@ void B200TreeLearner::ResetTrainingData(const Dataset* train_data, bool is_const
   Init(train_data, is_constant_hessian);
 }
 
+void B200TreeLearner::ResetIsConstantHessian(bool is_constant_hessian) {
+  Check(LGBMB200_LearnerSetConstantHessian(handle_, is_constant_hessian ? 1 : 0));
+}
+
 void B200TreeLearner::ResetConfig(const Config* config) {
+  CheckSupported(config);
   config_ = config;
   LGBMB200_Config c = ToB200Config(config);
   Check(LGBMB200_LearnerResetConfig(handle_, &c));
@@ -108,8 +152,13 @@ Tree* B200TreeLearner::Train(const score_t* gradients, const score_t* hessians, 
   // ColSampler by tree (serial_tree_learner.cpp:297)
   col_sampler_.ResetByTree();
   const std::vector<int8_t>& used = col_sampler_.is_feature_used_bytree();
-  Check(LGBMB200_LearnerSetFeatureMask(handle_, config_->feature_fraction < 1.0
-                                                    ? reinterpret_cast<const uint8_t*>(used.data()) : nullptr));
+  if (config_->feature_fraction < 1.0) {
+    Check(LGBMB200_LearnerSetFeatureMask(handle_, reinterpret_cast<const uint8_t*>(used.data())));
+    mask_set_ = true;
+  } else if (mask_set_) {
+    Check(LGBMB200_LearnerSetFeatureMask(handle_, nullptr));
+    mask_set_ = false;
+  }
   const int NL = config_->num_leaves;
   std::vector<LGBMB200_Split> splits(NL);
   std::vector<double> leaf_value(NL), leaf_weight(NL);

@@ -26,7 +26,7 @@ class B200TreeLearner : public TreeLearner {
   ~B200TreeLearner() override;
 
   void Init(const Dataset* train_data, bool is_constant_hessian) override;
-  void ResetIsConstantHessian(bool) override {}
+  void ResetIsConstantHessian(bool is_constant_hessian) override;
   void ResetTrainingData(const Dataset* train_data, bool is_constant_hessian) override;
   void ResetConfig(const Config* config) override;
   void SetForcedSplit(const Json* forced_split_json) override;
@@ -42,6 +42,7 @@ class B200TreeLearner : public TreeLearner {
 
  private:
   static LGBMB200_Config ToB200Config(const Config* config);
+  static void CheckSupported(const Config* config);
   void Check(int ret) const;
 
   const Config* config_;
@@ -51,6 +52,7 @@ class B200TreeLearner : public TreeLearner {
   int num_data_ = 0;
   int num_features_ = 0;
   int last_num_leaves_ = 0;
+  bool mask_set_ = false;
 };
 
 }  // namespace LightGBM

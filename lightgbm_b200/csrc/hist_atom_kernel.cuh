@@ -45,7 +45,7 @@
 namespace b200 {
 
 constexpr int kARows = 32;                 // rows per stage
-constexpr int kAConsumers = 8;             // consumer warps (2 per SMSP)
+constexpr int kAConsumers = 16;            // consumer warps (4 per SMSP: the per-cell ALU chains are latency-bound with fewer)
 constexpr int kAProducers = 4;             // producer warps (1 per SMSP)
 constexpr int kAThreads = (kAConsumers + kAProducers) * 32;
 constexpr int kATable = kBinsPerColumn * 32 * 4;      // one [bin][column] int32 table = 32 KB
@@ -59,12 +59,11 @@ struct AShape {
   static constexpr int kTables = G * kCgBytes;                           // 160 KB : 128 KB
   static constexpr int kRowBytes = kColGroup * G;                        // bin bytes per staged row
   static constexpr int kStageBytes = kARows * kRowBytes + kARows * 8;    // + int2 (g, h) per row: 2304 : 1280
-  static constexpr int kStages = CH ? 24 : 48;                           // multiple of lcm(consumers, producers)
-  static constexpr int kSmem = kTables + kStages * kStageBytes + kStages * 2 * 8;
+  static constexpr int kStages = CH ? 28 : 48;                           // ring depth
+  static constexpr int kSmem = kTables + kStages * kStageBytes + kStages * 2 * 8 + 16;
 };
 static_assert(AShape<true>::kSmem <= 232448 && AShape<false>::kSmem <= 232448, "exceeds 227 KB of shared memory per CTA");
-static_assert(AShape<true>::kStages % kAConsumers == 0 && AShape<true>::kStages % kAProducers == 0, "ring/warp mapping");
-static_assert(AShape<false>::kStages % kAConsumers == 0 && AShape<false>::kStages % kAProducers == 0, "ring/warp mapping");
+static_assert(AShape<true>::kStages > kAConsumers && AShape<false>::kStages > kAConsumers, "ring must hold more stages than there are consumers");
 
 struct HistAArgs {
   const uint8_t* bins;            // [num_data x pitch] row-major stored values, pitch a multiple of 64
@@ -76,8 +75,16 @@ struct HistAArgs {
   const int32_t* idx1;
   const Leaf* leaves;
   const Ctl* ctl;
-  unsigned long long* pool;       // int64 fixed-point histogram pool [slot][column][256][2]
+  unsigned long long* pool;       // int64 fixed-point histogram pool [slot][column][256][2] (written by k_hist_reduce)
   int64_t slot_stride;            // int64 elements per slot
+  // Flush path: a CTA never adds into the pool itself.  It DUMPS its raw int32 tables (the shared-memory image of one
+  // column-group set) as one block into `scratch[set][blk]`, blk = atomicAdd(blk_count[epoch][set], 1), and
+  // k_hist_reduce sums the blocks of every set into the leaf's pool slot with plain loads and stores.  Integer sums:
+  // the order in which blocks were claimed does not matter.  (Round-2 measurement: flushing with RED.ADD.64 cost
+  // ~0.6 us of L2 atomic time per CTA, 22 % of the 4M x 1024 root pass and most of a 50K-row pass.)
+  unsigned char* scratch;         // [sets][blk_cap] blocks of AShape::kTables bytes
+  int32_t* blk_count;             // [num_leaves][sets] blocks claimed per (histogram pass of the tree, set); zeroed once per tree
+  int32_t blk_cap;
   int32_t num_colgroups;          // pitch / 32
   int32_t min_rows_per_cta;       // small leaves: do not spread the (column set x rows) work over more CTAs than this allows
   int32_t use_tma;                // 1: contiguous (root, un-bagged) stages are staged by TMA tile copies
@@ -130,53 +137,23 @@ __device__ __forceinline__ bool a_work_setup(const HistAArgs& a, AWork* w) {
   return w->v_hi > w->v_lo;
 }
 
-// Flush the CTA's tables of column group `cg` into the leaf's pool slot and zero them.  Called by the 256 consumer
-// threads between two consumer barriers.  Thread t: column t & 31, bin pairs (t >> 5) + 8 i.
+// Dump the CTA's tables (the whole shared-memory image of one column-group set) into a scratch block and zero them.
+// Called by all consumer threads between two consumer barriers: 16-byte LDS -> STG + STS(0), fully coalesced.
 template <bool CH>
-__device__ __forceinline__ void a_flush_zero(unsigned tb, unsigned long long* dst_cg, int t, long long hq_const) {
-  const int col = t & 31, pg = t >> 5;
-  unsigned long long* dst = dst_cg + static_cast<int64_t>(col) * (kBinsPerColumn * 2);
-  const unsigned cb = tb + col * 4;
+__device__ __forceinline__ void a_dump_zero(unsigned char* smem, unsigned char* block, int t) {
+  const uint4* src = reinterpret_cast<const uint4*>(smem);
+  uint4* dst = reinterpret_cast<uint4*>(block);
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
-    const int m = pg + 8 * i;               // bins 2m, 2m+1
-    int hi[2], lo[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const unsigned ca = cb + (2 * m + e) * 128;
-      hi[e] = static_cast<int>(lds_u32(ca)); lo[e] = static_cast<int>(lds_u32(ca + kATable));
-    }
-    long long hv[2];
-    if (CH) {
-      const unsigned wa = cb + 2 * kATable + m * 128;
-      const uint32_t cw = lds_u32(wa);
-      hv[0] = static_cast<long long>(cw & 0xffffu) * hq_const; hv[1] = static_cast<long long>(cw >> 16) * hq_const;
-      if (cw != 0u) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(0u) : "memory");
-    } else {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const unsigned ca = cb + (2 * m + e) * 128 + 2 * kATable;
-        const int hh = static_cast<int>(lds_u32(ca)), hl = static_cast<int>(lds_u32(ca + kATable));
-        hv[e] = static_cast<long long>(hh) * 65536 + static_cast<long long>(static_cast<uint32_t>(hl));
-        if (hh != 0 || hl != 0) {
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(ca), "r"(0u) : "memory");
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(ca + kATable), "r"(0u) : "memory");
-        }
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const long long gv = static_cast<long long>(hi[e]) * 65536 + static_cast<long long>(static_cast<uint32_t>(lo[e]));
-      if (hi[e] != 0 || lo[e] != 0) {
-        const unsigned ca = cb + (2 * m + e) * 128;
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ca), "r"(0u) : "memory");
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ca + kATable), "r"(0u) : "memory");
-      }
-      if (gv != 0) atomicAdd(dst + 2 * (2 * m + e), static_cast<unsigned long long>(gv));
-      if (hv[e] != 0) atomicAdd(dst + 2 * (2 * m + e) + 1, static_cast<unsigned long long>(hv[e]));
-    }
+  for (int i = t; i < AShape<CH>::kTables / 16; i += kAConsumers * 32) {
+    const uint4 v = src[i];
+    __stcg(dst + i, v);
+    if ((v.x | v.y | v.z | v.w) != 0u) const_cast<uint4*>(src)[i] = zero;
   }
 }
+
+// The epoch of a histogram pass within its tree: one row of blk_count per pass (explicit mode uses row 0).
+__device__ __forceinline__ int a_epoch(const HistAArgs& a) { return a.explicit_n >= 0 ? 0 : a.ctl->num_leaves - 1; }
 
 template <bool CH>
 __global__ void __launch_bounds__(kAThreads, 1) k_hist_a(const HistAArgs a, const __grid_constant__ CUtensorMap tmap) {
@@ -207,22 +184,21 @@ __global__ void __launch_bounds__(kAThreads, 1) k_hist_a(const HistAArgs a, cons
     // ------------------------------------------------------------------ producer warp: stage rows
     const int pw = warp - kAConsumers;
     const int pf = (ip != nullptr) ? a.l2_prefetch : 0;
-    long long seq = 0;
+    const int total = static_cast<int>(w.v_hi - w.v_lo);          // stages of this CTA, numbered seq = 0..total-1
+    int set = static_cast<int>((w.v_lo + pw) / w.spc);
+    int st = static_cast<int>((w.v_lo + pw) - static_cast<long long>(set) * w.spc);
+    int slot = pw % NS; unsigned par = 0;
     int pf_id = -1;                 // row id whose segment is prefetched into L2 on the next visit
-    for (long long v = w.v_lo; v < w.v_hi; ++v, ++seq) {
-      if (static_cast<int>(seq % kAProducers) != pw) continue;
-      const int set = static_cast<int>(v / w.spc), st = static_cast<int>(v - static_cast<long long>(set) * w.spc);
+    for (int seq = pw; seq < total; seq += kAProducers) {
       const int p0 = st * kARows;
       const int cnt = min(kARows, w.n - p0);
       const uint8_t* colbase = a.bins + static_cast<int64_t>(set) * S::kRowBytes;
-      const int slot = static_cast<int>(seq % NS);
-      const unsigned par = static_cast<unsigned>((seq / NS) & 1);
       unsigned char* sb = ring + slot * S::kStageBytes;
       if (pf > 0) {
         // walk the index list `pf` of this warp's stages ahead and pull every row's segment into L2 (fire-and-forget)
         if (pf_id >= 0) prefetch_l2(colbase + static_cast<int64_t>(pf_id) * a.pitch);
         const int pp = p0 + pf * kAProducers * kARows + lane;
-        pf_id = (pp < w.n && st + pf * kAProducers < w.spc) ? __ldg(ip + pp) : -1;
+        pf_id = (pp < w.n) ? __ldg(ip + pp) : -1;
       }
       if (a.use_tma && ip == nullptr && cnt == kARows) {
         // contiguous rows (root of an un-bagged tree): ONE 2-D TMA tile {32 G columns, 32 rows} of the row-major matrix
@@ -235,21 +211,26 @@ __global__ void __launch_bounds__(kAThreads, 1) k_hist_a(const HistAArgs a, cons
         } else {
           mbar_arrive(full + slot);
         }
-        continue;
-      }
-      // gathered: lane l holds the id of row p0 + l; each row is 2 G chunks of 16 bytes
-      int rid = -1;
-      if (lane < cnt) rid = ip ? __ldg(ip + p0 + lane) : p0 + lane;
-      mbar_wait_parked(empty + slot, par ^ 1);           // the consumer released this ring slot
+      } else {
+        // gathered: lane l holds the id of row p0 + l; each row is 2 G chunks of 16 bytes
+        int rid = -1;
+        if (lane < cnt) rid = ip ? __ldg(ip + p0 + lane) : p0 + lane;
+        mbar_wait_parked(empty + slot, par ^ 1);           // the consumer released this ring slot
 #pragma unroll
-      for (int i = 0; i < 2 * G; ++i) {
-        const int c = lane + 32 * i;
-        const int row = c / (2 * G), part = c % (2 * G);
-        const int r = __shfl_sync(0xffffffffu, rid, row);
-        if (r >= 0) cp_async16(sb + row * S::kRowBytes + part * 16, colbase + static_cast<int64_t>(r) * a.pitch + part * 16);
+        for (int i = 0; i < 2 * G; ++i) {
+          const int c = lane + 32 * i;
+          const int row = c / (2 * G), part = c % (2 * G);
+          const int r = __shfl_sync(0xffffffffu, rid, row);
+          if (r >= 0) cp_async16(sb + row * S::kRowBytes + part * 16, colbase + static_cast<int64_t>(r) * a.pitch + part * 16);
+        }
+        if (rid >= 0) cp_async8(sb + kARows * S::kRowBytes + lane * 8, w.gq_ord != nullptr ? w.gq_ord + p0 + lane : a.gq + rid);
+        mbar_arrive_on_cp_async(full + slot);
       }
-      if (rid >= 0) cp_async8(sb + kARows * S::kRowBytes + lane * 8, w.gq_ord != nullptr ? w.gq_ord + p0 + lane : a.gq + rid);
-      mbar_arrive_on_cp_async(full + slot);
+      // next stage of this warp: kAProducers further along the (set, stage) sequence and the ring
+      st += kAProducers;
+      while (st >= w.spc) { st -= w.spc; ++set; }
+      slot += kAProducers;
+      if (slot >= NS) { slot -= NS; par ^= 1; }
     }
     return;
   }
@@ -269,73 +250,124 @@ __global__ void __launch_bounds__(kAThreads, 1) k_hist_a(const HistAArgs a, cons
     sel[k] = 0x4440u | static_cast<unsigned>(kk);
     cell[k] = tb0 + static_cast<unsigned>(j % G) * S::kCgBytes + (4u * q + kk) * 4u;
   }
-  const long long hq_const = CH ? a.ctl->h_const_q : 0;
-  const int t = threadIdx.x;        // 0..255 among the consumers
+  const int sets = a.num_colgroups / G, epoch = a_epoch(a);
+  volatile int* s_blk = reinterpret_cast<volatile int*>(empty + NS);      // 4 bytes behind the barriers
+  const int t = threadIdx.x;        // consumers are warps 0..kAConsumers-1
 
-  long long seq = 0;
-  long long v = w.v_lo;
-  while (v < w.v_hi) {
-    const int set = static_cast<int>(v / w.spc);
-    const int s0 = static_cast<int>(v - static_cast<long long>(set) * w.spc);
-    const int s1 = static_cast<int>(min(static_cast<long long>(w.spc), s0 + (w.v_hi - v)));
-    unsigned long long* dst_set = a.pool + static_cast<int64_t>(w.slot) * a.slot_stride +
-                                  static_cast<int64_t>(set) * S::kRowBytes * (kBinsPerColumn * 2);
-    int rows_acc = 0;
-    for (int st = s0; st < s1; ++st, ++seq) {
-      if (static_cast<int>(seq % kAConsumers) == cw) {
-        const int slot = static_cast<int>(seq % NS);
-        const unsigned par = static_cast<unsigned>((seq / NS) & 1);
-        mbar_wait(full + slot, par);
-        const int cnt = min(kARows, w.n - st * kARows);
-        const unsigned sb = ring0 + slot * S::kStageBytes;
-        // The stage is a flat array of 32-byte segments: segment s = (row s / G, column group s % G).  One unit = the
-        // 128 contiguous bytes of four segments: lane (q, j) reads bytes 4q..4q+3 of segment 4u + j (one conflict-free
-        // LDS.32 per unit) and owns those four cells.
+  // One stage = 8 G units of 128 bytes (four 32-byte segments; segment s = row s / G, column group s % G): lane (q, j)
+  // reads bytes 4q..4q+3 of segment 4u + j with one conflict-free LDS.32 and owns those four cells.
+  auto accumulate = [&](unsigned sb, int cnt) {
 #pragma unroll 2
-        for (int u = 0; u < (kARows * G) / 4; ++u) {
-          const int seg = 4 * u + j;
-          const int row = seg / G;
-          const int2 rd = lds_i2(sb + kARows * S::kRowBytes + row * 8);
-          const uint32_t wv = lds_u32(sb + seg * kColGroup + q * 4);
-          const int ghi = rd.x >> 16, glo = rd.x & 0xffff;
-          const int hhi = rd.y >> 16, hlo = rd.y & 0xffff;
-          if (row < cnt) {
+    for (int u = 0; u < (kARows * G) / 4; ++u) {
+      const int seg = 4 * u + j;
+      const int row = seg / G;
+      const int2 rd = lds_i2(sb + kARows * S::kRowBytes + row * 8);
+      const uint32_t wv = lds_u32(sb + seg * kColGroup + q * 4);
+      const int ghi = rd.x >> 16, glo = rd.x & 0xffff;
+      const int hhi = rd.y >> 16, hlo = rd.y & 0xffff;
+      if (row < cnt) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t b = __byte_perm(wv, 0u, sel[k]);
-              const unsigned ca = cell[k] + (b << 7);
-              red_s32(ca, ghi);
-              red_s32(ca + kATable, glo);
-              if (CH) {
-                // 16-bit count field of bin b: word (b >> 1) of the count table, low or high half
-                unsigned cc, inc;
-                asm("{\n\t.reg .u32 t;\n\tand.b32 t, %2, 0xfe;\n\tmad.lo.u32 %0, t, 64, %3;\n\tand.b32 t, %2, 1;\n\tmad.lo.u32 %1, t, 0xffff, 1;\n\t}"
-                    : "=r"(cc), "=r"(inc) : "r"(b), "r"(cell[k]));
-                red_s32(cc + 2 * kATable, static_cast<int>(inc));
-              }
-              else { red_s32(ca + 2 * kATable, hhi); red_s32(ca + 3 * kATable, hlo); }
-            }
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t b = __byte_perm(wv, 0u, sel[k]);
+          const unsigned ca = cell[k] + (b << 7);
+          red_s32(ca, ghi);
+          red_s32(ca + kATable, glo);
+          if (CH) {
+            // 16-bit count field of bin b: word (b >> 1) of the count table, low or high half
+            unsigned cc, inc;
+            asm("{\n\t.reg .u32 t;\n\tand.b32 t, %2, 0xfe;\n\tmad.lo.u32 %0, t, 64, %3;\n\tand.b32 t, %2, 1;\n\tmad.lo.u32 %1, t, 0xffff, 1;\n\t}"
+                : "=r"(cc), "=r"(inc) : "r"(b), "r"(cell[k]));
+            red_s32(cc + 2 * kATable, static_cast<int>(inc));
+          } else {
+            red_s32(ca + 2 * kATable, hhi); red_s32(ca + 3 * kATable, hlo);
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + slot);
-      }
-      rows_acc += kARows;
-      if (rows_acc >= kAFlushRows && st + 1 < s1) {
-        consumer_bar_sync_a();
-#pragma unroll
-        for (int gs = 0; gs < G; ++gs)
-          a_flush_zero<CH>(tb0 + gs * S::kCgBytes, dst_set + static_cast<int64_t>(gs) * kColGroup * (kBinsPerColumn * 2), t, hq_const);
-        consumer_bar_sync_a();
-        rows_acc = 0;
       }
     }
+  };
+
+  // The CTA's stages are numbered seq = 0..total-1 along (set, stage); consumer warp cw takes seq = cw, cw + 16, ...
+  // The sequence is cut into segments at set boundaries and every kAFlushRows rows; after each segment all consumer
+  // warps meet, flush the tables into the leaf's pool slot and zero them.
+  const int total = static_cast<int>(w.v_hi - w.v_lo);
+  int my_seq = cw, slot = cw % NS; unsigned par = 0;
+  int set = static_cast<int>(w.v_lo / w.spc);
+  int st0 = static_cast<int>(w.v_lo - static_cast<long long>(set) * w.spc);      // first stage of the current segment
+  int seq0 = 0;
+  while (seq0 < total) {
+    const int len = min(min(w.spc - st0, total - seq0), kAFlushRows / kARows);
+    const int seq1 = seq0 + len;
+    for (; my_seq < seq1; my_seq += kAConsumers) {
+      const int st = st0 + (my_seq - seq0);
+      mbar_wait(full + slot, par);
+      accumulate(ring0 + slot * S::kStageBytes, min(kARows, w.n - st * kARows));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + slot);
+      slot += kAConsumers;
+      if (slot >= NS) { slot -= NS; par ^= 1; }
+    }
+    // all consumer warps are done with the segment: claim a scratch block of this set, dump the tables, zero them
+    if (t == 0) *s_blk = atomicAdd(a.blk_count + epoch * sets + set, 1);
     consumer_bar_sync_a();
-#pragma unroll
-    for (int gs = 0; gs < G; ++gs)
-      a_flush_zero<CH>(tb0 + gs * S::kCgBytes, dst_set + static_cast<int64_t>(gs) * kColGroup * (kBinsPerColumn * 2), t, hq_const);
+    {
+      const int blk = *s_blk;
+      if (blk < a.blk_cap) a_dump_zero<CH>(smem, a.scratch + (static_cast<int64_t>(set) * a.blk_cap + blk) * S::kTables, t);
+    }
     consumer_bar_sync_a();
-    v += (s1 - s0);
+    seq0 = seq1; st0 += len;
+    if (st0 >= w.spc) { st0 = 0; ++set; }
+  }
+}
+
+// Sum the scratch blocks of every column-group set into the leaf's pool slot (plain stores: the slot needs no memset).
+// CH: thread -> (set, column group gs, bin pair m, column); per block it reads hi/lo of bins 2m, 2m+1 and their count
+// word.  General: thread -> (set, bin, column); hi/lo of the gradient and of the hessian.
+template <bool CH>
+__global__ void __launch_bounds__(256) k_hist_reduce(const HistAArgs a) {
+  using S = AShape<CH>;
+  constexpr int G = S::G;
+  pdl_enter();
+  int slot;
+  if (a.explicit_n >= 0) slot = a.explicit_slot;
+  else {
+    const Ctl* c = a.ctl;
+    if (!c->cur_valid || !c->do_find) return;
+    slot = a.leaves[c->smaller].slot;        // a rank holding no row of the leaf (row-shard) claims no block: zeros are written
+  }
+  const int sets = a.num_colgroups / G, epoch = a_epoch(a);
+  constexpr int kPerSet = CH ? G * 128 * 32 : kBinsPerColumn * 32;        // threads per set
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int set = idx / kPerSet;
+  if (set >= sets) return;
+  const int r = idx % kPerSet;
+  const int nblk = min(a.blk_count[epoch * sets + set], a.blk_cap);
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(a.scratch + static_cast<int64_t>(set) * a.blk_cap * S::kTables);
+  constexpr int kBlkWords = S::kTables / 4, kTabWords = kATable / 4;
+  unsigned long long* dst_slot = a.pool + static_cast<int64_t>(slot) * a.slot_stride;
+  if (CH) {
+    const int gs = r / 4096, m = (r % 4096) / 32, col = r % 32;
+    const uint32_t* p = base + gs * (S::kCgBytes / 4) + (2 * m) * 32 + col;
+    long long g0 = 0, g1 = 0; long long c0 = 0, c1 = 0;
+    for (int b = 0; b < nblk; ++b, p += kBlkWords) {
+      const int h0 = static_cast<int>(__ldcg(p)), h1 = static_cast<int>(__ldcg(p + 32));
+      const uint32_t l0 = __ldcg(p + kTabWords), l1 = __ldcg(p + kTabWords + 32);
+      const uint32_t cw = __ldcg(p + 2 * kTabWords - m * 32);        // count word m of the [128][32] count table
+      g0 += static_cast<long long>(h0) * 65536 + l0; g1 += static_cast<long long>(h1) * 65536 + l1;
+      c0 += cw & 0xffffu; c1 += cw >> 16;
+    }
+    const long long hq = a.ctl->h_const_q;
+    longlong2* d = reinterpret_cast<longlong2*>(dst_slot + (static_cast<int64_t>(set * G + gs) * kColGroup + col) * (kBinsPerColumn * 2) + 4 * m);
+    d[0] = make_longlong2(g0, c0 * hq);
+    d[1] = make_longlong2(g1, c1 * hq);
+  } else {
+    const int bin = r / 32, col = r % 32;
+    const uint32_t* p = base + bin * 32 + col;
+    long long g = 0, h = 0;
+    for (int b = 0; b < nblk; ++b, p += kBlkWords) {
+      g += static_cast<long long>(static_cast<int>(__ldcg(p))) * 65536 + __ldcg(p + kTabWords);
+      h += static_cast<long long>(static_cast<int>(__ldcg(p + 2 * kTabWords))) * 65536 + __ldcg(p + 3 * kTabWords);
+    }
+    *reinterpret_cast<longlong2*>(dst_slot + (static_cast<int64_t>(set) * kColGroup + col) * (kBinsPerColumn * 2) + 2 * bin) = make_longlong2(g, h);
   }
 }
 

@@ -82,7 +82,7 @@ class Learner {
 
   void SetConfig(const LGBMB200_Config& cfg) {
     REQUIRE(cfg.num_leaves >= 2, "num_leaves must be >= 2");
-    const bool leaves_changed = cfg.num_leaves != cfg_.num_leaves;
+    const bool leaves_changed = cfg.num_leaves != cfg_.num_leaves || (cfg.use_quantized_grad != 0) != (params_.quant != 0);
     cfg_ = cfg;
     params_.num_leaves = cfg.num_leaves; params_.max_depth = cfg.max_depth; params_.min_data_in_leaf = cfg.min_data_in_leaf;
     params_.pad = 0;
@@ -177,13 +177,26 @@ class Learner {
 
   void SetFeatureMask(const uint8_t* mask) {
     REQUIRE(inited_, "Init first");
+    const bool had = have_feature_mask_;
     if (mask == nullptr) { have_feature_mask_ = false; }
     else {
       CUDA_CHECK(cudaMemcpyAsync(feature_used_.p, mask, F_, cudaMemcpyHostToDevice, stream_));
       CUDA_CHECK(cudaStreamSynchronize(stream_));
       have_feature_mask_ = true;
     }
-    InvalidateGraph();
+    // the mask buffer is stable: a new mask is just new bytes; the captured graph only changes when the scan switches
+    // between "no mask" and "mask"
+    if (had != have_feature_mask_) InvalidateGraph();
+  }
+
+  // TreeLearner::ResetIsConstantHessian (tree_learner.h:49): GBDT::ResetTrainingData may swap the objective
+  void SetConstantHessian(int is_constant_hessian) {
+    REQUIRE(inited_, "Init first");
+    const bool v = is_constant_hessian != 0;
+    if (v == const_hess_) return;
+    const_hess_ = v; hess_fill_valid_ = false;
+    params_.quant_const_hess = const_hess_ ? 1 : 0;
+    AllocTreeState();          // the flush scratch is sized for the histogram kernel in use; also drops the graph
   }
 
   void SetBagging(const int32_t* idx, int32_t n, int on_device) {
@@ -325,7 +338,11 @@ class Learner {
 
   void FetchLeafIndex() {
     REQUIRE(inited_ && last_num_leaves_ > 0, "Train first");
-    if (row_leaf_.n < static_cast<size_t>(N_)) { row_leaf_.alloc(N_); CUDA_CHECK(cudaMallocHost(&h_row_leaf_, sizeof(int32_t) * N_)); }
+    if (row_leaf_.n < static_cast<size_t>(N_)) {
+      row_leaf_.alloc(N_);
+      if (h_row_leaf_) cudaFreeHost(h_row_leaf_);
+      CUDA_CHECK(cudaMallocHost(&h_row_leaf_, sizeof(int32_t) * N_));
+    }
     if (bag_count_ >= 0) CUDA_CHECK(cudaMemsetAsync(row_leaf_.p, 0xFF, sizeof(int32_t) * N_, stream_));
     dim3 grid(std::max(1, std::min(num_sms_ * 4, (N_ + 255) / 256)), last_num_leaves_);
     k_leaf_index<int32_t><<<grid, 256, 0, stream_>>>(leaves_.p, idx0_.p, idx1_.p, row_leaf_.p);
@@ -393,6 +410,7 @@ class Learner {
       didx = idx1_.p; n = n_idx;
     }
     CUDA_CHECK(cudaMemsetAsync(pool_.p, 0, sizeof(long long) * slot_stride_, stream_));
+    CUDA_CHECK(cudaMemsetAsync(blk_count_.p, 0, sizeof(int32_t) * hist_sets_, stream_));
     HistAArgs ha = MakeHistArgs();
     ha.explicit_n = n; ha.explicit_slot = 0; ha.explicit_idx = didx;
     cudaEvent_t e0, e1;
@@ -573,6 +591,15 @@ class Learner {
     splittable_new_.alloc(2 * static_cast<size_t>(F_));
     block_best_.alloc(2 * static_cast<size_t>((F_ + kScanWarps - 1) / kScanWarps));
     leaf_value_dev_.alloc(NL);
+    // flush scratch of k_hist_a: per column-group set, one block per (CTA, flush interval) — see HistAArgs
+    {
+      const int G = ConstHessHist() ? AShape<true>::G : AShape<false>::G;
+      const size_t blk = ConstHessHist() ? AShape<true>::kTables : AShape<false>::kTables;
+      hist_sets_ = Cpad_ / kColGroup / G;
+      blk_cap_ = (N_ / kARows) / (kAFlushRows / kARows) + num_sms_ + 2;
+      scratch_.alloc(static_cast<size_t>(hist_sets_) * blk_cap_ * blk);
+      blk_count_.alloc(static_cast<size_t>(NL) * hist_sets_);
+    }
     renew_partial_.alloc(static_cast<size_t>(NL) * kRenewBlocks * 2); renew_out_.alloc(NL);
     if (h_renew_) cudaFreeHost(h_renew_);
     CUDA_CHECK(cudaMallocHost(&h_renew_, sizeof(double) * NL));
@@ -601,6 +628,7 @@ class Learner {
     ha.idx0 = idx0_.p; ha.idx1 = idx1_.p;
     ha.leaves = leaves_.p; ha.ctl = ctl_.p; ha.pool = reinterpret_cast<unsigned long long*>(pool_.p);
     ha.slot_stride = slot_stride_; ha.num_colgroups = Cpad_ / kColGroup;
+    ha.scratch = scratch_.p; ha.blk_count = blk_count_.p; ha.blk_cap = blk_cap_;
     static const int min_rows = std::getenv("LGBMB200_MIN_ROWS") ? std::atoi(std::getenv("LGBMB200_MIN_ROWS")) : 2048;
     ha.min_rows_per_cta = std::max(32, min_rows);
     ha.explicit_n = -1; ha.explicit_slot = 0; ha.explicit_idx = nullptr;
@@ -667,10 +695,18 @@ class Learner {
   // but keeps the general kernel (its pool holds raw integer sums)
   bool ConstHessHist() const { return const_hess_ && !params_.quant; }
 
+  // histogram of the current smaller leaf: accumulate (k_hist_a dumps raw table blocks) + reduce into the pool slot;
+  // the packed-cell kernel of quantized training still adds into a zeroed slot with RED.ADD.64
   void LaunchHist(const HistAArgs& ha, const HistQArgs& qa, bool chain = false) {
-    if (PackedQuantHist()) LaunchChain(chain, k_hist_q, dim3(num_sms_ * 2), dim3(kHistThreads), kQSmemBytes, qa, tmap_);
-    else if (ConstHessHist()) LaunchChain(chain, k_hist_a<true>, dim3(num_sms_), dim3(kAThreads), AShape<true>::kSmem, ha, tmap2_);
-    else LaunchChain(chain, k_hist_a<false>, dim3(num_sms_), dim3(kAThreads), AShape<false>::kSmem, ha, tmap_);
+    if (PackedQuantHist()) { LaunchChain(chain, k_hist_q, dim3(num_sms_ * 2), dim3(kHistThreads), kQSmemBytes, qa, tmap_); return; }
+    if (ConstHessHist()) {
+      LaunchChain(chain, k_hist_a<true>, dim3(num_sms_), dim3(kAThreads), AShape<true>::kSmem, ha, tmap2_);
+      LaunchChain(true, k_hist_reduce<true>, dim3((hist_sets_ * AShape<true>::G * 128 * 32 + 255) / 256), dim3(256), 0, ha);
+    } else {
+      LaunchChain(chain, k_hist_a<false>, dim3(num_sms_), dim3(kAThreads), AShape<false>::kSmem, ha, tmap_);
+      LaunchChain(true, k_hist_reduce<false>, dim3((hist_sets_ * kBinsPerColumn * 32 + 255) / 256), dim3(256), 0, ha);
+    }
+    ++launches_;
   }
 
   // Launch of a kernel of the per-split chain.  With LGBMB200_DEBUG bit 16 the launch carries a
@@ -730,8 +766,13 @@ class Learner {
     CUDA_CHECK(cudaMemsetAsync(splittable_.p, 1, static_cast<size_t>(NL) * F_, stream_));
     launches_ += 2;
     Stamp(kProfPrep);
-    // one memset for every histogram slot this tree can use (slot i is filled by iteration i)
-    CUDA_CHECK(cudaMemsetAsync(pool_.p, 0, sizeof(long long) * slot_stride_ * static_cast<size_t>(NL - 1), stream_));
+    if (PackedQuantHist()) {
+      // k_hist_q adds into its slot: one memset for every histogram slot this tree can use (slot i is filled by iteration i)
+      CUDA_CHECK(cudaMemsetAsync(pool_.p, 0, sizeof(long long) * slot_stride_ * static_cast<size_t>(NL - 1), stream_));
+    } else {
+      // k_hist_a / k_hist_reduce overwrite their slot; only the per-pass block counters start from zero
+      CUDA_CHECK(cudaMemsetAsync(blk_count_.p, 0, sizeof(int32_t) * static_cast<size_t>(NL) * hist_sets_, stream_));
+    }
     Stamp(kProfMemset);
     for (int it = 0; it < NL - 1 + 1; ++it) {
       // it == 0: root pass; it >= 1: apply split it-1, then find splits for its two children
@@ -852,6 +893,9 @@ class Learner {
   DevBuf<FeatMeta> gmeta_;
   DevBuf<uint8_t> bins_, binsT_, flags_, feature_used_, splittable_, splittable_new_;
   DevBuf<BlockBest> block_best_;
+  DevBuf<unsigned char> scratch_;       // k_hist_a flush blocks [sets][blk_cap][table image]
+  DevBuf<int32_t> blk_count_;
+  int hist_sets_ = 0, blk_cap_ = 0;
   DevBuf<int2> gq_, gqo0_, gqo1_;       // per-tree fixed-point (g,h) by row id; leaf-ordered copies parallel to idx0_/idx1_
   DevBuf<int32_t> ghqo0_, ghqo1_;
   static constexpr int kRenewBlocks = 64;
@@ -936,6 +980,12 @@ int LGBMB200_LearnerResetConfig(LGBMB200_LearnerHandle h, const LGBMB200_Config*
   API_BEGIN();
   if (!h || !config) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->SetConfig(*config);
+  API_END();
+}
+int LGBMB200_LearnerSetConstantHessian(LGBMB200_LearnerHandle h, int32_t is_constant_hessian) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->SetConstantHessian(is_constant_hessian);
   API_END();
 }
 int LGBMB200_LearnerSetFeatureMask(LGBMB200_LearnerHandle h, const uint8_t* feature_used) {

@@ -83,8 +83,8 @@ def test_c2_first_tree_matches_the_compiled_reference(built_lib):
     dsp = dict(max_bin=255, min_data_in_bin=1, enable_bundle="false", feature_pre_filter="false", verbosity=-1,
                num_threads=min(32, os.cpu_count() or 8))
     ds = refapi.RefDatasetStreamed(lambda lo, hi: bins[lo:hi].astype(np.float32), rows, cols, y, dsp, block_rows=262144)
-    bst = refapi.RefBooster(ds, dict(dsp, objective="regression", num_leaves=leaves, min_data_in_leaf=20, learning_rate=1.0,
-                                     boost_from_average="false", device_type="cpu", force_col_wise="true", deterministic="true"))
+    bst = refapi.RefBooster(ds, dict(dsp, objective="custom", num_leaves=leaves, min_data_in_leaf=20, learning_rate=1.0,
+                                     device_type="cpu", force_col_wise="true", deterministic="true"))
     g = (float(np.mean(y, dtype=np.float64)) - y).astype(np.float32)
     h = np.ones(rows, np.float32)
     bst.update_custom(g, h)
