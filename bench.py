@@ -11,9 +11,10 @@ One "step" = one boosting iteration (L2 gradients -> Train one tree -> score upd
   e2e   : the same iteration through the reference-facing C-ABI call with HOST buffers: grad/hess are
           copied host->device inside Train (from pinned memory) and the per-row leaf ids device->host
           inside AddPredictionToScore, every step, inside the timed region.
-  roofline : dominant kernel = k_hist; algorithmic bytes = n_leaf*(C*1 + 8 [+4 index]) + C*256*16 per
-          launch, divided by the CUDA-event time of the k_hist launches (measured live, profiling pass).
-  cpu_baseline : the UNMODIFIED reference (oracle/_ref/lib_lightgbm.so) on the host cores, bounded sample.
+  roofline : dominant kernel = k_hist_a (+ its k_hist_reduce); algorithmic bytes = n_leaf*(C*1 + 8 [+4 index]) +
+          C*256*16 per launch, divided by the CUDA-event time of those launches (measured live, profiling pass).
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref/lib_lightgbm.so) on the host cores, bounded two-sample estimate;
+          the measured full-workload numbers are the `--impl reference` / `--impl reference_cuda` arms.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -138,10 +139,14 @@ def peak_hbm():
     return 6650.0, "fallback"
 
 
-def ncu_traffic():
+def ncu_traffic(workload, world):
+    """DRAM bytes per k_hist_a launch from the committed ncu capture (profiles/hist_traffic.json) — only when that
+    capture was taken on THIS workload at THIS GPU count; otherwise null (a number copied across configs is wrong)."""
     p = os.path.join(ROOT, "profiles", "hist_traffic.json")
     if os.path.exists(p):
-        return json.load(open(p))
+        t = json.load(open(p))
+        if t.get("workload") == workload and int(t.get("n_gpus", 0)) == world and t.get("kernel") == "k_hist_a":
+            return t
     return None
 
 
@@ -452,8 +457,8 @@ def main():
     alg_bytes = hist_rows * (my_cols + 8) + (hist_rows - root_rows) * 4 + hist_launches * my_cols * 256 * 16
     achieved = alg_bytes / (hist_ms * 1e-3) / 1e9
     peak, peak_kind = peak_hbm()
-    tr = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_hist", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    tr = ncu_traffic(args.workload, world)
+    roofline = {"bound": "hbm", "kernel": "k_hist_a (+ k_hist_reduce)" if not args.quantized else "k_hist_q", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_kind": peak_kind,
                 "traffic": tr["dram_bytes_per_launch"] if tr else None,
                 "hist_share_of_step": (hist_ms / prof_steps) / ms_per_step,
@@ -492,7 +497,7 @@ def main():
     line = {"metric": metric, "value": value, "unit": "iters/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": ("int8 gradients -> packed int16:int16 histogram cells -> int64 pool, f64 gain scan" if args.quantized else
-                      "fp32 partial sums -> int64 fixed-point histograms, f64 gain scan"), "data": "synthetic",
+                      "30-bit fixed-point (g,h) per tree -> exact int32 hi/lo shared-memory atomics -> int64 histograms, f64 gain scan"), "data": "synthetic",
             "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "wall_ms_per_step": wall * 1e3 / args.steps, "final_train_l2": final_l2,
             "first_timed_tree": tree_signature(first_tree)}
