@@ -33,13 +33,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "boosting iters/sec, 10M x 1K synthetic, 255 bins, 127 leaves"
+# BASELINE.json configs.  kind: how the feature values are drawn; shard: how N > 1 GPUs split the work.
 WORKLOADS = {
-    "C3": dict(rows=10_000_000, cols=1024, leaves=127, seed=44),
-    "C2": dict(rows=1_000_000, cols=256, leaves=63, seed=42),
+    "C3": dict(rows=10_000_000, cols=1024, leaves=127, seed=44, kind="dense", objective="regression", shard="features"),
+    "C2": dict(rows=1_000_000, cols=256, leaves=63, seed=42, kind="dense", objective="regression", shard="features"),
+    # 2048 sparse features, mutually exclusive inside blocks of 4 => EFB bundles them into 512 uint8 columns (<= 253 bins)
+    "C4": dict(rows=5_000_000, cols=2048, leaves=127, seed=45, kind="efb4", objective="binary", shard="features"),
+    # Higgs-shaped: 21 low-level + 7 derived features, GOSS (docs/Experiments.rst settings: 255 leaves), row-sharded
+    "C5": dict(rows=11_000_000, cols=28, leaves=255, seed=46, kind="higgs", objective="binary", shard="rows", goss=(0.2, 0.1)),
 }
-
-
 GEN_CHUNK = 65536
+EFB_P = 0.02           # P(feature != 0); features of one block of 4 are mutually exclusive
+EFB_VALUES = 63        # non-zero values 1..63 => 64 bins per feature, 1 + 4 * 63 = 253 stored values per bundle column
+
+
+def wl_columns(wl):
+    """stored uint8 columns of THIS repo's layout"""
+    return wl["cols"] // 4 if wl["kind"] == "efb4" else wl["cols"]
+
+
+def _chunk_jobs(rows, row_lo, row_hi, nblocks_lo, nblocks_hi):
+    return [(s, b) for s in range(row_lo, row_hi, GEN_CHUNK) for b in range(nblocks_lo, nblocks_hi)]
+
+
+def _run_jobs(work, jobs, threads):
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 8)) as ex:
+        list(ex.map(work, jobs))
 
 
 def gen_bins(rows, cols, seed, col_lo=0, col_hi=None, threads=None, row_lo=0, row_hi=None):
@@ -50,29 +70,138 @@ def gen_bins(rows, cols, seed, col_lo=0, col_hi=None, threads=None, row_lo=0, ro
     row_hi = rows if row_hi is None else min(rows, row_hi)
     assert row_lo % GEN_CHUNK == 0
     out = np.empty((row_hi - row_lo, col_hi - col_lo), dtype=np.uint8)
-    chunk, cblock = GEN_CHUNK, 128
-    jobs = [(s, b) for s in range(row_lo, row_hi, chunk) for b in range(col_lo // cblock, (col_hi + cblock - 1) // cblock)]
+    cblock = 128
 
     def work(job):
         s, b = job
-        e = min(rows, s + chunk)        # the chunk's extent in the FULL matrix fixes the stream length
+        e = min(rows, s + GEN_CHUNK)        # the chunk's extent in the FULL matrix fixes the stream length
         c0, c1 = b * cblock, min(cols, (b + 1) * cblock)
-        rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, b, s // chunk]))
+        rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, b, s // GEN_CHUNK]))
         blk = rng.integers(0, 255, (e - s, c1 - c0), dtype=np.uint8)
         lo, hi = max(c0, col_lo), min(c1, col_hi)
         e2 = min(e, row_hi)
         out[s - row_lo:e2 - row_lo, lo - col_lo:hi - col_lo] = blk[:e2 - s, lo - c0:hi - c0]
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 8)) as ex:
-        list(ex.map(work, jobs))
+    _run_jobs(work, _chunk_jobs(rows, row_lo, row_hi, col_lo // cblock, (col_hi + cblock - 1) // cblock), threads)
     return out
 
 
+def gen_efb4(rows, cols, seed, bundle_lo=0, bundle_hi=None, threads=None, row_lo=0, row_hi=None, raw=False):
+    """C4: `cols` sparse features in exclusive blocks of 4.  Per (row, block): with probability 1 - (1 - p)^4 exactly one of
+    the four features is non-zero, uniform in 1..63.  Returns either the BUNDLED uint8 columns [rows, bundles] exactly as
+    the reference's EFB stores such a block (feature_group.h:253-267: 0 = all four at their most frequent bin 0, else
+    1 + 63 * j + (v - 1) for feature j with value v => bin v), or (raw=True) the raw feature values [rows, 4 * bundles]."""
+    nb_total = cols // 4
+    bundle_hi = nb_total if bundle_hi is None else bundle_hi
+    row_hi = rows if row_hi is None else min(rows, row_hi)
+    assert row_lo % GEN_CHUNK == 0
+    nb = bundle_hi - bundle_lo
+    out = np.zeros((row_hi - row_lo, nb * (4 if raw else 1)), dtype=np.uint8)
+    bblock = 32                                   # bundles per Philox stream
+    p_any = 1.0 - (1.0 - EFB_P) ** 4
+
+    def work(job):
+        s, b = job
+        e = min(rows, s + GEN_CHUNK)
+        b0, b1 = b * bblock, min(nb_total, (b + 1) * bblock)
+        rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 1, b, s // GEN_CHUNK]))
+        act = rng.random((e - s, b1 - b0), dtype=np.float32) < p_any
+        j = rng.integers(0, 4, (e - s, b1 - b0), dtype=np.uint8)
+        v = rng.integers(1, EFB_VALUES + 1, (e - s, b1 - b0), dtype=np.uint8)
+        lo, hi = max(b0, bundle_lo), min(b1, bundle_hi)
+        e2 = min(e, row_hi)
+        act, j, v = act[:e2 - s, lo - b0:hi - b0], j[:e2 - s, lo - b0:hi - b0], v[:e2 - s, lo - b0:hi - b0]
+        if raw:
+            r, c = np.nonzero(act)
+            out[s - row_lo + r, 4 * (lo - bundle_lo + c) + j[r, c]] = v[r, c]
+        else:
+            out[s - row_lo:e2 - row_lo, lo - bundle_lo:hi - bundle_lo] = np.where(act, 1 + EFB_VALUES * j + (v - 1), 0).astype(np.uint8)
+    _run_jobs(work, _chunk_jobs(rows, row_lo, row_hi, bundle_lo // bblock, (bundle_hi + bblock - 1) // bblock), threads)
+    return out
+
+
+def gen_higgs(rows, seed, threads=None, row_lo=0, row_hi=None):
+    """C5: 28 columns — 21 "low-level" features uniform in 0..254 and 7 "high-level" ones = quantised means of three
+    low-level features."""
+    row_hi = rows if row_hi is None else min(rows, row_hi)
+    assert row_lo % GEN_CHUNK == 0
+    out = np.empty((row_hi - row_lo, 28), dtype=np.uint8)
+
+    def work(job):
+        s, _ = job
+        e = min(rows, s + GEN_CHUNK)
+        rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 2, 0, s // GEN_CHUNK]))
+        low = rng.integers(0, 255, (e - s, 21), dtype=np.uint8)
+        hi7 = np.stack([(low[:, 3 * k].astype(np.uint16) + low[:, 3 * k + 1] + low[:, 3 * k + 2]) // 3 for k in range(7)], axis=1)
+        blk = np.concatenate([low, hi7.astype(np.uint8)], axis=1)
+        e2 = min(e, row_hi)
+        out[s - row_lo:e2 - row_lo] = blk[:e2 - s]
+    _run_jobs(work, _chunk_jobs(rows, row_lo, row_hi, 0, 1), threads)
+    return out
+
+
+def gen_columns(wl, col_lo=0, col_hi=None, threads=None, row_lo=0, row_hi=None):
+    """this repo's stored columns [rows, col_hi - col_lo] for any workload"""
+    if wl["kind"] == "dense":
+        return gen_bins(wl["rows"], wl["cols"], wl["seed"], col_lo, col_hi, threads, row_lo, row_hi)
+    if wl["kind"] == "efb4":
+        return gen_efb4(wl["rows"], wl["cols"], wl["seed"], col_lo, col_hi, threads, row_lo, row_hi)
+    b = gen_higgs(wl["rows"], wl["seed"], threads, row_lo, row_hi)
+    return np.ascontiguousarray(b[:, col_lo:col_hi]) if (col_lo, col_hi) not in ((0, None), (0, 28)) else b
+
+
+def gen_raw_float(wl, threads=None, row_lo=0, row_hi=None):
+    """the raw feature matrix [rows, cols] float32 the reference arms are fed (its own binning / bundling reproduces the
+    stored columns above)"""
+    if wl["kind"] == "efb4":
+        b = gen_efb4(wl["rows"], wl["cols"], wl["seed"], 0, None, threads, row_lo, row_hi, raw=True)
+    else:
+        b = gen_columns(wl, 0, None, threads, row_lo, row_hi)
+    out = np.empty(b.shape, dtype=np.float32)
+    nt = max(1, min(16, threads or 8))
+    per = (len(b) + nt - 1) // nt
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=nt) as ex:       # numpy casts release the GIL
+        list(ex.map(lambda t: np.copyto(out[t * per:(t + 1) * per], b[t * per:(t + 1) * per], casting="unsafe"), range(nt)))
+    return out
+
+
+LABEL_COLS = {"dense": 32, "efb4": 16, "higgs": 28}      # stored columns the label depends on
+
+
+def gen_label_wl(wl, label_cols, row_lo=0):
+    """Labels of rows row_lo .. row_lo + len(label_cols) from the first LABEL_COLS stored columns.  regression: linear +
+    N(0, 0.5); binary: Bernoulli(sigmoid(linear)).  The per-row random stream is drawn for the whole workload and sliced."""
+    rng = np.random.Generator(np.random.Philox(key=wl["seed"] + 1000))
+    n = len(label_cols)
+    if wl["kind"] == "dense":
+        w = rng.normal(size=32)
+        noise = rng.normal(size=wl["rows"]).astype(np.float32)[row_lo:row_lo + n]
+        return ((label_cols.astype(np.float32) / 127.0 - 1.0) @ w.astype(np.float32) + 0.5 * noise).astype(np.float32)
+    w = rng.normal(size=label_cols.shape[1])
+    u = rng.random(wl["rows"], dtype=np.float32)[row_lo:row_lo + n]
+    if wl["kind"] == "efb4":
+        x = (label_cols > 0).astype(np.float32) * (((label_cols.astype(np.int32) - 1) % EFB_VALUES + 1) / float(EFB_VALUES))   # value / 63 of the active feature
+        logit = 3.0 * (x @ w.astype(np.float32))
+    else:
+        logit = (label_cols.astype(np.float32) / 127.0 - 1.0) @ (0.5 * w).astype(np.float32)
+    return (u < 1.0 / (1.0 + np.exp(-logit))).astype(np.float32)
+
+
 def gen_label(rows, cols, seed, bins_first32):
-    rng = np.random.Generator(np.random.Philox(key=seed + 1000))
-    w = rng.normal(size=32)
-    noise = rng.normal(size=rows).astype(np.float32)
-    return ((bins_first32.astype(np.float32) / 127.0 - 1.0) @ w.astype(np.float32) + 0.5 * noise).astype(np.float32)
+    return gen_label_wl(dict(kind="dense", rows=rows, cols=cols, seed=seed), bins_first32)
+
+
+def make_layout(lgb, wl, columns, col_lo=0):
+    """Layout of a column slice [col_lo, col_lo + columns.shape[1]) of the workload"""
+    nc = columns.shape[1]
+    if wl["kind"] != "efb4":
+        lay = lgb.Layout.identity(columns)
+        lay.feat_real_index = np.arange(col_lo, col_lo + nc, dtype=np.int32)
+        return lay
+    f = np.arange(4 * nc, dtype=np.int32)
+    z = np.zeros(4 * nc, np.int32)
+    return lgb.Layout(np.ascontiguousarray(columns, dtype=np.uint8), f // 4, (1 + EFB_VALUES * (f % 4)).astype(np.int32),
+                      np.full(4 * nc, EFB_VALUES + 1, np.int32), z.copy(), z.copy(), z.copy(), (4 * col_lo + f).astype(np.int32))
 
 
 class ClockSampler:
@@ -161,44 +290,34 @@ REF_BLOCK_ROWS = 4 * GEN_CHUNK
 
 
 def _ref_params(wl, threads, device="cpu", quantized=0):
-    dsp = dict(max_bin=255, min_data_in_bin=1, enable_bundle="false", feature_pre_filter="false", verbosity=-1,
-               num_threads=threads, device_type=device)
+    # Dataset parameters.  C4: the Dataset is CONSTRUCTED with the cuda rules (dense storage, bundles capped at 256 bins,
+    # dataset.cpp:119,141,357-372) for every arm, so that the CPU learner trains on the same bundled columns.
+    dsp = dict(max_bin=255, min_data_in_bin=1, enable_bundle="true" if wl["kind"] == "efb4" else "false", feature_pre_filter="false",
+               verbosity=-1, num_threads=threads, device_type="cuda" if wl["kind"] == "efb4" else device)
     if device == "cuda":
         dsp.update(gpu_device_id=0, num_gpu=1)
-    bp = dict(dsp, objective="regression", num_leaves=wl["leaves"], learning_rate=0.1, min_data_in_leaf=20)
+    bp = dict(dsp, objective=wl["objective"], num_leaves=wl["leaves"], learning_rate=0.1, min_data_in_leaf=20, device_type=device)
+    if wl.get("goss"):
+        bp.update(data_sample_strategy="goss", top_rate=wl["goss"][0], other_rate=wl["goss"][1])
     if quantized:
         bp.update(use_quantized_grad="true", num_grad_quant_bins=quantized)
     return dsp, bp
 
 
 def _ref_dataset(refapi, wl, rows, dsp, threads):
-    """Reference Dataset over rows [0, rows) of the workload, streamed in REF_BLOCK_ROWS blocks."""
-    first32 = np.empty((rows, 32), dtype=np.uint8)
+    """Reference Dataset over rows [0, rows) of the workload, streamed in REF_BLOCK_ROWS blocks of raw float features."""
+    lc = LABEL_COLS[wl["kind"]]
+    label_cols = np.empty((rows, lc), dtype=np.uint8)
 
     def block(lo, hi):
-        b = gen_bins(wl["rows"], wl["cols"], wl["seed"], threads=min(32, threads), row_lo=lo, row_hi=hi)
-        first32[lo:hi] = b[:, :32]
-        out = np.empty(b.shape, dtype=np.float32)
-        nt = max(1, min(16, threads))
-        per = (len(b) + nt - 1) // nt
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=nt) as ex:       # numpy casts release the GIL
-            list(ex.map(lambda t: np.copyto(out[t * per:(t + 1) * per], b[t * per:(t + 1) * per], casting="unsafe"), range(nt)))
-        return out
+        label_cols[lo:hi] = gen_columns(wl, 0, lc, threads=min(32, threads), row_lo=lo, row_hi=hi)
+        return gen_raw_float(wl, threads=min(32, threads), row_lo=lo, row_hi=hi)
     t0 = time.time()
-    ds = refapi.RefDatasetStreamed(block, rows, wl["cols"], None, dsp, block_rows=REF_BLOCK_ROWS)
-    y = gen_label(wl["rows"], wl["cols"], wl["seed"], first32) if rows == wl["rows"] else \
-        gen_label_rows(wl, first32)
-    ds.set_label(y)
+    ds = refapi.RefDatasetStreamed(block, rows, wl["cols"], None, dsp, block_rows=REF_BLOCK_ROWS,
+                                   sample_rows=REF_BLOCK_ROWS if wl["kind"] == "efb4" else 65_536,
+                                   sampled_columns=wl["kind"] == "efb4")       # EFB needs the real training-set construction
+    ds.set_label(gen_label_wl(wl, label_cols))
     return ds, time.time() - t0
-
-
-def gen_label_rows(wl, first32):
-    """Labels of the first len(first32) rows of the workload (the noise stream is row-ordered, so a prefix is a prefix)."""
-    rng = np.random.Generator(np.random.Philox(key=wl["seed"] + 1000))
-    w = rng.normal(size=32)
-    noise = rng.normal(size=wl["rows"]).astype(np.float32)[:len(first32)]
-    return ((first32.astype(np.float32) / 127.0 - 1.0) @ w.astype(np.float32) + 0.5 * noise).astype(np.float32)
 
 
 def _time_iters(bst, warmup, steps):
@@ -246,15 +365,19 @@ def host_mem_available():
     return avail
 
 
-def run_reference(args, wl, rank, world, device="cpu"):
-    """Full-workload reference arm; returns None on ranks != 0."""
+def run_reference(args, wl, rank, world, device="cpu", dropin=False):
+    """Full-workload arm through the LGBM_* C API: the reference CPU learner, the reference CUDA learner, or (dropin)
+    THIS repo's learner behind the unmodified reference host code (integration/_build/lib_lightgbm.so, device_type=cuda:
+    LGBM_BoosterUpdateOneIter -> GBDT::TrainOneIter -> B200TreeLearner -> liblgbm_b200.so).  None on ranks != 0."""
     if rank != 0:
         return None
-    if device == "cuda":
+    if dropin:
+        os.environ["LGBM_REF_LIB"] = os.path.join(ROOT, "integration", "_build", "lib_lightgbm.so")
+    elif device == "cuda":
         os.environ["LGBM_REF_LIB"] = os.path.join(ROOT, "oracle", "_ref", "cuda", "lib_lightgbm.so")
     from oracle import refapi
     if not os.path.exists(refapi.REF_LIB):
-        return {"unavailable": f"{refapi.REF_LIB} not built (oracle/Makefile.ref{'cuda' if device == 'cuda' else ''})"}
+        return {"unavailable": f"{refapi.REF_LIB} not built (oracle/Makefile.ref{'cuda' if device == 'cuda' else ''}, integration/Makefile)"}
     cores = effective_cores()
     rows = wl["rows"]
     need = 3.2 * rows * wl["cols"] + (2 << 30)      # column-wise + row-wise bin copies + one fp32 block, bytes
@@ -273,7 +396,9 @@ def run_reference(args, wl, rank, world, device="cpu"):
     trees = bst.trees()
     bst.free()
     ds.free()
-    kind = ("the reference's own CUDA learner (src/treelearner/cuda, -DUSE_CUDA, sm_100), boosting on the GPU" if device == "cuda"
+    kind = ("this repo's learner behind the reference's LGBM_* C API (integration/_build/lib_lightgbm.so, device_type=cuda; "
+            "host objective and score, gradients H2D and leaf ids D2H every iteration)" if dropin else
+            "the reference's own CUDA learner (src/treelearner/cuda, -DUSE_CUDA, sm_100), boosting on the GPU" if device == "cuda"
             else "the reference's OpenMP CPU learner, col/row-wise chosen by its own auto-timing")
     sample = f"all {rows} rows x {wl['cols']} cols, {wl['leaves']} leaves, {kind}, {threads} host threads; " \
              f"dataset construction {t_ds:.1f}s excluded{note}"
@@ -316,12 +441,13 @@ def run_reference_fit(args, wl):
     ds2, t_ds = _ref_dataset(refapi, wl, s2, dsp, cores)
     threads = _calibrate_threads(refapi, ds2, wl, cores, "cpu", args.quantized)
     dsp, bp = _ref_params(wl, threads, "cpu", args.quantized)
+    warm = 10 if wl.get("goss") else 1            # GOSS starts sampling after 1 / learning_rate iterations (goss.hpp:33)
     b2 = refapi.RefBooster(ds2, bp)
-    t2 = _time_iters(b2, 1, 3)
+    t2 = _time_iters(b2, warm, 3)
     b2.free(); ds2.free()
     ds1, _ = _ref_dataset(refapi, wl, s1, dsp, cores)
     b1 = refapi.RefBooster(ds1, bp)
-    t1 = _time_iters(b1, 1, 3)
+    t1 = _time_iters(b1, warm, 3)
     b1.free(); ds1.free()
     slope = max((t2 - t1) / (s2 - s1), 0.0)
     icpt = max(t1 - slope * s1, 0.0)
@@ -337,7 +463,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference_cuda"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference_cuda", "dropin"])
     ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "C3"), choices=list(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override rows (debug only; makes the number INVALID)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -350,20 +476,29 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     rank, world, local = dist_env()
     wl = dict(WORKLOADS[args.workload])
+    if wl.get("goss"):
+        args.warmup = max(args.warmup, 10)       # both arms: GOSS samples only after 1 / learning_rate = 10 iterations
     if args.rows:
         wl["rows"] = args.rows
-    metric = METRIC if args.workload == "C3" else f"boosting iters/sec, {wl['rows']} x {wl['cols']} synthetic, 255 bins, {wl['leaves']} leaves"
-    config = {"workload": f"{args.workload}: {wl['rows']} rows x {wl['cols']} dense features, 255 bins, {wl['leaves']} leaves, "
-                          f"L2 regression, min_data_in_leaf=20, lr=0.1" +
+    metric = METRIC if args.workload == "C3" else f"boosting iters/sec, {wl['rows']} x {wl['cols']} synthetic ({wl['kind']}), {wl['leaves']} leaves"
+    kind_txt = {"dense": f"{wl['cols']} dense features, 255 bins",
+                "efb4": f"{wl['cols']} sparse features (p=0.02, exclusive in blocks of 4 -> {wl['cols'] // 4} EFB-bundled columns, <= 253 bins)",
+                "higgs": f"{wl['cols']} Higgs-shaped features (21 low-level + 7 derived), 255 bins"}[wl["kind"]]
+    obj_txt = "L2 regression" if wl["objective"] == "regression" else "binary logloss"
+    if wl.get("goss"):
+        obj_txt += f", GOSS top_rate={wl['goss'][0]} other_rate={wl['goss'][1]}"
+    config = {"workload": f"{args.workload}: {wl['rows']} rows x {kind_txt}, {wl['leaves']} leaves, "
+                          f"{obj_txt}, min_data_in_leaf=20, lr=0.1" +
                           (f", use_quantized_grad num_grad_quant_bins={args.quantized} (NOT the BASELINE configuration)" if args.quantized else ""),
-              "parallelism": (f"feature-shard x{world}" + ("" if args.no_replicate else ", partition columns replicated on every GPU"))
-              if world > 1 else "single GPU",
-              "l2_flush": "inputs larger than L2 (bin matrix 10.24 GB >> 126 MB)" if wl["rows"] * wl["cols"] > 2e9 else
-                          "bin matrix larger than L2 per GPU"}
+              "parallelism": ((f"row-shard x{world}" if wl["shard"] == "rows" else
+                               f"feature-shard x{world}" + ("" if args.no_replicate else ", partition columns replicated on every GPU"))
+                              if world > 1 else "single GPU"),
+              "l2_flush": (f"inputs larger than L2 (bin matrix {wl['rows'] * wl_columns(wl) / 1e9:.2f} GB >> 126 MB)"
+                           if wl["rows"] * wl_columns(wl) > 2e8 else "bin matrix smaller than L2: L2 flushed by the per-tree 8 B/row gradient pass only")}
 
-    if args.impl in ("reference", "reference_cuda"):
-        dev = "cuda" if args.impl == "reference_cuda" else "cpu"
-        r = run_reference(args, wl, rank, world, dev)
+    if args.impl in ("reference", "reference_cuda", "dropin"):
+        dev = "cpu" if args.impl == "reference" else "cuda"
+        r = run_reference(args, wl, rank, world, dev, dropin=args.impl == "dropin")
         if rank == 0:
             if "unavailable" in r:
                 print(json.dumps({"impl": args.impl, "unavailable": r["unavailable"]}), flush=True)
@@ -373,11 +508,15 @@ def main():
             line = {"metric": metric, "impl": args.impl, "value": r["value"], "unit": "iters/sec", "n_gpus": args.gpus,
                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                     "scaling": "strong", "vs_baseline": None,
-                    "dtype": "f64 histograms (fp32 grad/hess)" if dev == "cpu" else "fp32 shared-memory atomics -> f64 histograms (gpu_use_dp=false)",
+                    "dtype": ("f64 histograms (fp32 grad/hess)" if dev == "cpu" else
+                              "30-bit fixed-point (g,h) -> exact int32 shared-memory atomics -> int64 histograms" if args.impl == "dropin" else
+                              "fp32 shared-memory atomics -> f64 histograms (gpu_use_dp=false)"),
                     "data": "synthetic", "config": config,
                     "cpu_baseline": {"value": r["value"], "unit": "iters/sec", "cores": r["cores"], "kind": "reference",
                                      "sample": r["sample"]},
-                    "e2e": {"value": r["value"], "unit": "iters/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "e2e": {"value": r["value"], "unit": "iters/sec",
+                            "h2d_bytes_per_step": (wl["rows"] * 4 + 4) if args.impl == "dropin" else 0,
+                            "d2h_bytes_per_step": (wl["rows"] * (1 if wl["leaves"] <= 255 else 4) + 4096) if args.impl == "dropin" else 0},
                     "first_timed_tree": r["first_tree"]}
             print(json.dumps(line), flush=True)
         return
@@ -392,20 +531,35 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", rank=rank, world_size=world)
-    # feature-shard: every rank holds ALL rows x its column slice
-    lo, hi = D.shard_columns(cols, world)[rank]
     host_threads = max(4, (os.cpu_count() or 8) // max(world, 1))
-    bins = gen_bins(rows, cols, wl["seed"], lo, hi, threads=min(32, host_threads))
-    first32 = bins[:, :32] if lo == 0 and hi >= 32 else gen_bins(rows, cols, wl["seed"], 0, 32, threads=min(32, host_threads))
-    y = gen_label(rows, cols, wl["seed"], first32)
-    lay = lgb.Layout.identity(bins)
-    lay.feat_real_index = np.arange(lo, hi, dtype=np.int32)
+    ncols = wl_columns(wl)
+    lc = LABEL_COLS[wl["kind"]]
+    goss = wl.get("goss")
+    const_hess = wl["objective"] == "regression" and not goss          # RegressionL2loss::IsConstantHessian, GOSS rescales
     cfg = lgb.Config(num_leaves=leaves, min_data_in_leaf=20, gpu_device_id=local, use_cuda_graph=True,
                      use_quantized_grad=args.quantized > 0, num_grad_quant_bins=max(args.quantized, 2), stochastic_rounding=True)
-    L = D.make_sharded_learner(lay, cfg, rank, world, replicate_columns=not args.no_replicate,
-                               is_constant_hessian=True)      # unweighted L2: IsConstantHessian()
-    B = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=True, learner=L)
-    my_cols = hi - lo
+    if wl["shard"] == "rows" and world > 1:
+        # row-shard: every rank holds its row slice x ALL columns and the labels of those rows
+        r0, r1 = D.shard_rows(rows, world)[rank]
+        a0 = r0 // GEN_CHUNK * GEN_CHUNK
+        cols_arr = gen_columns(wl, threads=min(32, host_threads), row_lo=a0, row_hi=r1)[r0 - a0:]
+        y = gen_label_wl(wl, cols_arr[:, :lc], row_lo=r0)
+        lay = make_layout(lgb, wl, cols_arr)
+        L = D.make_row_sharded_learner(lay, cfg, rank, world)
+        my_cols, my_rows = ncols, r1 - r0
+    else:
+        # feature-shard (C2/C3/C4): every rank holds ALL rows x its column slice
+        lo, hi = D.shard_columns(ncols, world)[rank]
+        cols_arr = gen_columns(wl, lo, hi, threads=min(32, host_threads))
+        label_cols = cols_arr[:, :lc] if lo == 0 and hi >= lc else gen_columns(wl, 0, lc, threads=min(32, host_threads))
+        y = gen_label_wl(wl, label_cols)
+        lay = make_layout(lgb, wl, cols_arr, lo)
+        L = D.make_sharded_learner(lay, cfg, rank, world, replicate_columns=not args.no_replicate, is_constant_hessian=const_hess)
+        my_cols, my_rows = hi - lo, rows
+    bkw = dict(objective=wl["objective"])
+    if goss:
+        bkw.update(data_sample_strategy="goss", top_rate=goss[0], other_rate=goss[1])
+    B = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=True, learner=L, **bkw)
 
     def max_over_ranks(x):
         if dist is None:
@@ -440,7 +594,7 @@ def main():
     ms_per_step = ms_total / args.steps
     value = 1e3 / ms_per_step
     clocks = clk.summary()
-    final_l2 = B.l2()
+    final_loss = B.l2() if wl["objective"] == "regression" else B.logloss()      # local rows in row-shard mode
 
     # --- roofline of the dominant kernel (k_hist), measured live with CUDA events around every launch
     L.set_profiling(True)
@@ -449,11 +603,15 @@ def main():
     for _ in range(prof_steps):
         B.update()
     hist_ms, hist_rows, hist_launches = L.hist_stats()
+    hist_root_rows = sum(int(t.leaf_count.sum()) for t in B.trees[-prof_steps:])      # bag sizes of the profiled trees
     by_kind = {k: v / prof_steps for k, v in L.profile_by_kind().items()}
     L.set_profiling(False)
     # algorithmic bytes: per histogrammed row C bin bytes + 8 (grad,hess) + 4 (row index, not for the root),
     # per launch the C*256*16 B of the int64 pool slot it fills
-    root_rows = rows * prof_steps
+    root_rows = hist_root_rows if goss else my_rows * prof_steps
+    if wl["shard"] == "rows" and world > 1:       # split records carry GLOBAL counts; this rank built 1/world of those rows
+        hist_rows /= world
+        root_rows = root_rows / world if goss else root_rows
     alg_bytes = hist_rows * (my_cols + 8) + (hist_rows - root_rows) * 4 + hist_launches * my_cols * 256 * 16
     achieved = alg_bytes / (hist_ms * 1e-3) / 1e9
     peak, peak_kind = peak_hbm()
@@ -468,8 +626,8 @@ def main():
 
     # --- e2e: host buffers through the C-ABI, copies inside the timed region
     e2e = None
-    if not args.no_e2e:
-        H = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=False, learner=L, pinned=True)
+    if not args.no_e2e and not goss and not (wl["shard"] == "rows" and world > 1):
+        H = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=False, learner=L, pinned=True, objective=wl["objective"])
         for _ in range(args.warmup):
             H.update()
         barrier()
@@ -480,7 +638,7 @@ def main():
             H.update()
         barrier()
         dt = max_over_ranks((time.time() - t0) / args.steps)
-        e2e = {"value": 1.0 / dt, "unit": "iters/sec", "h2d_bytes_per_step": rows * 4 + 4, "d2h_bytes_per_step": rows * (1 if leaves <= 255 else 4) + 4096,
+        e2e = {"value": 1.0 / dt, "unit": "iters/sec", "h2d_bytes_per_step": rows * (4 if const_hess else 8) + 4, "d2h_bytes_per_step": rows * (1 if leaves <= 255 else 4) + 4096,
                "ms_per_step": dt * 1e3, "host_ms_per_step": {k: v / args.steps for k, v in H.host_ms.items()},
                "note": "host gradients (pinned, 4 B/row; the hessian is constant for L2 and only hessians[0] is read, as "
                        "in the reference) -> H2D inside Train; per-row leaf ids (1 B/row up to 255 leaves) D2H inside AddPredictionToScore; "
@@ -499,7 +657,8 @@ def main():
             "dtype": ("int8 gradients -> packed int16:int16 histogram cells -> int64 pool, f64 gain scan" if args.quantized else
                       "30-bit fixed-point (g,h) per tree -> exact int32 hi/lo shared-memory atomics -> int64 histograms, f64 gain scan"), "data": "synthetic",
             "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "wall_ms_per_step": wall * 1e3 / args.steps, "final_train_l2": final_l2,
+            "cpu_baseline": cpu, "wall_ms_per_step": wall * 1e3 / args.steps,
+            ("final_train_l2" if wl["objective"] == "regression" else "final_train_logloss"): final_loss,
             "first_timed_tree": tree_signature(first_tree)}
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -143,6 +143,24 @@ LGBMB200_EXPORT int LGBMB200_LearnerSetFeatureMask(LGBMB200_LearnerHandle h, con
 LGBMB200_EXPORT int LGBMB200_LearnerSetBaggingData(LGBMB200_LearnerHandle h, const int32_t* used_indices,
                                                    int32_t num_used, int32_t on_device);
 
+/* GOSSStrategy::Bagging (reference src/boosting/goss.hpp:30-77, :118-167) on the device: grad/hess are DEVICE arrays
+ * [num_data], modified in place (kept small-gradient rows are multiplied by (n - top_k) / other_k); the kept rows become
+ * the learner's bagging set exactly as if SetBaggingData had been called with their ascending indices.  One exact global
+ * threshold (the reference takes one per OpenMP chunk) and a counter-based uniform per (seed, iteration, row): which
+ * small-gradient rows are drawn is statistically, not bitwise, the reference's.  The caller applies the reference's
+ * "no sampling during the first 1/learning_rate iterations" rule (goss.hpp:33) and passes is_constant_hessian = 0 at
+ * Init (IsHessianChange(), goss.hpp:105). */
+LGBMB200_EXPORT int LGBMB200_LearnerGossSample(LGBMB200_LearnerHandle h, float* grad_dev, float* hess_dev, double top_rate,
+                                               double other_rate, int32_t seed, int32_t iteration, int32_t* out_bag_count);
+/* GBDT::UpdateScore with a bagging set (reference gbdt.cpp:505-530): the partition only holds the bagged rows, the
+ * out-of-bag rows are scored by predicting the tree on them.  This routes EVERY row of the training matrix through the
+ * last tree on the device (bin matrix + split records) and adds its leaf value to score_dev[row].  Single GPU or
+ * row-shard (every column present). */
+LGBMB200_EXPORT int LGBMB200_LearnerAddPredictionAllRows(LGBMB200_LearnerHandle h, const double* leaf_value, int32_t num_leaves,
+                                                         double* score_dev);
+/* the current bagging set (host copy; test / RenewTreeOutput hook) */
+LGBMB200_EXPORT int LGBMB200_LearnerGetBaggingData(LGBMB200_LearnerHandle h, int32_t* indices_host, int32_t num_indices);
+
 /* Tree* TreeLearner::Train(const score_t* gradients, const score_t* hessians, bool is_first_tree) —
  * reference tree_learner.h:71; serial_tree_learner.cpp:182-248.  grad/hess are device pointers iff
  * on_device (== boosting_on_cuda, cuda_single_gpu_tree_learner.cpp:101-106), else host pointers. */

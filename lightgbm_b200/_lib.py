@@ -11,7 +11,7 @@ _lib = None
 
 EXPORTS = [
     "LGBMB200_GetLastError", "LGBMB200_LearnerCreate", "LGBMB200_LearnerInit", "LGBMB200_LearnerResetConfig",
-    "LGBMB200_LearnerSetFeatureMask", "LGBMB200_LearnerSetConstantHessian", "LGBMB200_LearnerSetBaggingData", "LGBMB200_LearnerTrain",
+    "LGBMB200_LearnerSetFeatureMask", "LGBMB200_LearnerSetConstantHessian", "LGBMB200_LearnerSetBaggingData", "LGBMB200_LearnerGossSample", "LGBMB200_LearnerGetBaggingData", "LGBMB200_LearnerAddPredictionAllRows", "LGBMB200_LearnerTrain",
     "LGBMB200_LearnerAddPredictionToScore", "LGBMB200_LearnerGetPartition", "LGBMB200_LearnerGetLeafHistogram",
     "LGBMB200_LearnerConstructHistogram", "LGBMB200_L2Gradients", "LGBMB200_BinaryGradients", "LGBMB200_LearnerKernelLaunches",
     "LGBMB200_LearnerHistStats", "LGBMB200_LearnerSetProfiling", "LGBMB200_LearnerProfileByKind", "LGBMB200_DeviceAlloc", "LGBMB200_DeviceFree",

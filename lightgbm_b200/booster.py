@@ -46,12 +46,20 @@ def _parallel_rows(n: int, fn) -> None:
 class B200Booster:
     def __init__(self, layout: Layout, label: np.ndarray, config: Config, learning_rate: float = 0.1,
                  boost_from_average: bool = True, device_resident: bool = True, learner: B200TreeLearner | None = None,
-                 pinned: bool = False, objective: str = "regression", sigmoid: float = 1.0):
+                 pinned: bool = False, objective: str = "regression", sigmoid: float = 1.0,
+                 data_sample_strategy: str = "bagging", top_rate: float = 0.2, other_rate: float = 0.1, bagging_seed: int = 3):
+        assert data_sample_strategy in ("bagging", "goss")
+        self.goss = data_sample_strategy == "goss"
+        # GOSS lives on the device here; with host buffers it is the reference GBDT's own GOSSStrategy that samples and
+        # scores the out-of-bag rows (the drop-in of integration/), not this mirror
+        assert not (self.goss and not device_resident), "data_sample_strategy='goss' needs device_resident=True"
+        self.top_rate, self.other_rate, self.bagging_seed = float(top_rate), float(other_rate), int(bagging_seed)
         if learner is None:
             learner = B200TreeLearner(config)
             # RegressionL2loss::IsConstantHessian() is true for unweighted L2 (regression_objective.hpp:165-171);
-            # BinaryLogloss is not.  update_custom() on such a learner must pass equal hessians too.
-            learner.init(layout, is_constant_hessian=(objective == "regression"))
+            # BinaryLogloss is not; GOSS rescales hessians (GOSSStrategy::IsHessianChange, goss.hpp:105 -> gbdt.cpp:124).
+            # update_custom() on such a learner must pass equal hessians too.
+            learner.init(layout, is_constant_hessian=(objective == "regression" and not self.goss))
         self.learner = learner
         self.n = layout.num_data
         self.lr = float(learning_rate)
@@ -94,6 +102,9 @@ class B200Booster:
                 self.learner.l2_gradients(self.d_score, self.d_label, self.d_grad, self.d_hess, self.n)
             else:
                 self.learner.binary_gradients(self.d_score, self.d_label, self.d_grad, self.d_hess, self.n, self.sigmoid)
+            if self.goss and len(self.trees) >= int(1.0 / self.lr):
+                # GOSSStrategy::Bagging (goss.hpp:30-77) on the device: no sampling during the first 1/lr iterations
+                self.learner.goss_sample(self.d_grad, self.d_hess, self.top_rate, self.other_rate, self.bagging_seed, len(self.trees))
             tree = self.learner.train(self.d_grad, self.d_hess)
         else:
             t0 = time.perf_counter()
@@ -116,7 +127,10 @@ class B200Booster:
         tree.shrinkage(self.lr)
         if tree.num_leaves > 1:
             if self.device_resident:
-                self.learner.add_prediction_to_score(tree, self.d_score)
+                if self.goss and len(self.trees) >= int(1.0 / self.lr):
+                    self.learner.add_prediction_all_rows(tree, self.d_score)      # out-of-bag rows are scored too (gbdt.cpp:505-530)
+                else:
+                    self.learner.add_prediction_to_score(tree, self.d_score)
             else:
                 t3 = time.perf_counter()
                 self.learner.add_prediction_to_score(tree, self.score)

@@ -21,6 +21,7 @@
 #include "../../include/lgbm_b200.h"
 #include "hist_atom_kernel.cuh"
 #include "hist_q_kernel.cuh"
+#include "goss_kernel.cuh"
 #include "partition_kernel.cuh"
 #include "scan_kernel.cuh"
 #include "types.cuh"
@@ -203,11 +204,47 @@ class Learner {
     REQUIRE(inited_, "Init first");
     if (idx == nullptr) { if (bag_count_ >= 0) InvalidateGraph(); bag_count_ = -1; return; }
     REQUIRE(n > 0 && n <= N_, "bad bagging count");
-    if (bag_.n < static_cast<size_t>(N_)) bag_.alloc(N_);
+    // the bag buffer and its device-side count have stable addresses: a new bag (any size) replays the captured graph;
+    // only the switch between "no bag" and "bag" changes the launch sequence
+    if (bag_.n < static_cast<size_t>(N_)) { bag_.alloc(N_); bag_n_dev_.alloc(1); InvalidateGraph(); }
     CUDA_CHECK(cudaMemcpyAsync(bag_.p, idx, sizeof(int32_t) * n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(bag_n_dev_.p, &n, sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
     CUDA_CHECK(cudaStreamSynchronize(stream_));
-    if (bag_count_ != n) InvalidateGraph();
+    if (bag_count_ < 0) InvalidateGraph();
     bag_count_ = n;
+  }
+
+  // GOSSStrategy::Bagging on the device (goss_kernel.cuh): gradients / hessians are device arrays, modified in place;
+  // the kept rows become this learner's bagging set without touching the host.
+  int32_t GossSample(float* grad, float* hess, double top_rate, double other_rate, int32_t seed, int32_t iteration) {
+    REQUIRE(inited_, "Init first");
+    REQUIRE(top_rate > 0.0 && other_rate > 0.0 && top_rate + other_rate <= 1.0, "GOSS needs top_rate > 0, other_rate > 0, top_rate + other_rate <= 1");
+    if (bag_.n < static_cast<size_t>(N_)) { bag_.alloc(N_); bag_n_dev_.alloc(1); InvalidateGraph(); }
+    if (goss_state_.n == 0) { goss_state_.alloc(1); goss_hist_.alloc(256); goss_blocks_.alloc(part_blocks_); }
+    GossArgs ga;
+    ga.grad = grad; ga.hess = hess; ga.n = N_; ga.hist = goss_hist_.p; ga.st = goss_state_.p;
+    ga.flag_words = reinterpret_cast<uint32_t*>(flags_.p); ga.block_cnt = goss_blocks_.p; ga.bag = bag_.p; ga.bag_count = bag_n_dev_.p;
+    ga.top_rate = top_rate; ga.other_rate = other_rate; ga.seed = static_cast<uint32_t>(seed); ga.iter = static_cast<uint32_t>(iteration);
+    k_goss_begin<<<1, 32, 0, stream_>>>(ga);
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      k_goss_hist<<<num_sms_ * 4, kGossThreads, 0, stream_>>>(ga, shift);
+      k_goss_pick<<<1, 32, 0, stream_>>>(ga, shift);
+    }
+    k_goss_mark<<<part_blocks_, kGossThreads, 0, stream_>>>(ga);
+    k_goss_scatter<<<part_blocks_, kGossThreads, 0, stream_>>>(ga);
+    launches_ += 11;
+    CUDA_CHECK(cudaGetLastError());
+    int32_t n = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n, bag_n_dev_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    REQUIRE(n > 0 && n <= N_, "GOSS kept no row");
+    if (bag_count_ < 0) InvalidateGraph();
+    bag_count_ = n;
+    return n;
+  }
+  void GetBag(int32_t* out, int32_t n) {
+    REQUIRE(bag_count_ >= 0 && n == bag_count_, "no bagging set of that size");
+    CUDA_CHECK(cudaMemcpy(out, bag_.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
   }
 
   void Train(const float* grad, const float* hess, int on_device, LGBMB200_Tree* out) {
@@ -320,6 +357,22 @@ class Learner {
     for (auto& t : th) t.join();
   }
 
+  // every row (in the bag or not) through the last tree: score += leaf value (device score) and / or leaf ids
+  void RouteAllRows(const double* leaf_value_host, int num_leaves, double* score_dev, int32_t* row_leaf_dev) {
+    REQUIRE(inited_ && last_num_leaves_ > 0, "Train first");
+    REQUIRE(num_leaves == last_num_leaves_, "num_leaves does not match the last trained tree");
+    REQUIRE(!(peers_.world > 1 && peers_.mode != 1), "routing needs every column on this rank (single GPU or row-shard)");
+    const int ns = num_leaves - 1;
+    REQUIRE(ns <= kRouteMaxSplits, "too many leaves for k_route_rows");
+    if (score_dev != nullptr)
+      CUDA_CHECK(cudaMemcpyAsync(leaf_value_dev_.p, leaf_value_host, sizeof(double) * num_leaves, cudaMemcpyHostToDevice, stream_));
+    k_route_rows<<<num_sms_ * 8, 256, sizeof(RouteSplit) * std::max(ns, 1), stream_>>>(bins_.p, pitch_, N_, splits_.p, feat_.p, ns,
+                                                                                       leaf_value_dev_.p, score_dev, row_leaf_dev);
+    ++launches_;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+  }
+
   void FetchLeafIndex8() {
     REQUIRE(inited_ && last_num_leaves_ > 0 && last_num_leaves_ <= 255, "Train first (<= 255 leaves)");
     if (row_leaf8_.n < static_cast<size_t>(N_)) {
@@ -397,7 +450,7 @@ class Learner {
     }
     // prep with "no bagging" semantics over all rows: packs gh and sets the fixed-point scales
     PrepArgs pa = MakePrepArgs(g, h);
-    pa.bag = nullptr; pa.bag_count = 0;
+    pa.bag = nullptr; pa.bag_count = nullptr;
     pa.peers.world = 1;            // stand-alone hook: local histogram only, no exchange
     k_prep<<<prep_blocks_, kPrepThreads, 0, stream_>>>(pa);
     k_root_init<<<1, 32, 0, stream_>>>(pa);
@@ -616,7 +669,7 @@ class Learner {
   PrepArgs MakePrepArgs(const float* g, const float* h) {
     PrepArgs pa;
     pa.grad = g; pa.hess = h; pa.gq = gq_.p; pa.idx0 = idx0_.p;
-    pa.bag = bag_count_ >= 0 ? bag_.p : nullptr; pa.bag_count = bag_count_ >= 0 ? bag_count_ : 0;
+    pa.bag = bag_count_ >= 0 ? bag_.p : nullptr; pa.bag_count = bag_count_ >= 0 ? bag_n_dev_.p : nullptr;
     pa.num_data = N_; pa.partials = partials_.p; pa.leaves = leaves_.p; pa.ctl = ctl_.p; pa.params = params_;
     pa.max_leaves = params_.num_leaves; pa.num_partials = prep_blocks_; pa.peers = peers_;
     pa.ghq = PackedQuantHist() ? ghq_.p : nullptr;
@@ -906,7 +959,9 @@ class Learner {
   bool const_hess_ = false, hess_fill_valid_ = false;
   float hess_fill_ = 0.f;
   DevBuf<double> leaf_value_dev_;
-  DevBuf<int32_t> idx0_, idx1_, block_left_, bag_, row_leaf_;
+  DevBuf<int32_t> idx0_, idx1_, block_left_, bag_, bag_n_dev_, row_leaf_, goss_blocks_;
+  DevBuf<GossState> goss_state_;
+  DevBuf<uint32_t> goss_hist_;
   int32_t* h_row_leaf_ = nullptr;
   DevBuf<uint8_t> row_leaf8_;
   uint8_t* h_row_leaf8_ = nullptr;
@@ -1000,6 +1055,20 @@ int LGBMB200_LearnerSetBaggingData(LGBMB200_LearnerHandle h, const int32_t* used
   static_cast<Learner*>(h)->SetBagging(used_indices, num_used, on_device);
   API_END();
 }
+int LGBMB200_LearnerGossSample(LGBMB200_LearnerHandle h, float* grad_dev, float* hess_dev, double top_rate, double other_rate,
+                               int32_t seed, int32_t iteration, int32_t* out_bag_count) {
+  API_BEGIN();
+  if (!h || !grad_dev || !hess_dev) throw CudaError{"null argument"};
+  const int32_t n = static_cast<Learner*>(h)->GossSample(grad_dev, hess_dev, top_rate, other_rate, seed, iteration);
+  if (out_bag_count) *out_bag_count = n;
+  API_END();
+}
+int LGBMB200_LearnerGetBaggingData(LGBMB200_LearnerHandle h, int32_t* indices_host, int32_t num_indices) {
+  API_BEGIN();
+  if (!h || !indices_host) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->GetBag(indices_host, num_indices);
+  API_END();
+}
 int LGBMB200_LearnerTrain(LGBMB200_LearnerHandle h, const float* gradients, const float* hessians, int32_t on_device, LGBMB200_Tree* out_tree) {
   API_BEGIN();
   if (!h || !gradients || !hessians || !out_tree) throw CudaError{"null argument"};
@@ -1010,6 +1079,12 @@ int LGBMB200_LearnerAddPredictionToScore(LGBMB200_LearnerHandle h, const double*
   API_BEGIN();
   if (!h || !leaf_value || !score) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->AddPredictionToScore(leaf_value, num_leaves, score, on_device);
+  API_END();
+}
+int LGBMB200_LearnerAddPredictionAllRows(LGBMB200_LearnerHandle h, const double* leaf_value, int32_t num_leaves, double* score_dev) {
+  API_BEGIN();
+  if (!h || !leaf_value || !score_dev) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->RouteAllRows(leaf_value, num_leaves, score_dev, nullptr);
   API_END();
 }
 int LGBMB200_LearnerGetPartition(LGBMB200_LearnerHandle h, int32_t* leaf_begin, int32_t* leaf_count, int32_t* indices) {

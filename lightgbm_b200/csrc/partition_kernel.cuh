@@ -327,7 +327,8 @@ struct PrepArgs {
   int2* gq;                 // [num_data] fixed-point (g, h) of this tree (k_quant_rows; quantized training: k_quantize)
   int32_t* idx0;
   const int32_t* bag;       // device bag indices or nullptr
-  int32_t bag_count;
+  const int32_t* bag_count; // device: number of bag indices (read by the kernels, so that a new bag of a different size —
+                            // bagging or GOSS every iteration — replays the SAME captured graph)
   int32_t num_data;
   PartialSum* partials;     // [gridDim.x]
   Leaf* leaves;
@@ -355,9 +356,10 @@ __global__ void __launch_bounds__(kPrepThreads) k_prep(const PrepArgs a) {
     if (a.bag == nullptr) { sg += g; sh += h; a.idx0[i] = i; }
   }
   if (a.bag != nullptr) {
-    int perb = (a.bag_count + nb - 1) / nb;
+    const int bag_n = *a.bag_count;
+    int perb = (bag_n + nb - 1) / nb;
     perb = (perb + kPrepThreads - 1) / kPrepThreads * kPrepThreads;
-    const int blo = min(a.bag_count, static_cast<int>(blockIdx.x) * perb), bhi = min(a.bag_count, blo + perb);
+    const int blo = min(bag_n, static_cast<int>(blockIdx.x) * perb), bhi = min(bag_n, blo + perb);
     for (int i = blo + threadIdx.x; i < bhi; i += kPrepThreads) {
       const int r = a.bag[i];
       a.idx0[i] = r;
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(32) k_root_init(const PrepArgs a) {
   if (tid == 0) {
     double sg = 0.0, sh = 0.0; float mg = 0.f, mh = 0.f;
     for (int b = 0; b < a.num_partials; ++b) { sg += a.partials[b].g; sh += a.partials[b].h; mg = fmaxf(mg, a.partials[b].gmax); mh = fmaxf(mh, a.partials[b].hmax); }
-    s_in[0] = sg; s_in[1] = sh; s_in[2] = mg; s_in[3] = mh; s_in[4] = a.bag ? a.bag_count : a.num_data;
+    s_in[0] = sg; s_in[1] = sh; s_in[2] = mg; s_in[3] = mh; s_in[4] = a.bag ? *a.bag_count : a.num_data;
     s_in[5] = s_in[6] = s_in[7] = 0;
   }
   __syncthreads();
@@ -526,9 +528,10 @@ __global__ void __launch_bounds__(kPrepThreads) k_quantize(const PrepArgs a) {
     if (a.bag == nullptr) { sg += q.x; sh += q.y; }
   }
   if (a.bag != nullptr) {
-    int perb = (a.bag_count + nb - 1) / nb;
+    const int bag_n = *a.bag_count;
+    int perb = (bag_n + nb - 1) / nb;
     perb = (perb + kPrepThreads - 1) / kPrepThreads * kPrepThreads;
-    const int blo = min(a.bag_count, static_cast<int>(blockIdx.x) * perb), bhi = min(a.bag_count, blo + perb);
+    const int blo = min(bag_n, static_cast<int>(blockIdx.x) * perb), bhi = min(bag_n, blo + perb);
     for (int i = blo + threadIdx.x; i < bhi; i += kPrepThreads) {
       const int2 q = quantize_row(a, c, a.bag[i]);       // recomputed: the row may belong to another block's range
       sg += q.x; sh += q.y;
@@ -635,6 +638,35 @@ __global__ void __launch_bounds__(256) k_leaf_index(const Leaf* leaves, const in
   const Leaf& L = leaves[blockIdx.y];
   const int32_t* idx = (L.buf ? idx1 : idx0) + L.begin;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < L.lcount; i += gridDim.x * 256) row_leaf[idx[i]] = static_cast<T>(blockIdx.y);
+}
+
+// Route EVERY row through the tree that was just grown (the split records in application order) and add its leaf's
+// value to the score / record its leaf id.  With a bagging set (bagging, GOSS) the partition only holds the bagged
+// rows; the reference scores the out-of-bag rows by predicting the tree on them (GBDT::UpdateScore, gbdt.cpp:505-530 ->
+// Tree::AddPredictionToScore on bin iterators): this is that, over the device bin matrix, replaying the splits:
+// a row sitting in leaf s.leaf when split i is applied moves to leaf i + 1 iff it does not go left.
+struct RouteSplit { int32_t leaf, col, threshold, default_left; FeatMeta m; };
+constexpr int kRouteMaxSplits = 1024;
+__global__ void __launch_bounds__(256) k_route_rows(const uint8_t* __restrict__ bins, int64_t pitch, int n, const SplitRec* splits,
+                                                    const FeatMeta* feat, int num_splits, const double* leaf_value, double* score,
+                                                    int32_t* row_leaf) {
+  extern __shared__ RouteSplit s_sp[];
+  for (int i = threadIdx.x; i < num_splits; i += blockDim.x) {
+    const SplitRec r = splits[i];
+    RouteSplit q; q.leaf = r.leaf; q.m = feat[r.feature]; q.col = q.m.col; q.threshold = r.threshold; q.default_left = r.default_left;
+    s_sp[i] = q;
+  }
+  __syncthreads();
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    const uint8_t* rp = bins + static_cast<int64_t>(row) * pitch;
+    int leaf = 0;
+    for (int i = 0; i < num_splits; ++i) {
+      const RouteSplit& q = s_sp[i];
+      if (q.leaf == leaf && !goes_left(rp[q.col], q.m, q.threshold, q.default_left)) leaf = i + 1;
+    }
+    if (score != nullptr) score[row] += leaf_value[leaf];
+    if (row_leaf != nullptr) row_leaf[row] = leaf;
+  }
 }
 
 __global__ void k_fill_f32(float* p, float v, int n) {

@@ -270,6 +270,18 @@ class B200TreeLearner:
         ptr, dev = _ptr_of(used_indices)
         check(lib().LGBMB200_LearnerSetBaggingData(self.handle, ptr, C.c_int32(n), C.c_int32(dev)))
 
+    # GOSSStrategy::Bagging on the device (goss.hpp:30-77): gradients / hessians are DeviceArrays, modified in place
+    def goss_sample(self, grad_dev, hess_dev, top_rate: float, other_rate: float, seed: int = 0, iteration: int = 0) -> int:
+        n = C.c_int32(0)
+        check(lib().LGBMB200_LearnerGossSample(self.handle, _ptr_of(grad_dev)[0], _ptr_of(hess_dev)[0], C.c_double(top_rate),
+                                               C.c_double(other_rate), C.c_int32(seed), C.c_int32(iteration), C.byref(n)))
+        return n.value
+
+    def get_bagging_data(self, n: int) -> np.ndarray:
+        out = np.empty(n, np.int32)
+        check(lib().LGBMB200_LearnerGetBaggingData(self.handle, _p(out), C.c_int32(n)))
+        return out
+
     # Tree* TreeLearner::Train(const score_t* gradients, const score_t* hessians, bool is_first_tree)
     def train(self, gradients, hessians, is_first_tree: bool = False) -> Tree:
         if isinstance(gradients, np.ndarray):
@@ -298,6 +310,11 @@ class B200TreeLearner:
             assert out_score.dtype == np.float64 and out_score.flags.c_contiguous
         sp, sd = _ptr_of(out_score)
         check(lib().LGBMB200_LearnerAddPredictionToScore(self.handle, _p(lv), C.c_int32(tree.num_leaves), sp, C.c_int32(sd)))
+
+    # GBDT::UpdateScore with a bagging set: every row (bagged or not) through the last tree, device score
+    def add_prediction_all_rows(self, tree: Tree, score_dev) -> None:
+        lv = np.ascontiguousarray(tree.leaf_value, dtype=np.float64)
+        check(lib().LGBMB200_LearnerAddPredictionAllRows(self.handle, _p(lv), C.c_int32(tree.num_leaves), _ptr_of(score_dev)[0]))
 
     # DataPartition::GetIndexOnLeaf for all leaves of the last tree
     def get_partition(self, num_leaves: int):

@@ -281,13 +281,29 @@ class RefDatasetStreamed(RefDataset):
     helper thread while the current one is being pushed."""
 
     def __init__(self, block_fn, nrow: int, ncol: int, label: np.ndarray | None, params: dict, block_rows: int = 250_000,
-                 sample_rows: int = 65_536):
+                 sample_rows: int = 65_536, sampled_columns: bool = False):
+        """sampled_columns=True builds the Dataset skeleton with LGBM_DatasetCreateFromSampledColumn (bin mappers AND the
+        EFB bundling decision from the sample, exactly as a file / matrix load would: DatasetLoader::ConstructFromSampleData)
+        instead of LGBM_DatasetCreateByReference, whose CreateValid keeps one feature per group."""
         from concurrent.futures import ThreadPoolExecutor
         L = lib()
         first = np.ascontiguousarray(block_fn(0, min(nrow, block_rows)), dtype=np.float32)
-        sample = RefDataset(first[:min(len(first), sample_rows)], None, params)
         self.handle = C.c_void_p()
-        _check(L.LGBM_DatasetCreateByReference(sample.handle, C.c_int64(nrow), C.byref(self.handle)))
+        sample = None
+        if sampled_columns:
+            smp = first[:min(len(first), sample_rows)]
+            vals, idxs, cnts = [], [], np.zeros(ncol, dtype=np.int32)
+            for c in range(ncol):
+                nz = np.nonzero(smp[:, c])[0].astype(np.int32)          # zeros are implicit in the sampled-column format
+                vals.append(np.ascontiguousarray(smp[nz, c], dtype=np.float64)); idxs.append(nz); cnts[c] = len(nz)
+            pv = (C.POINTER(C.c_double) * ncol)(*[v.ctypes.data_as(C.POINTER(C.c_double)) for v in vals])
+            pi = (C.POINTER(C.c_int) * ncol)(*[i.ctypes.data_as(C.POINTER(C.c_int)) for i in idxs])
+            _check(L.LGBM_DatasetCreateFromSampledColumn(pv, pi, C.c_int32(ncol), cnts.ctypes.data_as(C.POINTER(C.c_int)),
+                                                         C.c_int32(len(smp)), C.c_int32(nrow), C.c_int64(nrow),
+                                                         C.c_char_p(params_str(params)), C.byref(self.handle)))
+        else:
+            sample = RefDataset(first[:min(len(first), sample_rows)], None, params)
+            _check(L.LGBM_DatasetCreateByReference(sample.handle, C.c_int64(nrow), C.byref(self.handle)))
         with ThreadPoolExecutor(max_workers=1) as ex:
             lo, blk = 0, first
             while lo < nrow:
@@ -299,7 +315,8 @@ class RefDatasetStreamed(RefDataset):
                 lo = hi
                 blk = nxt.result() if nxt is not None else None
         del first
-        sample.free()
+        if sample is not None:
+            sample.free()
         if label is not None:
             self.set_label(label)
         self.num_data = nrow
