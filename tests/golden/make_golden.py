@@ -148,9 +148,74 @@ def example_cases():
              quant=dict(num_grad_quant_bins=8, quant_train_renew_leaf=True))
 
 
+EFB4_GEN = dict(rows=200_000, cols=256, seed=45, grad_seed=9045)
+
+
+def efb4_inputs():
+    """The C4-shaped inputs of the efb4 fixture, a pure function of EFB4_GEN (bench.py generators): bundled columns,
+    raw features, binary labels, logistic gradients at a seeded random score."""
+    import bench
+    wl = dict(bench.WORKLOADS["C4"], rows=EFB4_GEN["rows"], cols=EFB4_GEN["cols"], seed=EFB4_GEN["seed"])
+    raw = bench.gen_efb4(wl["rows"], wl["cols"], wl["seed"], raw=True)
+    y = bench.gen_label_wl(wl, bench.gen_columns(wl, 0, bench.LABEL_COLS["efb4"]))
+    score = np.random.default_rng(EFB4_GEN["grad_seed"]).normal(size=wl["rows"]) * 0.8
+    p = 1.0 / (1.0 + np.exp(-score))
+    return wl, raw, y, (p - y).astype(np.float32), (p * (1.0 - p)).astype(np.float32)
+
+
+def bundle_by_layout(raw, feat_column, feat_lo, feat_real_index, num_columns):
+    """Stored group values (feature_group.h:253-267) of sparse raw features whose value v > 0 has bin v and whose most
+    frequent bin 0 is elided, for the bundling (column, offset per feature) a reference Dataset chose."""
+    out = np.zeros((len(raw), num_columns), dtype=np.uint8)
+    for f in range(len(feat_column)):
+        v = raw[:, feat_real_index[f]]
+        nz = np.nonzero(v)[0]
+        out[nz, feat_column[f]] = feat_lo[f] + v[nz] - 1
+    return out
+
+
+def efb4_case():
+    """C4 at fixture scale: 200 000 x 256 sparse features, exclusive in blocks of 4, through the
+    reference's OWN Dataset construction with the cuda rules (sampled-column API + PushRows: EFB bundles them into 64
+    uint8 columns), binary-logloss gradients, the reference CPU learner's 63-leaf tree.  The 12.8 MB bin matrix is not
+    stored: the fixture keeps the layout the reference produced, checksums of the matrix / gradients, and the tree; the
+    loader regenerates the inputs from EFB4_GEN and checks them against the checksums."""
+    import bench
+    wl, raw, y, g, h = efb4_inputs()
+    dsp = dict(BASE_DS, enable_bundle="true", device_type="cuda", num_threads=8)
+    ds = refapi.RefDatasetStreamed(lambda lo, hi: bench.gen_raw_float(wl, row_lo=lo, row_hi=hi), wl["rows"], wl["cols"], y, dsp,
+                                   block_rows=4 * bench.GEN_CHUNK, sample_rows=wl["rows"], sampled_columns=True)
+    lay = ds.layout()
+    cols = bundle_by_layout(raw, lay.feat_column, lay.feat_lo, lay.feat_real_index, lay.num_columns)
+    assert lay.num_columns == wl["cols"] // 4 and np.array_equal(lay.bins, cols), "the reference stored the bundles differently"
+    lp = dict(DEFAULTS, num_leaves=63, min_data_in_leaf=20)
+    bp = dict(dsp, **BASE_BOOST, **lp); bp["device_type"] = "cpu"; bp["num_threads"] = 1
+    bst = refapi.RefBooster(ds, bp)
+    bst.update_custom(g, h)
+    t = bst.trees()[0]
+    feats, tbins = thresholds_to_bins(lay, t)
+    d = lay.to_npz_dict(with_bins=False)
+    d.update(gen_efb4=np.array([EFB4_GEN[k] for k in ("rows", "cols", "seed", "grad_seed")], np.int64),
+             bins_checksum=np.array([int(cols.astype(np.uint64).sum()), int((cols.astype(np.uint64) * (np.arange(cols.shape[1], dtype=np.uint64) + 1)).sum())], np.uint64),
+             grad_checksum=np.array([float(g.astype(np.float64).sum()), float(h.astype(np.float64).sum())]),
+             params=np.array([lp[k] for k in LEARNER_KEYS], np.float64),
+             ref_num_leaves=np.int64(t.num_leaves), ref_split_feature_inner=feats, ref_threshold_bin=tbins,
+             ref_split_leaf=t.split_leaf(), ref_default_left=t.default_left.astype(np.int32), ref_split_gain=t.split_gain,
+             ref_internal_count=t.internal_count, ref_leaf_value=t.leaf_value, ref_leaf_count=t.leaf_count,
+             ref_leaf_weight=t.leaf_weight, ref_threshold_real=t.threshold)
+    path = os.path.join(HERE, "efb4_200k_x256.npz")
+    np.savez_compressed(path, **d)
+    print(f"efb4_200k_x256: N={lay.num_data} C={lay.num_columns} F={lay.num_features} leaves={t.num_leaves} "
+          f"multi_feature_cols={int((lay.feat_in_group > 1).sum())} -> {os.path.getsize(path)} B")
+    bst.free(); ds.free()
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "quant":
         quantized_cases()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "efb4":
+        efb4_case()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "examples":
         example_cases()

@@ -1,6 +1,7 @@
 """Loads the golden fixtures of tests/golden/*.npz (written by tests/golden/make_golden.py from the real reference)."""
 import glob
 import os
+import sys
 
 import numpy as np
 
@@ -20,6 +21,19 @@ class Golden:
     def __init__(self, name):
         d = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
         self.name = name
+        if "gen_efb4" in d:
+            # inputs regenerated from their seeds (tests/golden/make_golden.py efb4_inputs) and checked against the
+            # checksums taken when the reference produced the fixture
+            sys.path.insert(0, os.path.join(GOLDEN_DIR))
+            sys.path.insert(0, os.path.dirname(os.path.dirname(GOLDEN_DIR)))
+            import make_golden
+            assert [int(v) for v in d["gen_efb4"]] == [make_golden.EFB4_GEN[k] for k in ("rows", "cols", "seed", "grad_seed")]
+            _, raw, _, g, h = make_golden.efb4_inputs()
+            cols = make_golden.bundle_by_layout(raw, d["feat_column"], d["feat_lo"], d["feat_real_index"], int(d["dims"][1]))
+            w = np.arange(cols.shape[1], dtype=np.uint64) + 1
+            assert int(cols.astype(np.uint64).sum()) == int(d["bins_checksum"][0]) and int((cols.astype(np.uint64) * w).sum()) == int(d["bins_checksum"][1])
+            assert float(g.astype(np.float64).sum()) == float(d["grad_checksum"][0]) and float(h.astype(np.float64).sum()) == float(d["grad_checksum"][1])
+            d["bins"], d["grad"], d["hess"] = cols, g, h
         self.layout = Layout.from_npz_dict(d)
         self.grad, self.hess = d["grad"], d["hess"]
         self.params = {k: (int(v) if k in INT_KEYS else float(v)) for k, v in zip(LEARNER_KEYS, d["params"])}
