@@ -242,6 +242,12 @@ LGBMB200_EXPORT int LGBMB200_LearnerCommExportPool(LGBMB200_LearnerHandle h, uin
 LGBMB200_EXPORT int LGBMB200_LearnerCommConnectRows(LGBMB200_LearnerHandle h, int32_t rank, int32_t world,
                                                     const uint8_t* comm_handles, const uint8_t* pool_handles);
 
+/* Leaf id of every row of [row_lo, row_hi) in the last tree, one byte per row (needs <= 255 leaves; 0xFF = the row is
+ * outside the bagging set): the host-score path of AddPredictionToScore for a caller that keeps only a row slice of the
+ * scores (N > 1 feature-sharded ranks each update 1/N of the host score). */
+LGBMB200_EXPORT int LGBMB200_LearnerGetLeafIndexRange8(LGBMB200_LearnerHandle h, int32_t row_lo, int32_t row_hi,
+                                                       uint8_t* leaf_index_host);
+
 /* Per-row leaf id of the last tree (host output, -1 for rows outside the bag): what the CPU learner's
  * DataPartition encodes and the reference CUDA learner keeps in cuda_data_index_to_leaf_index_
  * (reference src/treelearner/cuda/cuda_data_partition.cu:113). */

@@ -15,7 +15,7 @@ EXPORTS = [
     "LGBMB200_LearnerAddPredictionToScore", "LGBMB200_LearnerGetPartition", "LGBMB200_LearnerGetLeafHistogram",
     "LGBMB200_LearnerConstructHistogram", "LGBMB200_L2Gradients", "LGBMB200_BinaryGradients", "LGBMB200_LearnerKernelLaunches",
     "LGBMB200_LearnerHistStats", "LGBMB200_LearnerSetProfiling", "LGBMB200_LearnerProfileByKind", "LGBMB200_DeviceAlloc", "LGBMB200_DeviceFree",
-    "LGBMB200_MemcpyH2D", "LGBMB200_MemcpyD2H", "LGBMB200_LearnerFree", "LGBMB200_LearnerGetLeafIndex",
+    "LGBMB200_MemcpyH2D", "LGBMB200_MemcpyD2H", "LGBMB200_LearnerFree", "LGBMB200_LearnerGetLeafIndex", "LGBMB200_LearnerGetLeafIndexRange8",
     "LGBMB200_LearnerCommExport", "LGBMB200_LearnerCommConnect", "LGBMB200_LearnerCommExportPool", "LGBMB200_LearnerCommConnectRows",
     "LGBMB200_LearnerCommExportColumns", "LGBMB200_LearnerCommShareColumns", "LGBMB200_LearnerTimerStart", "LGBMB200_LearnerTimerStop", "LGBMB200_HostAllocPinned", "LGBMB200_HostFreePinned",
 ]

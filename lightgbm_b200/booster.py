@@ -161,3 +161,56 @@ class B200Booster:
     def l2(self) -> float:
         s = self.scores()
         return float(np.mean((s - self.label) ** 2))
+
+
+class RowSlicedHostBooster:
+    """Host-buffer L2 boosting for `world` feature-sharded ranks (one process per GPU): every rank holds ALL rows of its
+    column slice on the device, but only rows [lo, hi) of the HOST label / score.  Per iteration a rank computes the
+    gradients of its own row slice, copies those 4 (hi - lo) bytes host->device from pinned memory, and the full
+    gradient vector is assembled on every GPU by one all-gather over NVLink (torch.distributed / NCCL: plumbing); after
+    Train it fetches the leaf ids of its own rows (1 byte each) and updates its slice of the host score.  Host work and
+    PCIe traffic per rank are 1/world of the single-process path (at 8 GPUs every rank used to
+    recompute all N gradients and ship the same 40 MB)."""
+
+    def __init__(self, learner: B200TreeLearner, label_full: np.ndarray, learning_rate: float, rank: int, world: int, dist, torch):
+        self.learner, self.lr, self.dist, self.torch = learner, float(learning_rate), dist, torch
+        n = len(label_full)
+        self.n, self.per = n, (n + world - 1) // world
+        self.lo, self.hi = min(n, rank * self.per), min(n, (rank + 1) * self.per)
+        init = float(np.mean(label_full, dtype=np.float64))
+        self.label = np.ascontiguousarray(label_full[self.lo:self.hi], dtype=np.float32)
+        self.score = np.full(self.hi - self.lo, init, dtype=np.float64)
+        self.h_grad = torch.zeros(self.per, dtype=torch.float32).pin_memory()
+        self.grad = self.h_grad.numpy()
+        self.d_local = torch.zeros(self.per, dtype=torch.float32, device="cuda")
+        self.d_full = torch.zeros(self.per * world, dtype=torch.float32, device="cuda")
+        self.d_hess = torch.ones(self.per * world, dtype=torch.float32, device="cuda")
+        self.leaf8 = np.zeros(self.per, dtype=np.uint8)
+        self.host_ms = {"gradients": 0.0, "train": 0.0, "score": 0.0}
+        self.trees = []
+
+    def update(self) -> Tree:
+        t0 = time.perf_counter()
+        m = self.hi - self.lo
+
+        def l2(a, b):
+            np.subtract(self.score[a:b], self.label[a:b], out=self.grad[a:b], casting="unsafe")
+        _parallel_rows(m, l2)
+        t1 = time.perf_counter()
+        self.d_local.copy_(self.h_grad, non_blocking=True)
+        self.dist.all_gather_into_tensor(self.d_full, self.d_local)
+        self.torch.cuda.current_stream().synchronize()         # the learner runs on its own stream
+        tree = self.learner.train(self.d_full, self.d_hess)
+        t2 = time.perf_counter()
+        tree.shrinkage(self.lr)
+        if tree.num_leaves > 1:
+            self.learner.get_leaf_index_range8(self.lo, self.hi, self.leaf8)
+            lv = tree.leaf_value
+
+            def add(a, b):
+                self.score[a:b] += lv[self.leaf8[a:b]]
+            _parallel_rows(m, add)
+        t3 = time.perf_counter()
+        self.host_ms["gradients"] += (t1 - t0) * 1e3; self.host_ms["train"] += (t2 - t1) * 1e3; self.host_ms["score"] += (t3 - t2) * 1e3
+        self.trees.append(tree)
+        return tree

@@ -389,6 +389,25 @@ class Learner {
     CUDA_CHECK(cudaStreamSynchronize(stream_));
   }
 
+  // leaf ids (one byte per row, 0xFF = outside the bag) of rows [lo, hi) only: N > 1 ranks that each keep a row slice of
+  // the host score fetch their slice instead of all N bytes
+  void GetLeafIndexRange8(int32_t lo, int32_t hi, uint8_t* out_host) {
+    REQUIRE(inited_ && last_num_leaves_ > 0 && last_num_leaves_ <= 255, "Train first (<= 255 leaves)");
+    REQUIRE(lo >= 0 && lo <= hi && hi <= N_, "bad row range");
+    if (row_leaf8_.n < static_cast<size_t>(N_)) {
+      row_leaf8_.alloc(N_);
+      if (h_row_leaf8_) cudaFreeHost(h_row_leaf8_);
+      CUDA_CHECK(cudaMallocHost(&h_row_leaf8_, static_cast<size_t>(N_)));
+    }
+    if (bag_count_ >= 0) CUDA_CHECK(cudaMemsetAsync(row_leaf8_.p, 0xFF, static_cast<size_t>(N_), stream_));
+    dim3 grid(std::max(1, std::min(num_sms_ * 4, (N_ + 255) / 256)), last_num_leaves_);
+    k_leaf_index<uint8_t><<<grid, 256, 0, stream_>>>(leaves_.p, idx0_.p, idx1_.p, row_leaf8_.p);
+    ++launches_;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out_host, row_leaf8_.p + lo, static_cast<size_t>(hi - lo), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+  }
+
   void FetchLeafIndex() {
     REQUIRE(inited_ && last_num_leaves_ > 0, "Train first");
     if (row_leaf_.n < static_cast<size_t>(N_)) {
@@ -1180,6 +1199,12 @@ int LGBMB200_LearnerGetLeafIndex(LGBMB200_LearnerHandle h, int32_t* leaf_index_h
   API_BEGIN();
   if (!h || !leaf_index_host) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->GetLeafIndex(leaf_index_host);
+  API_END();
+}
+int LGBMB200_LearnerGetLeafIndexRange8(LGBMB200_LearnerHandle h, int32_t row_lo, int32_t row_hi, uint8_t* leaf_index_host) {
+  API_BEGIN();
+  if (!h || !leaf_index_host) throw CudaError{"null argument"};
+  static_cast<Learner*>(h)->GetLeafIndexRange8(row_lo, row_hi, leaf_index_host);
   API_END();
 }
 int LGBMB200_LearnerTimerStart(LGBMB200_LearnerHandle h) {

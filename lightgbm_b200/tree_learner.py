@@ -382,6 +382,11 @@ class B200TreeLearner:
         check(lib().LGBMB200_LearnerGetLeafIndex(self.handle, _p(out)))
         return out
 
+    def get_leaf_index_range8(self, lo: int, hi: int, out: np.ndarray) -> np.ndarray:
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and len(out) >= hi - lo
+        check(lib().LGBMB200_LearnerGetLeafIndexRange8(self.handle, C.c_int32(lo), C.c_int32(hi), _p(out)))
+        return out
+
     def timer_start(self) -> None:
         check(lib().LGBMB200_LearnerTimerStart(self.handle))
 
