@@ -627,7 +627,22 @@ def main():
     # --- e2e: host buffers through the C-ABI, copies inside the timed region
     e2e = None
     if not args.no_e2e and not goss and not (wl["shard"] == "rows" and world > 1):
-        H = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=False, learner=L, pinned=True, objective=wl["objective"])
+        if world > 1:
+            # every rank owns a row slice of the HOST label / score: gradients of the slice H2D + one NVLink all-gather,
+            # leaf ids of the slice D2H (lightgbm_b200/booster.py RowSlicedHostBooster)
+            import torch
+            from lightgbm_b200.booster import RowSlicedHostBooster
+            H = RowSlicedHostBooster(L, y, 0.1, rank, world, dist, torch)
+            h2d, d2h = H.per * 4, H.per
+            note = ("every rank: L2 gradients of its N/world row slice on the host (pinned) -> H2D 4 B/row of the slice -> all-gather of the "
+                    "full gradient vector over NVLink (NCCL) -> Train -> leaf ids of the slice D2H (1 B/row) -> host score += leaf value; "
+                    "bytes are per rank")
+        else:
+            H = lgb.B200Booster(lay, y, cfg, learning_rate=0.1, device_resident=False, learner=L, pinned=True, objective=wl["objective"])
+            h2d, d2h = rows * (4 if const_hess else 8) + 4, rows * (1 if leaves <= 255 else 4) + 4096
+            note = ("host gradients (pinned, 4 B/row; the hessian is constant for L2 and only hessians[0] is read, as "
+                    "in the reference) -> H2D inside Train; per-row leaf ids (1 B/row up to 255 leaves) D2H inside AddPredictionToScore; "
+                    "host computes g = score - y and score += leaf_value[leaf_id]")
         for _ in range(args.warmup):
             H.update()
         barrier()
@@ -638,11 +653,8 @@ def main():
             H.update()
         barrier()
         dt = max_over_ranks((time.time() - t0) / args.steps)
-        e2e = {"value": 1.0 / dt, "unit": "iters/sec", "h2d_bytes_per_step": rows * (4 if const_hess else 8) + 4, "d2h_bytes_per_step": rows * (1 if leaves <= 255 else 4) + 4096,
-               "ms_per_step": dt * 1e3, "host_ms_per_step": {k: v / args.steps for k, v in H.host_ms.items()},
-               "note": "host gradients (pinned, 4 B/row; the hessian is constant for L2 and only hessians[0] is read, as "
-                       "in the reference) -> H2D inside Train; per-row leaf ids (1 B/row up to 255 leaves) D2H inside AddPredictionToScore; "
-                       "host computes g = score - y and score += leaf_value[leaf_id]"}
+        e2e = {"value": 1.0 / dt, "unit": "iters/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3, "host_ms_per_step": {k: v / args.steps for k, v in H.host_ms.items()}, "note": note}
 
     cpu = None
     if rank != 0:

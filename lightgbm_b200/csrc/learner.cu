@@ -75,7 +75,7 @@ class Learner {
   // Developer A/B switches (not part of the boundary): LGBMB200_DEBUG is a bit mask read once per process.
   //   1: no column-major copy for the partition   2: no TMA staging   16: programmatic dependent launch on the chain
   //   32: k_select folded into k_scan's last block   64: quantized training never uses the packed-cell kernel
-  //   256: no leaf-ordered (g,h) copies
+  //   256: no leaf-ordered (g,h) copies   512: partition as two launches (flags, scatter) instead of the fused cooperative one
   static int DebugBits() {
     static const int bits = std::getenv("LGBMB200_DEBUG") ? std::atoi(std::getenv("LGBMB200_DEBUG")) : 0;
     return bits;
@@ -786,13 +786,24 @@ class Learner {
   // this becomes a programmatic graph edge.  Profiling mode (an event after every launch) keeps plain launches.
   template <typename... KArgs, typename... Args>
   void LaunchChain(bool chain, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    LaunchChainEx(chain, false, kernel, grid, block, smem, std::forward<Args>(args)...);
+  }
+  // cooperative = true: the launch fails unless every block of the grid can be resident at once (k_partition's
+  // grid-wide barrier relies on it)
+  template <typename... KArgs, typename... Args>
+  void LaunchChainEx(bool chain, bool cooperative, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
     cudaLaunchConfig_t lc = {};
     lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = stream_;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (chain && (DebugBits() & 16) && !profiling_ && !cooperative) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (cooperative) { at[na].id = cudaLaunchAttributeCooperative; at[na].val.cooperative = 1; ++na; }
     lc.attrs = at;
-    lc.numAttrs = (chain && (DebugBits() & 16) && !profiling_) ? 1 : 0;
+    lc.numAttrs = na;
     CUDA_CHECK(cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...));
   }
 
@@ -849,11 +860,18 @@ class Learner {
     for (int it = 0; it < NL - 1 + 1; ++it) {
       // it == 0: root pass; it >= 1: apply split it-1, then find splits for its two children
       if (it > 0) {
-        LaunchChain(true, k_part_flags, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
-        Stamp(kProfPartFlags);
-        LaunchChain(true, k_part_scatter, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
-        Stamp(kProfPartScatter);
-        launches_ += 2;
+        if ((peers_.world > 1 && peers_.mode == 0) || (DebugBits() & 512)) {
+          // the split's owner computes the go-left bits and pushes them: two launches (only the owner runs the first)
+          LaunchChain(true, k_part_flags, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
+          Stamp(kProfPartFlags);
+          LaunchChain(true, k_part_scatter, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
+          Stamp(kProfPartScatter);
+          launches_ += 2;
+        } else {
+          LaunchChainEx(true, true, k_partition, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
+          Stamp(kProfPartScatter);
+          ++launches_;
+        }
         if (it == NL - 1) break;   // the tree is full: no need to look for further splits
       }
       LaunchHist(ha, qa, it > 0);   // it == 0 follows a memset node: plain dependency

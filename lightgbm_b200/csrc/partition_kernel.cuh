@@ -68,8 +68,7 @@ __device__ __forceinline__ void part_block_range(int n, int nblocks, int b, int*
 // then publishes a sequence number; k_part_scatter on every rank waits for it.
 constexpr int kPartUnroll = 4;
 
-__global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
-  pdl_enter();
+__device__ __forceinline__ void part_flags_body(const PartArgs& a) {
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
   const int me = a.peers.rank;
@@ -152,8 +151,12 @@ __global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a) {
+__global__ void __launch_bounds__(kPartThreads) k_part_flags(const PartArgs a) {
   pdl_enter();
+  part_flags_body(a);
+}
+
+__device__ __forceinline__ void part_scatter_body(const PartArgs& a) {
   Ctl* c = a.ctl;
   if (!c->cur_valid) return;
   const int n = c->cur_count, begin = c->cur_begin;
@@ -298,6 +301,37 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
     c->do_find = do_find;
     if (c->error) c->cur_valid = 0;
   }
+}
+
+__global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a) {
+  pdl_enter();
+  part_scatter_body(a);
+}
+
+// Both phases in ONE cooperative launch (all blocks co-resident): flags + per-block counts, a grid-wide barrier on a
+// monotonic counter in the control block, then the scatter and the SplitInner bookkeeping.  One launch boundary per split
+// less on the critical path.  Used whenever every rank computes its own flags (single GPU, replicated partition columns,
+// row-shard); the owner-pushes-flags mode keeps the two launches (only the owner runs the first).
+__global__ void __launch_bounds__(kPartThreads) k_partition(const PartArgs a) {
+  pdl_enter();
+  Ctl* c = a.ctl;
+  if (!c->cur_valid) return;             // uniform over the grid: nobody reaches the barrier
+  part_flags_body(a);
+  __shared__ unsigned s_target;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned old = atomicAdd(&c->part_barrier, 1u);
+    const unsigned target = (old / gridDim.x + 1u) * gridDim.x;
+    long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned*>(&c->part_barrier) < target) {
+      if (clock64() - t0 > kWatchdogCycles) { c->error = 1; break; }
+    }
+    s_target = target;
+    __threadfence();
+  }
+  __syncthreads();
+  part_scatter_body(a);
 }
 
 // One-off at Init: column-major copy of the bin matrix (32x32 byte tiles through shared memory)
