@@ -210,7 +210,7 @@ LGBMB200_EXPORT int LGBMB200_LearnerProfileByKind(LGBMB200_LearnerHandle h, doub
 
 /* ---- Multi-GPU, feature-shard (semantic model: FeatureParallelTreeLearner, reference
  * src/treelearner/feature_parallel_tree_learner.cpp:37-78 + SyncUpGlobalBestSplit, parallel_tree_learner.h:207-232).
- * One learner per GPU (one process per GPU, or several learners in one process); every learner is Init-ed with ALL
+ * One learner per GPU (one process per GPU, or several learners in one process (LGBMB200_LearnersConnectLocal)); every learner is Init-ed with ALL
  * rows and ITS column slice (feat_real_index stays global).  Per split the ranks exchange their two per-leaf best
  * candidates and the split's owner pushes the go-left flags — both through NVLink peer memory inside the kernels
  * (no NCCL call, no host round trip).  Bootstrap: every rank exports a 64-byte CUDA-IPC handle of its exchange
@@ -219,6 +219,14 @@ LGBMB200_EXPORT int LGBMB200_LearnerProfileByKind(LGBMB200_LearnerHandle h, doub
 LGBMB200_EXPORT int LGBMB200_LearnerCommExport(LGBMB200_LearnerHandle h, uint8_t* handle_out_64);
 LGBMB200_EXPORT int LGBMB200_LearnerCommConnect(LGBMB200_LearnerHandle h, int32_t rank, int32_t world,
                                                 const uint8_t* all_handles, const int32_t* feature_offsets);
+
+/* The same feature-shard bootstrap for `world` learners inside ONE process, one per GPU (how the reference's own
+ * multi-GPU mode is driven: one host thread per device, include/LightGBM/cuda/cuda_nccl_topology.hpp:177-188): peer
+ * access replaces CUDA IPC.  handles[r] is rank r's learner, already Init-ed with its column slice; afterwards Train must
+ * be called on ALL of them concurrently (one host thread each) with the same gradients.  replicate_columns = 1 also gives
+ * every rank a copy of every rank's partition columns (see CommShareColumns). */
+LGBMB200_EXPORT int LGBMB200_LearnersConnectLocal(LGBMB200_LearnerHandle* handles, int32_t world, const int32_t* feature_offsets,
+                                                  int32_t replicate_columns);
 
 /* Optional, after CommConnect: replicate every rank's column-major partition columns on every rank (costs
  * total_columns x num_data bytes of HBM per GPU, filled by NVLink peer copies — the 180 GB of a B200 hold a

@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <stdexcept>
+#include <string>
+#include <thread>
 
 namespace LightGBM {
 
@@ -57,12 +60,41 @@ void B200TreeLearner::CheckSupported(const Config* config) {
 
 B200TreeLearner::B200TreeLearner(const Config* config) : config_(config), col_sampler_(config) {
   CheckSupported(config);
-  LGBMB200_Config c = ToB200Config(config);
-  Check(LGBMB200_LearnerCreate(&c, &handle_));
+  // devices: gpu_device_id_list ("0,1,2,...") if given, else gpu_device_id .. gpu_device_id + num_gpu - 1
+  const int W = std::max(1, config->num_gpu);
+  if (W > 8) Log::Fatal("lgbm_b200: num_gpu > 8 is not supported");
+  if (!config->gpu_device_id_list.empty()) {
+    for (const std::string& tok : Common::Split(config->gpu_device_id_list.c_str(), ',')) devices_.push_back(std::atoi(tok.c_str()));
+    if (static_cast<int>(devices_.size()) != W) Log::Fatal("lgbm_b200: gpu_device_id_list must name num_gpu devices");
+  } else {
+    for (int r = 0; r < W; ++r) devices_.push_back(std::max(0, config->gpu_device_id) + r);
+  }
+  handles_.assign(W, nullptr);
+  for (int r = 0; r < W; ++r) {
+    LGBMB200_Config c = ToB200Config(config);
+    if (W > 1 || config->gpu_device_id >= 0) c.gpu_device_id = devices_[r];
+    Check(LGBMB200_LearnerCreate(&c, &handles_[r]));
+  }
+  handle_ = handles_[0];
 }
 
 B200TreeLearner::~B200TreeLearner() {
-  if (handle_) LGBMB200_LearnerFree(handle_);
+  for (LGBMB200_LearnerHandle h : handles_) if (h) LGBMB200_LearnerFree(h);
+}
+
+// run f(rank) for every rank: concurrently (one host thread per device) when there are several — Train blocks inside
+// the in-kernel NVLink exchange until every rank has joined
+template <typename F>
+void B200TreeLearner::ForEachRank(F&& f) const {
+  const int W = static_cast<int>(handles_.size());
+  if (W == 1) { f(0); return; }
+  std::vector<std::thread> th;
+  std::vector<std::string> err(W);
+  for (int r = 0; r < W; ++r) th.emplace_back([&, r]() {
+    try { f(r); } catch (const std::exception& e) { err[r] = e.what(); } catch (...) { err[r] = "unknown error"; }
+  });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < W; ++r) if (!err[r].empty()) Log::Fatal("lgbm_b200 (GPU rank %d): %s", r, err[r].c_str());
 }
 
 void B200TreeLearner::Init(const Dataset* train_data, bool is_constant_hessian) {
@@ -90,7 +122,27 @@ void B200TreeLearner::Init(const Dataset* train_data, bool is_constant_hessian) 
   // cache-resident (one thread walking a whole column would touch a new cache line of the matrix per byte).
   for (int g = 0; g < C; ++g)
     if (train_data->FeatureGroupNumBin(g) > 256) Log::Fatal("lgbm_b200: a feature group has more than 256 bins (use max_bin <= 255)");
-  std::vector<uint8_t> bins(static_cast<size_t>(num_data_) * C);
+  // feature-shard plan: contiguous runs of column groups per rank, in units of 64 columns (one histogram column-group
+  // set) while there are enough of them; inner features are numbered group by group, so a rank's features are contiguous
+  const int W = static_cast<int>(handles_.size());
+  std::vector<int> col_begin(W + 1, 0);
+  {
+    const int unit = (C >= 64 * W) ? 64 : (C >= 32 * W ? 32 : 1);
+    const int units = (C + unit - 1) / unit;
+    for (int r = 0; r < W; ++r) col_begin[r + 1] = std::min(C, (units * (r + 1) / W) * unit);
+    col_begin[W] = C;
+  }
+  feat_begin_.assign(W + 1, 0);
+  for (int r = 0; r < W; ++r) {
+    int f = feat_begin_[r];
+    while (f < num_features_ && col[f] < col_begin[r + 1]) ++f;
+    feat_begin_[r + 1] = f;
+    if (W > 1 && (col_begin[r + 1] == col_begin[r] || f == feat_begin_[r])) Log::Fatal("lgbm_b200: num_gpu = %d is more than the %d feature groups can feed", W, C);
+  }
+  std::vector<std::vector<uint8_t>> bins(W);
+  for (int r = 0; r < W; ++r) bins[r].resize(static_cast<size_t>(num_data_) * (col_begin[r + 1] - col_begin[r]));
+  std::vector<int> owner(C);
+  for (int r = 0; r < W; ++r) for (int g = col_begin[r]; g < col_begin[r + 1]; ++g) owner[g] = r;
   constexpr int kTileRows = 256;
   const int num_tiles = (num_data_ + kTileRows - 1) / kTileRows;
   bool iter_failed = false;
@@ -113,18 +165,27 @@ void B200TreeLearner::Init(const Dataset* train_data, bool is_constant_hessian) 
         const int r0 = tile * kTileRows, r1 = std::min(num_data_, r0 + kTileRows);
         for (int g = 0; g < C; ++g) {
           BinIterator* it = its[g].get();
-          for (int i = r0; i < r1; ++i) bins[static_cast<size_t>(i) * C + g] = static_cast<uint8_t>(it->RawGet(i));
+          const int r = owner[g], Cr = col_begin[r + 1] - col_begin[r], gl = g - col_begin[r];
+          uint8_t* dst = bins[r].data();
+          for (int i = r0; i < r1; ++i) dst[static_cast<size_t>(i) * Cr + gl] = static_cast<uint8_t>(it->RawGet(i));
         }
       }
     }
   }
   if (iter_failed) Log::Fatal("lgbm_b200: cannot iterate a feature group");
-  LGBMB200_Layout lay;
-  lay.num_data = num_data_; lay.num_columns = C; lay.num_features = num_features_;
-  lay.feat_column = col.data(); lay.feat_lo = lo.data(); lay.feat_num_bin = nbin.data();
-  lay.feat_most_freq_bin = mfb.data(); lay.feat_default_bin = dbin.data(); lay.feat_missing_type = miss.data();
-  lay.feat_real_index = real.data();
-  Check(LGBMB200_LearnerInit(handle_, &lay, bins.data(), is_constant_hessian ? 1 : 0));
+  for (int r = 0; r < W; ++r) {
+    const int f0 = feat_begin_[r], nf = feat_begin_[r + 1] - f0;
+    std::vector<int32_t> lcol(nf);
+    for (int f = 0; f < nf; ++f) lcol[f] = col[f0 + f] - col_begin[r];
+    LGBMB200_Layout lay;
+    lay.num_data = num_data_; lay.num_columns = col_begin[r + 1] - col_begin[r]; lay.num_features = nf;
+    lay.feat_column = lcol.data(); lay.feat_lo = lo.data() + f0; lay.feat_num_bin = nbin.data() + f0;
+    lay.feat_most_freq_bin = mfb.data() + f0; lay.feat_default_bin = dbin.data() + f0; lay.feat_missing_type = miss.data() + f0;
+    lay.feat_real_index = real.data() + f0;
+    Check(LGBMB200_LearnerInit(handles_[r], &lay, bins[r].data(), is_constant_hessian ? 1 : 0));
+    std::vector<uint8_t>().swap(bins[r]);
+  }
+  if (W > 1) Check(LGBMB200_LearnersConnectLocal(handles_.data(), W, feat_begin_.data(), /*replicate_columns=*/1));
   col_sampler_.SetTrainingData(train_data);
 }
 
@@ -133,14 +194,17 @@ void B200TreeLearner::ResetTrainingData(const Dataset* train_data, bool is_const
 }
 
 void B200TreeLearner::ResetIsConstantHessian(bool is_constant_hessian) {
-  Check(LGBMB200_LearnerSetConstantHessian(handle_, is_constant_hessian ? 1 : 0));
+  for (LGBMB200_LearnerHandle h : handles_) Check(LGBMB200_LearnerSetConstantHessian(h, is_constant_hessian ? 1 : 0));
 }
 
 void B200TreeLearner::ResetConfig(const Config* config) {
   CheckSupported(config);
   config_ = config;
-  LGBMB200_Config c = ToB200Config(config);
-  Check(LGBMB200_LearnerResetConfig(handle_, &c));
+  for (size_t r = 0; r < handles_.size(); ++r) {
+    LGBMB200_Config c = ToB200Config(config);
+    if (handles_.size() > 1 || config->gpu_device_id >= 0) c.gpu_device_id = devices_[r];
+    Check(LGBMB200_LearnerResetConfig(handles_[r], &c));
+  }
   if (train_data_ != nullptr) col_sampler_.SetConfig(config);
 }
 
@@ -153,21 +217,31 @@ Tree* B200TreeLearner::Train(const score_t* gradients, const score_t* hessians, 
   col_sampler_.ResetByTree();
   const std::vector<int8_t>& used = col_sampler_.is_feature_used_bytree();
   if (config_->feature_fraction < 1.0) {
-    Check(LGBMB200_LearnerSetFeatureMask(handle_, reinterpret_cast<const uint8_t*>(used.data())));
+    for (size_t r = 0; r < handles_.size(); ++r)
+      Check(LGBMB200_LearnerSetFeatureMask(handles_[r], reinterpret_cast<const uint8_t*>(used.data()) + feat_begin_[r]));
     mask_set_ = true;
   } else if (mask_set_) {
-    Check(LGBMB200_LearnerSetFeatureMask(handle_, nullptr));
+    for (LGBMB200_LearnerHandle h : handles_) Check(LGBMB200_LearnerSetFeatureMask(h, nullptr));
     mask_set_ = false;
   }
   const int NL = config_->num_leaves;
-  std::vector<LGBMB200_Split> splits(NL);
-  std::vector<double> leaf_value(NL), leaf_weight(NL);
-  std::vector<int32_t> leaf_count(NL), leaf_depth(NL);
-  LGBMB200_Tree t;
-  t.num_leaves = 0; t.splits = splits.data(); t.leaf_value = leaf_value.data(); t.leaf_weight = leaf_weight.data();
-  t.leaf_count = leaf_count.data(); t.leaf_depth = leaf_depth.data();
-  // host gradients (boosting_on_gpu_ == false in a non-USE_CUDA build of GBDT, gbdt.cpp:110-135)
-  Check(LGBMB200_LearnerTrain(handle_, gradients, hessians, /*on_device=*/0, &t));
+  const int W = static_cast<int>(handles_.size());
+  // every rank grows the identical tree (deterministic in-kernel exchange); rank 0's copy is replayed below
+  std::vector<std::vector<LGBMB200_Split>> r_splits(W, std::vector<LGBMB200_Split>(NL));
+  std::vector<std::vector<double>> r_value(W, std::vector<double>(NL)), r_weight(W, std::vector<double>(NL));
+  std::vector<std::vector<int32_t>> r_count(W, std::vector<int32_t>(NL)), r_depth(W, std::vector<int32_t>(NL));
+  std::vector<LGBMB200_Tree> r_tree(W);
+  // host gradients (boosting_on_gpu_ == false in a non-USE_CUDA build of GBDT, gbdt.cpp:110-135): every rank copies them
+  // to its own GPU over its own PCIe link
+  ForEachRank([&](int r) {
+    LGBMB200_Tree& tr = r_tree[r];
+    tr.num_leaves = 0; tr.splits = r_splits[r].data(); tr.leaf_value = r_value[r].data(); tr.leaf_weight = r_weight[r].data();
+    tr.leaf_count = r_count[r].data(); tr.leaf_depth = r_depth[r].data();
+    if (LGBMB200_LearnerTrain(handles_[r], gradients, hessians, /*on_device=*/0, &tr) != 0) throw std::runtime_error(LGBMB200_GetLastError());
+  });
+  const LGBMB200_Tree& t = r_tree[0];
+  const std::vector<LGBMB200_Split>& splits = r_splits[0];
+  const std::vector<double>& leaf_value = r_value[0];
   last_num_leaves_ = t.num_leaves;
 
   // replay through the reference's own Tree::Split (tree.cpp:65-79) so model text / predict are unchanged
@@ -201,7 +275,7 @@ Tree* B200TreeLearner::FitByExistingTree(const Tree*, const std::vector<int>&, c
 
 void B200TreeLearner::SetBaggingData(const Dataset* subset, const data_size_t* used_indices, data_size_t num_data) {
   if (subset != nullptr) Log::Fatal("lgbm_b200: bagging with a subset Dataset is not supported (set bagging_fraction >= 0.5 or use GOSS)");
-  Check(LGBMB200_LearnerSetBaggingData(handle_, used_indices, num_data, /*on_device=*/0));
+  for (LGBMB200_LearnerHandle h : handles_) Check(LGBMB200_LearnerSetBaggingData(h, used_indices, num_data, /*on_device=*/0));
 }
 
 void B200TreeLearner::AddPredictionToScore(const Tree* tree, double* out_score) const {

@@ -45,6 +45,14 @@ class B200TreeLearner : public TreeLearner {
   static void CheckSupported(const Config* config);
   void Check(int ret) const;
 
+  // num_gpu > 1 (config.h:1126; gpu_device_id_list :1132): features are sharded over the GPUs of this box, one
+  // library learner per device inside this process, driven by one host thread each (the shape of the reference's
+  // own multi-GPU mode, cuda_nccl_topology.hpp:177-188).  handle_ is rank 0's learner.
+  std::vector<LGBMB200_LearnerHandle> handles_;
+  std::vector<int> devices_;
+  std::vector<int> feat_begin_;          // inner feature range [feat_begin_[r], feat_begin_[r + 1]) of rank r
+  template <typename F> void ForEachRank(F&& f) const;
+
   const Config* config_;
   const Dataset* train_data_ = nullptr;
   LGBMB200_LearnerHandle handle_ = nullptr;

@@ -504,6 +504,15 @@ class Learner {
 
   // ---- feature-shard bootstrap: export this rank's CommBlock, then map every peer's
   void CommExport(uint8_t* handle_out) {
+    CommPrepare();
+    cudaIpcMemHandle_t hnd;
+    CUDA_CHECK(cudaIpcGetMemHandle(&hnd, comm_local_));
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle_out, &hnd, 64);
+  }
+  // this rank's CommBlock (allocated on first use): what peers map (CUDA IPC between processes, plain peer access
+  // between learners of one process)
+  void* CommPrepare() {
     REQUIRE(inited_, "Init first");
     const int64_t stride = ((static_cast<int64_t>(N_) + 31) / 32 * 4 + 255) / 256 * 256;
     const size_t bytes = sizeof(CommBlock) + 2 * static_cast<size_t>(stride) + sizeof(FeatMeta) * static_cast<size_t>(F_);
@@ -520,28 +529,36 @@ class Learner {
       CUDA_CHECK(cudaMemcpy(comm_meta_tail(cb, stride), feat_.p, sizeof(FeatMeta) * F_, cudaMemcpyDeviceToDevice));
       CUDA_CHECK(cudaDeviceSynchronize());
     }
-    cudaIpcMemHandle_t hnd;
-    CUDA_CHECK(cudaIpcGetMemHandle(&hnd, comm_local_));
-    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    std::memcpy(handle_out, &hnd, 64);
+    return comm_local_;
   }
   void CommConnect(int rank, int world, const uint8_t* handles, const int32_t* feature_offsets) {
     REQUIRE(comm_local_ != nullptr, "CommExport first");
     REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "bad rank/world");
-    peers_ = CommPeers{};
-    peers_.rank = rank; peers_.world = world; peers_.flags_stride = comm_stride_;
+    void* blocks[kMaxRanks] = {nullptr};
     for (int r = 0; r < world; ++r) {
-      if (r == rank) { peers_.block[r] = reinterpret_cast<CommBlock*>(comm_local_); continue; }
+      if (r == rank) { blocks[r] = comm_local_; continue; }
       cudaIpcMemHandle_t hnd;
       std::memcpy(&hnd, handles + 64 * r, 64);
       void* p = nullptr;
       CUDA_CHECK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
-      peers_.block[r] = reinterpret_cast<CommBlock*>(p);
+      blocks[r] = p;
       comm_opened_.push_back(p);
     }
+    CommConnectPtrs(rank, world, blocks, feature_offsets);
+  }
+  // blocks[r] = rank r's CommBlock, reachable from this device (IPC mapping or peer access)
+  void CommConnectPtrs(int rank, int world, void* const* blocks, const int32_t* feature_offsets) {
+    REQUIRE(comm_local_ != nullptr, "CommPrepare first");
+    REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "bad rank/world");
+    peers_ = CommPeers{};
+    peers_.rank = rank; peers_.world = world; peers_.flags_stride = comm_stride_;
+    for (int r = 0; r < world; ++r) peers_.block[r] = reinterpret_cast<CommBlock*>(r == rank ? comm_local_ : blocks[r]);
     feature_offsets_.assign(feature_offsets, feature_offsets + world + 1);
     InvalidateGraph();
   }
+  const uint8_t* ColumnsPtr() const { return binsT_.p; }
+  int device() const { return device_; }
+  int inited_device() const { return inited_ ? device_ : (cfg_.gpu_device_id >= 0 ? cfg_.gpu_device_id : -1); }
 
   // feature-shard, optional: replicate every rank's column-major partition columns on every rank
   // (C_total x N bytes of HBM per GPU), so that each rank computes the go-left flags of EVERY split itself and the
@@ -554,6 +571,24 @@ class Learner {
     std::memcpy(handle_out, &hnd, 64);
   }
   void CommShareColumns(const uint8_t* column_handles) {
+    REQUIRE(peers_.world > 1 && peers_.mode != 1, "CommConnect (feature-shard) first");
+    const int W = peers_.world;
+    const uint8_t* cols[kMaxRanks] = {nullptr};
+    std::vector<void*> opened;
+    for (int r = 0; r < W; ++r) {
+      if (r == peers_.rank) continue;
+      cudaIpcMemHandle_t hnd;
+      std::memcpy(&hnd, column_handles + 64 * r, 64);
+      void* p = nullptr;
+      CUDA_CHECK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+      opened.push_back(p);
+      cols[r] = static_cast<const uint8_t*>(p);
+    }
+    CommShareColumnsPtrs(cols);
+    for (void* p : opened) cudaIpcCloseMemHandle(p);
+  }
+  // cols[r] = rank r's column-major copy (own entry ignored), reachable from this device
+  void CommShareColumnsPtrs(const uint8_t* const* cols) {
     REQUIRE(peers_.world > 1 && peers_.mode != 1, "CommConnect (feature-shard) first");
     REQUIRE(binsT_.p != nullptr, "the column-major copy is disabled (LGBMB200_Config.reserved bit 0)");
     CUDA_CHECK(cudaStreamSynchronize(stream_));        // my own transpose has finished
@@ -569,17 +604,8 @@ class Learner {
     REQUIRE(nf[peers_.rank] == F_ && nc[peers_.rank] == C_, "own shard shape mismatch");
     binsT_full_.alloc(static_cast<size_t>(col_off[W]) * N_);
     std::vector<FeatMeta> gm(static_cast<size_t>(std::max(f_off[W], 1)));
-    std::vector<void*> opened;
     for (int r = 0; r < W; ++r) {
-      const uint8_t* src = binsT_.p;
-      if (r != peers_.rank) {
-        cudaIpcMemHandle_t hnd;
-        std::memcpy(&hnd, column_handles + 64 * r, 64);
-        void* p = nullptr;
-        CUDA_CHECK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
-        opened.push_back(p);
-        src = static_cast<const uint8_t*>(p);
-      }
+      const uint8_t* src = (r == peers_.rank) ? binsT_.p : cols[r];
       CUDA_CHECK(cudaMemcpyAsync(binsT_full_.p + static_cast<size_t>(col_off[r]) * N_, src, static_cast<size_t>(nc[r]) * N_,
                                  cudaMemcpyDefault, stream_));
       if (nf[r] > 0)
@@ -587,7 +613,6 @@ class Learner {
       for (int f = 0; f < nf[r]; ++f) gm[f_off[r] + f].col += col_off[r];
     }
     CUDA_CHECK(cudaStreamSynchronize(stream_));
-    for (void* p : opened) cudaIpcCloseMemHandle(p);
     gmeta_.alloc(gm.size());
     CUDA_CHECK(cudaMemcpy(gmeta_.p, gm.data(), sizeof(FeatMeta) * gm.size(), cudaMemcpyHostToDevice));
     peers_.mode = 2;
@@ -1045,12 +1070,23 @@ using b200::CudaError;
 using b200::Learner;
 
 #define API_BEGIN() try {
+#define API_BEGIN_H(h) try { DeviceGuard _dev_guard((h) ? static_cast<Learner*>(h)->inited_device() : -1);
 #define API_END()                                            \
   }                                                          \
   catch (const CudaError& e) { b200::g_last_error = e.msg; return -1; } \
   catch (const std::exception& e) { b200::g_last_error = e.what(); return -1; } \
   catch (...) { b200::g_last_error = "unknown error"; return -1; } \
   return 0;
+
+// Several learners (one per GPU) may live in one process (LGBMB200_LearnersConnectLocal): every entry point runs on the
+// learner's own device and restores the caller's current device afterwards.
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 extern "C" {
 
@@ -1063,176 +1099,216 @@ int LGBMB200_LearnerCreate(const LGBMB200_Config* config, LGBMB200_LearnerHandle
   API_END();
 }
 int LGBMB200_LearnerInit(LGBMB200_LearnerHandle h, const LGBMB200_Layout* layout, const uint8_t* bins_host, int32_t is_constant_hessian) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !layout || !bins_host) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->Init(*layout, bins_host, is_constant_hessian);
   API_END();
 }
 int LGBMB200_LearnerResetConfig(LGBMB200_LearnerHandle h, const LGBMB200_Config* config) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !config) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->SetConfig(*config);
   API_END();
 }
 int LGBMB200_LearnerSetConstantHessian(LGBMB200_LearnerHandle h, int32_t is_constant_hessian) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->SetConstantHessian(is_constant_hessian);
   API_END();
 }
 int LGBMB200_LearnerSetFeatureMask(LGBMB200_LearnerHandle h, const uint8_t* feature_used) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->SetFeatureMask(feature_used);
   API_END();
 }
 int LGBMB200_LearnerSetBaggingData(LGBMB200_LearnerHandle h, const int32_t* used_indices, int32_t num_used, int32_t on_device) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->SetBagging(used_indices, num_used, on_device);
   API_END();
 }
 int LGBMB200_LearnerGossSample(LGBMB200_LearnerHandle h, float* grad_dev, float* hess_dev, double top_rate, double other_rate,
                                int32_t seed, int32_t iteration, int32_t* out_bag_count) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !grad_dev || !hess_dev) throw CudaError{"null argument"};
   const int32_t n = static_cast<Learner*>(h)->GossSample(grad_dev, hess_dev, top_rate, other_rate, seed, iteration);
   if (out_bag_count) *out_bag_count = n;
   API_END();
 }
 int LGBMB200_LearnerGetBaggingData(LGBMB200_LearnerHandle h, int32_t* indices_host, int32_t num_indices) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !indices_host) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->GetBag(indices_host, num_indices);
   API_END();
 }
 int LGBMB200_LearnerTrain(LGBMB200_LearnerHandle h, const float* gradients, const float* hessians, int32_t on_device, LGBMB200_Tree* out_tree) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !gradients || !hessians || !out_tree) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->Train(gradients, hessians, on_device, out_tree);
   API_END();
 }
 int LGBMB200_LearnerAddPredictionToScore(LGBMB200_LearnerHandle h, const double* leaf_value, int32_t num_leaves, double* score, int32_t on_device) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !leaf_value || !score) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->AddPredictionToScore(leaf_value, num_leaves, score, on_device);
   API_END();
 }
 int LGBMB200_LearnerAddPredictionAllRows(LGBMB200_LearnerHandle h, const double* leaf_value, int32_t num_leaves, double* score_dev) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !leaf_value || !score_dev) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->RouteAllRows(leaf_value, num_leaves, score_dev, nullptr);
   API_END();
 }
 int LGBMB200_LearnerGetPartition(LGBMB200_LearnerHandle h, int32_t* leaf_begin, int32_t* leaf_count, int32_t* indices) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !leaf_begin || !leaf_count || !indices) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->GetPartition(leaf_begin, leaf_count, indices);
   API_END();
 }
 int LGBMB200_LearnerGetLeafHistogram(LGBMB200_LearnerHandle h, int32_t leaf, double* out) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !out) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->GetLeafHistogram(leaf, out);
   API_END();
 }
 int LGBMB200_LearnerConstructHistogram(LGBMB200_LearnerHandle h, const float* gradients, const float* hessians, int32_t on_device,
                                        const int32_t* indices_host, int32_t num_indices, double* hist_out, float* elapsed_ms) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !gradients || !hessians) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->ConstructHistogram(gradients, hessians, on_device, indices_host, num_indices, hist_out, elapsed_ms);
   API_END();
 }
 int LGBMB200_L2Gradients(LGBMB200_LearnerHandle h, const double* score_dev, const float* label_dev, float* grad_dev, float* hess_dev, int32_t n) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->L2Gradients(score_dev, label_dev, grad_dev, hess_dev, n);
   API_END();
 }
 int LGBMB200_BinaryGradients(LGBMB200_LearnerHandle h, const double* score_dev, const float* label_dev, float* grad_dev, float* hess_dev,
                              int32_t n, double sigmoid) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->BinaryGradients(score_dev, label_dev, grad_dev, hess_dev, n, sigmoid);
   API_END();
 }
 int64_t LGBMB200_LearnerKernelLaunches(LGBMB200_LearnerHandle h) { return h ? static_cast<Learner*>(h)->launches() : 0; }
 int LGBMB200_LearnerHistStats(LGBMB200_LearnerHandle h, int32_t reset, double* hist_ms, double* hist_rows, int64_t* hist_launches) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->HistStats(reset, hist_ms, hist_rows, hist_launches);
   API_END();
 }
 int LGBMB200_LearnerProfileByKind(LGBMB200_LearnerHandle h, double* ms_out_9) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !ms_out_9) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->ProfileByKind(ms_out_9);
   API_END();
 }
 int LGBMB200_LearnerSetProfiling(LGBMB200_LearnerHandle h, int32_t enable) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->SetProfiling(enable);
   API_END();
 }
 int LGBMB200_LearnerCommExport(LGBMB200_LearnerHandle h, uint8_t* handle_out_64) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !handle_out_64) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->CommExport(handle_out_64);
   API_END();
 }
 int LGBMB200_LearnerCommConnect(LGBMB200_LearnerHandle h, int32_t rank, int32_t world, const uint8_t* all_handles,
                                 const int32_t* feature_offsets) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !all_handles || !feature_offsets) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->CommConnect(rank, world, all_handles, feature_offsets);
   API_END();
 }
-int LGBMB200_LearnerCommExportColumns(LGBMB200_LearnerHandle h, uint8_t* handle_out_64) {
+// Feature-shard bootstrap for `world` learners that live in ONE process, one per GPU (the reference's own multi-GPU
+// shape: one host thread per device, include/LightGBM/cuda/cuda_nccl_topology.hpp:177-188): peer access instead of CUDA
+// IPC.  handles[r] = the learner of rank r, already Init-ed with its column slice.
+int LGBMB200_LearnersConnectLocal(LGBMB200_LearnerHandle* handles, int32_t world, const int32_t* feature_offsets, int32_t replicate_columns) {
   API_BEGIN();
+  if (!handles || !feature_offsets || world < 1 || world > b200::kMaxRanks) throw CudaError{"bad argument"};
+  int prev = 0;
+  CUDA_CHECK(cudaGetDevice(&prev));
+  std::vector<Learner*> L(world);
+  std::vector<void*> blocks(world);
+  for (int r = 0; r < world; ++r) {
+    if (!handles[r]) throw CudaError{"null learner"};
+    L[r] = static_cast<Learner*>(handles[r]);
+    CUDA_CHECK(cudaSetDevice(L[r]->device()));
+    blocks[r] = L[r]->CommPrepare();
+  }
+  for (int i = 0; i < world; ++i) {
+    CUDA_CHECK(cudaSetDevice(L[i]->device()));
+    for (int j = 0; j < world; ++j) {
+      if (L[j]->device() == L[i]->device()) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(L[j]->device(), 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) { cudaSetDevice(prev); throw CudaError{std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)}; }
+    }
+  }
+  for (int r = 0; r < world; ++r) {
+    CUDA_CHECK(cudaSetDevice(L[r]->device()));
+    L[r]->CommConnectPtrs(r, world, blocks.data(), feature_offsets);
+  }
+  if (replicate_columns && world > 1) {
+    std::vector<const uint8_t*> cols(world);
+    for (int r = 0; r < world; ++r) cols[r] = L[r]->ColumnsPtr();
+    for (int r = 0; r < world; ++r) {
+      CUDA_CHECK(cudaSetDevice(L[r]->device()));
+      L[r]->CommShareColumnsPtrs(cols.data());
+    }
+  }
+  CUDA_CHECK(cudaSetDevice(prev));
+  API_END();
+}
+int LGBMB200_LearnerCommExportColumns(LGBMB200_LearnerHandle h, uint8_t* handle_out_64) {
+  API_BEGIN_H(h);
   REQUIRE(h && handle_out_64, "null argument");
   static_cast<Learner*>(h)->CommExportColumns(handle_out_64);
   API_END();
 }
 int LGBMB200_LearnerCommShareColumns(LGBMB200_LearnerHandle h, const uint8_t* all_column_handles) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   REQUIRE(h && all_column_handles, "null argument");
   static_cast<Learner*>(h)->CommShareColumns(all_column_handles);
   API_END();
 }
 int LGBMB200_LearnerCommExportPool(LGBMB200_LearnerHandle h, uint8_t* handle_out_64) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !handle_out_64) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->CommExportPool(handle_out_64);
   API_END();
 }
 int LGBMB200_LearnerCommConnectRows(LGBMB200_LearnerHandle h, int32_t rank, int32_t world, const uint8_t* comm_handles,
                                     const uint8_t* pool_handles) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !comm_handles || !pool_handles) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->CommConnectRows(rank, world, comm_handles, pool_handles);
   API_END();
 }
 int LGBMB200_LearnerGetLeafIndex(LGBMB200_LearnerHandle h, int32_t* leaf_index_host) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !leaf_index_host) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->GetLeafIndex(leaf_index_host);
   API_END();
 }
 int LGBMB200_LearnerGetLeafIndexRange8(LGBMB200_LearnerHandle h, int32_t row_lo, int32_t row_hi, uint8_t* leaf_index_host) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !leaf_index_host) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->GetLeafIndexRange8(row_lo, row_hi, leaf_index_host);
   API_END();
 }
 int LGBMB200_LearnerTimerStart(LGBMB200_LearnerHandle h) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h) throw CudaError{"null argument"};
   static_cast<Learner*>(h)->TimerStart();
   API_END();
 }
 int LGBMB200_LearnerTimerStop(LGBMB200_LearnerHandle h, float* elapsed_ms) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   if (!h || !elapsed_ms) throw CudaError{"null argument"};
   *elapsed_ms = static_cast<Learner*>(h)->TimerStop();
   API_END();
@@ -1270,7 +1346,7 @@ int LGBMB200_MemcpyD2H(void* dst_host, const void* src_dev, int64_t bytes) {
   API_END();
 }
 int LGBMB200_LearnerFree(LGBMB200_LearnerHandle h) {
-  API_BEGIN();
+  API_BEGIN_H(h);
   delete static_cast<Learner*>(h);
   API_END();
 }

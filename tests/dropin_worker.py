@@ -32,6 +32,8 @@ def main():
     ds = refapi.RefDataset(X, y, dsp)
     bp = dict(dsp, objective=obj, num_leaves=31, learning_rate=0.1, min_data_in_leaf=20, device_type=device,
               force_row_wise="true", deterministic="true", num_threads=1 if device == "cpu" else 4)
+    if device == "cuda" and int(os.environ.get("DROPIN_NUM_GPU", "1")) > 1:
+        bp["num_gpu"] = int(os.environ["DROPIN_NUM_GPU"])      # features sharded over the GPUs of this box, one process
     if quant:
         bp.update(use_quantized_grad="true", stochastic_rounding="false", num_grad_quant_bins=4 if case == "identity" else 8,
                   quant_train_renew_leaf="false" if case == "identity" else "true")

@@ -16,8 +16,8 @@ DROPIN = os.path.join(ROOT, "integration", "_build", "lib_lightgbm.so")
 REFLIB = os.path.join(ROOT, "oracle", "_ref", "lib_lightgbm.so")
 
 
-def run(lib, device, n, f, iters, case):
-    env = dict(os.environ, LGBM_REF_LIB=lib)
+def run(lib, device, n, f, iters, case, num_gpu=1):
+    env = dict(os.environ, LGBM_REF_LIB=lib, DROPIN_NUM_GPU=str(num_gpu))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_worker.py"), device, str(n), str(f), str(iters), case],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -57,3 +57,32 @@ def test_lgbm_capi_quantized_training_matches_reference_cpu(case, n, f):
     np.testing.assert_allclose(g0["split_gain"], c0["split_gain"], rtol=1e-6)      # stored as float32 text
     np.testing.assert_allclose(g0["leaf_value"], c0["leaf_value"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(gpu["pred"], cpu["pred"], rtol=2e-3, atol=2e-3)
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(not (os.path.exists(DROPIN) and os.path.exists(REFLIB)), reason="drop-in / reference library not built")
+@pytest.mark.parametrize("case,n,f", [("identity", 30000, 96), ("mixed", 20000, 70)])
+def test_lgbm_capi_num_gpu_2_matches_single_gpu_and_reference(case, n, f):
+    """device_type=cuda, num_gpu=2 through the real LGBM_* API: the adapter shards the feature groups over two library
+    learners inside ONE process (LGBMB200_LearnersConnectLocal, one host thread per GPU) — the model must equal the
+    single-GPU drop-in's bit for bit and the reference CPU learner's first tree."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    iters = 4
+    two = run(DROPIN, "cuda", n, f, iters, case, num_gpu=2)
+    one = run(DROPIN, "cuda", n, f, iters, case, num_gpu=1)
+    cpu = run(REFLIB, "cpu", n, f, iters, case)
+    assert two["num_trees"] == one["num_trees"] == iters
+    for a, b in zip(two["trees"], one["trees"]):
+        assert a == b                                   # integer histograms: sharding cannot change a single bit
+    g0, c0 = two["trees"][0], cpu["trees"][0]
+    k = min(8, len(c0["split_feature"]))
+    assert g0["split_feature"][:k] == c0["split_feature"][:k]
+    np.testing.assert_allclose(two["pred"], cpu["pred"], rtol=2e-3, atol=2e-3)
