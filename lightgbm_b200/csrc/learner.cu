@@ -75,7 +75,7 @@ class Learner {
   // Developer A/B switches (not part of the boundary): LGBMB200_DEBUG is a bit mask read once per process.
   //   1: no column-major copy for the partition   2: no TMA staging   16: programmatic dependent launch on the chain
   //   32: k_select folded into k_scan's last block   64: quantized training never uses the packed-cell kernel
-  //   256: no leaf-ordered (g,h) copies   512: partition as two launches (flags, scatter) instead of the fused cooperative one
+  //   256: no leaf-ordered (g,h) copies
   static int DebugBits() {
     static const int bits = std::getenv("LGBMB200_DEBUG") ? std::atoi(std::getenv("LGBMB200_DEBUG")) : 0;
     return bits;
@@ -885,18 +885,14 @@ class Learner {
     for (int it = 0; it < NL - 1 + 1; ++it) {
       // it == 0: root pass; it >= 1: apply split it-1, then find splits for its two children
       if (it > 0) {
-        if ((peers_.world > 1 && peers_.mode == 0) || (DebugBits() & 512)) {
-          // the split's owner computes the go-left bits and pushes them: two launches (only the owner runs the first)
-          LaunchChain(true, k_part_flags, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
-          Stamp(kProfPartFlags);
-          LaunchChain(true, k_part_scatter, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
-          Stamp(kProfPartScatter);
-          launches_ += 2;
-        } else {
-          LaunchChainEx(true, true, k_partition, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
-          Stamp(kProfPartScatter);
-          ++launches_;
-        }
+        // (a single cooperative launch with a grid-wide barrier between the two phases was measured on 2M x 1024 x 127
+        // leaves: 12.82 ms per tree against 12.72 ms for the two launches — under graph replay a launch boundary costs
+        // no more than the barrier — and was not kept)
+        LaunchChain(true, k_part_flags, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
+        Stamp(kProfPartFlags);
+        LaunchChain(true, k_part_scatter, dim3(part_blocks_), dim3(kPartThreads), 0, pt);
+        Stamp(kProfPartScatter);
+        launches_ += 2;
         if (it == NL - 1) break;   // the tree is full: no need to look for further splits
       }
       LaunchHist(ha, qa, it > 0);   // it == 0 follows a memset node: plain dependency

@@ -308,32 +308,6 @@ __global__ void __launch_bounds__(kPartThreads) k_part_scatter(const PartArgs a)
   part_scatter_body(a);
 }
 
-// Both phases in ONE cooperative launch (all blocks co-resident): flags + per-block counts, a grid-wide barrier on a
-// monotonic counter in the control block, then the scatter and the SplitInner bookkeeping.  One launch boundary per split
-// less on the critical path.  Used whenever every rank computes its own flags (single GPU, replicated partition columns,
-// row-shard); the owner-pushes-flags mode keeps the two launches (only the owner runs the first).
-__global__ void __launch_bounds__(kPartThreads) k_partition(const PartArgs a) {
-  pdl_enter();
-  Ctl* c = a.ctl;
-  if (!c->cur_valid) return;             // uniform over the grid: nobody reaches the barrier
-  part_flags_body(a);
-  __shared__ unsigned s_target;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned old = atomicAdd(&c->part_barrier, 1u);
-    const unsigned target = (old / gridDim.x + 1u) * gridDim.x;
-    long long t0 = clock64();
-    while (*reinterpret_cast<volatile unsigned*>(&c->part_barrier) < target) {
-      if (clock64() - t0 > kWatchdogCycles) { c->error = 1; break; }
-    }
-    s_target = target;
-    __threadfence();
-  }
-  __syncthreads();
-  part_scatter_body(a);
-}
-
 // One-off at Init: column-major copy of the bin matrix (32x32 byte tiles through shared memory)
 __global__ void __launch_bounds__(256) k_transpose_bins(const uint8_t* __restrict__ bins, int64_t pitch, int64_t N, int C,
                                                         uint8_t* __restrict__ binsT) {

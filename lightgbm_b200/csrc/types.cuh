@@ -91,7 +91,6 @@ struct Ctl {
   unsigned long long xchg_seq; // number of candidate exchanges done so far (mailbox sequence)
   unsigned long long flag_seq; // number of flag pushes done so far
   uint32_t part_blocks_done;   // last-block detection in k_part_flags
-  uint32_t part_barrier;       // k_partition: monotonic arrival counter of its grid-wide barrier (never reset)
   uint32_t scan_done;          // last-block detection in k_scan (fused selection)
   unsigned long long hist_seq; // row-shard: number of "my local histogram is complete" signals sent
   unsigned long long misc_seq; // row-shard: number of small all-gathers (root sums, left counts) done
