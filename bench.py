@@ -372,7 +372,7 @@ def run_reference(args, wl, rank, world, device="cpu", dropin=False):
     if rank != 0:
         return None
     if dropin:
-        os.environ["LGBM_REF_LIB"] = os.path.join(ROOT, "integration", "_build", "lib_lightgbm.so")
+        os.environ["LGBM_REF_LIB"] = os.path.join(ROOT, "integration", "_build_cuda" if dropin == "device" else "_build", "lib_lightgbm.so")
     elif device == "cuda":
         os.environ["LGBM_REF_LIB"] = os.path.join(ROOT, "oracle", "_ref", "cuda", "lib_lightgbm.so")
     from oracle import refapi
@@ -396,7 +396,10 @@ def run_reference(args, wl, rank, world, device="cpu", dropin=False):
     trees = bst.trees()
     bst.free()
     ds.free()
-    kind = ("this repo's learner behind the reference's LGBM_* C API (integration/_build/lib_lightgbm.so, device_type=cuda; "
+    kind = ("this repo's learner behind the reference's LGBM_* C API, linked against the -DUSE_CUDA reference host code "
+            "(integration/_build_cuda/lib_lightgbm.so): the reference's CUDA objective and score updater keep gradients and scores "
+            "in HBM (boosting_on_gpu_), nothing crosses PCIe per iteration" if dropin == "device" else
+            "this repo's learner behind the reference's LGBM_* C API (integration/_build/lib_lightgbm.so, device_type=cuda; "
             "host objective and score, gradients H2D and leaf ids D2H every iteration)" if dropin else
             "the reference's own CUDA learner (src/treelearner/cuda, -DUSE_CUDA, sm_100), boosting on the GPU" if device == "cuda"
             else "the reference's OpenMP CPU learner, col/row-wise chosen by its own auto-timing")
@@ -463,7 +466,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference_cuda", "dropin"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference_cuda", "dropin", "dropin_device"])
     ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "C3"), choices=list(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override rows (debug only; makes the number INVALID)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -496,9 +499,9 @@ def main():
               "l2_flush": (f"inputs larger than L2 (bin matrix {wl['rows'] * wl_columns(wl) / 1e9:.2f} GB >> 126 MB)"
                            if wl["rows"] * wl_columns(wl) > 2e8 else "bin matrix smaller than L2: L2 flushed by the per-tree 8 B/row gradient pass only")}
 
-    if args.impl in ("reference", "reference_cuda", "dropin"):
+    if args.impl in ("reference", "reference_cuda", "dropin", "dropin_device"):
         dev = "cpu" if args.impl == "reference" else "cuda"
-        r = run_reference(args, wl, rank, world, dev, dropin=args.impl == "dropin")
+        r = run_reference(args, wl, rank, world, dev, dropin={"dropin": "host", "dropin_device": "device"}.get(args.impl, False))
         if rank == 0:
             if "unavailable" in r:
                 print(json.dumps({"impl": args.impl, "unavailable": r["unavailable"]}), flush=True)
@@ -509,7 +512,7 @@ def main():
                     "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                     "scaling": "strong", "vs_baseline": None,
                     "dtype": ("f64 histograms (fp32 grad/hess)" if dev == "cpu" else
-                              "30-bit fixed-point (g,h) -> exact int32 shared-memory atomics -> int64 histograms" if args.impl == "dropin" else
+                              "30-bit fixed-point (g,h) -> exact int32 shared-memory atomics -> int64 histograms" if args.impl.startswith("dropin") else
                               "fp32 shared-memory atomics -> f64 histograms (gpu_use_dp=false)"),
                     "data": "synthetic", "config": config,
                     "cpu_baseline": {"value": r["value"], "unit": "iters/sec", "cores": r["cores"], "kind": "reference",

@@ -58,7 +58,8 @@ void B200TreeLearner::CheckSupported(const Config* config) {
   if (config->max_bin > 255) Log::Fatal("lgbm_b200: max_bin > 255 is not supported");
 }
 
-B200TreeLearner::B200TreeLearner(const Config* config) : config_(config), col_sampler_(config) {
+B200TreeLearner::B200TreeLearner(const Config* config, bool boosting_on_cuda)
+    : config_(config), col_sampler_(config), on_device_(boosting_on_cuda) {
   CheckSupported(config);
   // devices: gpu_device_id_list ("0,1,2,...") if given, else gpu_device_id .. gpu_device_id + num_gpu - 1
   const int W = std::max(1, config->num_gpu);
@@ -231,13 +232,14 @@ Tree* B200TreeLearner::Train(const score_t* gradients, const score_t* hessians, 
   std::vector<std::vector<double>> r_value(W, std::vector<double>(NL)), r_weight(W, std::vector<double>(NL));
   std::vector<std::vector<int32_t>> r_count(W, std::vector<int32_t>(NL)), r_depth(W, std::vector<int32_t>(NL));
   std::vector<LGBMB200_Tree> r_tree(W);
-  // host gradients (boosting_on_gpu_ == false in a non-USE_CUDA build of GBDT, gbdt.cpp:110-135): every rank copies them
-  // to its own GPU over its own PCIe link
+  // host gradients (boosting_on_gpu_ == false: always so in a non-USE_CUDA build of GBDT, gbdt.cpp:110-135): every rank
+  // copies them to its own GPU over its own PCIe link; device gradients (USE_CUDA build, CUDA objective) are read in place
+  const int on_dev = on_device_ ? 1 : 0;
   ForEachRank([&](int r) {
     LGBMB200_Tree& tr = r_tree[r];
     tr.num_leaves = 0; tr.splits = r_splits[r].data(); tr.leaf_value = r_value[r].data(); tr.leaf_weight = r_weight[r].data();
     tr.leaf_count = r_count[r].data(); tr.leaf_depth = r_depth[r].data();
-    if (LGBMB200_LearnerTrain(handles_[r], gradients, hessians, /*on_device=*/0, &tr) != 0) throw std::runtime_error(LGBMB200_GetLastError());
+    if (LGBMB200_LearnerTrain(handles_[r], gradients, hessians, on_dev, &tr) != 0) throw std::runtime_error(LGBMB200_GetLastError());
   });
   const LGBMB200_Tree& t = r_tree[0];
   const std::vector<LGBMB200_Split>& splits = r_splits[0];
@@ -275,14 +277,19 @@ Tree* B200TreeLearner::FitByExistingTree(const Tree*, const std::vector<int>&, c
 
 void B200TreeLearner::SetBaggingData(const Dataset* subset, const data_size_t* used_indices, data_size_t num_data) {
   if (subset != nullptr) Log::Fatal("lgbm_b200: bagging with a subset Dataset is not supported (set bagging_fraction >= 0.5 or use GOSS)");
-  for (LGBMB200_LearnerHandle h : handles_) Check(LGBMB200_LearnerSetBaggingData(h, used_indices, num_data, /*on_device=*/0));
+#ifdef USE_CUDA
+  const int idx_on_dev = 1;       // a -DUSE_CUDA GBDT hands the bag as a device array (bagging.hpp:110-111, goss.hpp:50-51)
+#else
+  const int idx_on_dev = 0;
+#endif
+  for (LGBMB200_LearnerHandle h : handles_) Check(LGBMB200_LearnerSetBaggingData(h, used_indices, num_data, idx_on_dev));
 }
 
 void B200TreeLearner::AddPredictionToScore(const Tree* tree, double* out_score) const {
   if (tree->num_leaves() <= 1) return;
   std::vector<double> lv(tree->num_leaves());
   for (int i = 0; i < tree->num_leaves(); ++i) lv[i] = tree->LeafOutput(i);
-  Check(LGBMB200_LearnerAddPredictionToScore(handle_, lv.data(), tree->num_leaves(), out_score, /*on_device=*/0));
+  Check(LGBMB200_LearnerAddPredictionToScore(handle_, lv.data(), tree->num_leaves(), out_score, on_device_ ? 1 : 0));
 }
 
 void B200TreeLearner::RenewTreeOutput(Tree* tree, const ObjectiveFunction* obj,

@@ -22,11 +22,12 @@ namespace LightGBM {
 
 class B200TreeLearner : public TreeLearner {
  public:
-  explicit B200TreeLearner(const Config* config);
+  explicit B200TreeLearner(const Config* config, bool boosting_on_cuda = false);
   ~B200TreeLearner() override;
 
   void Init(const Dataset* train_data, bool is_constant_hessian) override;
   void ResetIsConstantHessian(bool is_constant_hessian) override;
+  void ResetBoostingOnGPU(const bool boosting_on_gpu) override { on_device_ = boosting_on_gpu; }
   void ResetTrainingData(const Dataset* train_data, bool is_constant_hessian) override;
   void ResetConfig(const Config* config) override;
   void SetForcedSplit(const Json* forced_split_json) override;
@@ -61,6 +62,9 @@ class B200TreeLearner : public TreeLearner {
   int num_features_ = 0;
   int last_num_leaves_ = 0;
   bool mask_set_ = false;
+  // boosting_on_gpu_ of GBDT (gbdt.cpp:110-135; only ever true in a -DUSE_CUDA build of the reference host code, whose
+  // CUDA objectives and CUDAScoreUpdater then hand DEVICE gradients / scores to Train / AddPredictionToScore)
+  bool on_device_ = false;
 };
 
 }  // namespace LightGBM

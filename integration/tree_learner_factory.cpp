@@ -15,9 +15,9 @@
 namespace LightGBM {
 
 TreeLearner* TreeLearner::CreateTreeLearner(const std::string& learner_type, const std::string& device_type,
-                                            const Config* config, const bool /*boosting_on_cuda*/) {
+                                            const Config* config, const bool boosting_on_cuda) {
   if (device_type == "cuda") {
-    if (learner_type == "serial") return new B200TreeLearner(config);
+    if (learner_type == "serial") return new B200TreeLearner(config, boosting_on_cuda);
     Log::Fatal("lgbm_b200 supports tree_learner=serial on a single machine (multi-GPU is configured through num_gpu).");
   }
   const bool gpu = device_type == "gpu";

@@ -86,3 +86,23 @@ def test_lgbm_capi_num_gpu_2_matches_single_gpu_and_reference(case, n, f):
     k = min(8, len(c0["split_feature"]))
     assert g0["split_feature"][:k] == c0["split_feature"][:k]
     np.testing.assert_allclose(two["pred"], cpu["pred"], rtol=2e-3, atol=2e-3)
+
+
+DROPIN_CUDA = os.path.join(ROOT, "integration", "_build_cuda", "lib_lightgbm.so")
+
+
+@pytest.mark.skipif(not (os.path.exists(DROPIN_CUDA) and os.path.exists(REFLIB)), reason="device-resident drop-in / reference library not built")
+@pytest.mark.parametrize("case,n,f", [("identity", 20000, 12), ("mixed", 20000, 10)])
+def test_device_resident_dropin_matches_reference_cpu(case, n, f):
+    """The adapter linked against the -DUSE_CUDA build of the reference host code (integration/Makefile `cuda`): the
+    reference's own CUDA objective and CUDAScoreUpdater keep gradients and scores on the device and call
+    B200TreeLearner::Train / AddPredictionToScore with DEVICE pointers (boosting_on_gpu_, gbdt.cpp:110-135)."""
+    iters = 5
+    gpu = run(DROPIN_CUDA, "cuda", n, f, iters, case)
+    cpu = run(REFLIB, "cpu", n, f, iters, case)
+    assert gpu["num_trees"] == cpu["num_trees"] == iters
+    g0, c0 = gpu["trees"][0], cpu["trees"][0]
+    k = min(8, len(c0["split_feature"]))
+    assert g0["split_feature"][:k] == c0["split_feature"][:k]
+    np.testing.assert_allclose(g0["threshold"][:k], c0["threshold"][:k], rtol=1e-9)
+    np.testing.assert_allclose(gpu["pred"], cpu["pred"], rtol=2e-3, atol=2e-3)
