@@ -87,27 +87,14 @@ struct HistAArgs {
   int32_t* blk_count;             // [num_leaves][sets] blocks claimed per (histogram pass of the tree, set); zeroed once per tree
   int32_t blk_cap;
   int32_t num_colgroups;          // pitch / 32
-  int32_t min_rows_per_cta;       // small leaves: do not spread the (column set x rows) work over more CTAs than this allows
+  float split_k;                  // work-split constant: CTA groups = sqrt(split_k * rows * set groups), see a_work_setup
   int32_t use_tma;                // 1: contiguous (root, un-bagged) stages are staged by TMA tile copies
   int32_t l2_prefetch;            // > 0: gathered passes prefetch the rows of the stage this many stages ahead into L2
-  int32_t use_gather4;            // 1: gathered stages are moved by TMA tile::gather4 (four row ids per instruction)
   // explicit mode (stand-alone ConstructHistogram hook): explicit_n >= 0
   int32_t explicit_n;
   int32_t explicit_slot;
   const int32_t* explicit_idx;    // nullptr = identity
 };
-
-constexpr int kOobRow = 0x40000000;      // any row coordinate >= num_data: the TMA unit zero-fills that row
-// tx bytes registered separately from the arrivals (the 32 arrivals of a gathered stage come from the lanes' cp.async)
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(bytes) : "memory");
-}
-// four rows {r0..r3} x box_w columns starting at column `col` -> [4][box_w] in shared memory (UTMALDG.2D.GATHER4)
-__device__ __forceinline__ void tma_gather4_2d(unsigned smem_dst, const CUtensorMap* tmap, int col, int r0, int r1, int r2, int r3, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-               ::"r"(smem_dst), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3),
-                 "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))) : "memory");
-}
 
 __device__ __forceinline__ void red_s32(unsigned addr, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds_u32(unsigned addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
@@ -148,9 +135,11 @@ __device__ __forceinline__ bool a_work_setup(const HistAArgs& a, AWork* w) {
   const int set_groups = (sets + Q - 1) / Q;
   w->spc = (w->n + kARows - 1) / kARows;
   const long long total = static_cast<long long>(set_groups) * w->spc;
-  // CTA groups that take part: all of them unless the leaf is so small that the per-CTA fixed cost (table dump + its
-  // share of the reduce) would dominate; never fewer than one per set group
-  long long P = (static_cast<long long>(set_groups) * w->n + a.min_rows_per_cta - 1) / a.min_rows_per_cta;
+  // CTA groups that take part.  Accumulating costs ~t_row per (row, set group) and is divided by P; every group adds a
+  // fixed cost t_blk (its table dumps + their share of k_hist_reduce): T(P) = W t_row / P + P t_blk, W = n * set_groups,
+  // is smallest at P* = sqrt(W t_row / t_blk).  a.split_k = t_row / t_blk (measured ~0.044 for the constant-hessian
+  // kernel: 5.6 ns per row against 128 ns per group).  Never fewer than one group per set group, at most grid / Q.
+  long long P = static_cast<long long>(sqrtf(a.split_k * static_cast<float>(w->n) * static_cast<float>(set_groups)) + 0.5f);
   if (P < set_groups) P = set_groups;
   const long long max_groups = static_cast<long long>(gridDim.x) / Q;
   if (P > max_groups) P = max_groups;
@@ -183,8 +172,7 @@ __device__ __forceinline__ void a_dump_zero(unsigned char* smem, unsigned char* 
 __device__ __forceinline__ int a_epoch(const HistAArgs& a) { return a.explicit_n >= 0 ? 0 : a.ctl->num_leaves - 1; }
 
 template <bool CH>
-__global__ void __launch_bounds__(kAThreads, 1) k_hist_a(const HistAArgs a, const __grid_constant__ CUtensorMap tmap,
-                                                         const __grid_constant__ CUtensorMap tmap_g4) {
+__global__ void __launch_bounds__(kAThreads, 1) k_hist_a(const HistAArgs a, const __grid_constant__ CUtensorMap tmap) {
   using S = AShape<CH>;
   constexpr int G = S::G, NS = S::kStages;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -245,24 +233,15 @@ __global__ void __launch_bounds__(kAThreads, 1) k_hist_a(const HistAArgs a, cons
         int rid = -1;
         if (lane < cnt) rid = ip ? __ldg(ip + p0 + lane) : p0 + lane;
         mbar_wait_parked(empty + slot, par ^ 1);           // the consumer released this ring slot
-        if (a.use_gather4) {
-          // eight tile::gather4 instructions move the stage's 32 row segments (rows past the leaf's end: an out-of-range
-          // coordinate, zero-filled); their bytes complete on the stage's mbarrier next to the lanes' (g,h) copies
-          const int r0 = __shfl_sync(0xffffffffu, rid, (lane & 7) * 4), r1 = __shfl_sync(0xffffffffu, rid, (lane & 7) * 4 + 1);
-          const int r2 = __shfl_sync(0xffffffffu, rid, (lane & 7) * 4 + 2), r3 = __shfl_sync(0xffffffffu, rid, (lane & 7) * 4 + 3);
-          if (lane == 0) mbar_expect_tx(full + slot, kARows * S::kRowBytes);
-          __syncwarp();
-          if (lane < 8)
-            tma_gather4_2d(static_cast<unsigned>(__cvta_generic_to_shared(sb)) + lane * 4 * S::kRowBytes, &tmap_g4, set * S::kRowBytes,
-                           r0 >= 0 ? r0 : kOobRow, r1 >= 0 ? r1 : kOobRow, r2 >= 0 ? r2 : kOobRow, r3 >= 0 ? r3 : kOobRow, full + slot);
-        } else {
+        // (TMA tile::gather4 — four row ids per instruction, UTMALDG.2D.GATHER4 — was built, parity-checked and timed here
+        // in round 2: 1.84 ms against 1.62 ms for these cp.async on a 2M-row gathered pass of 4M x 1024, 3.34 against
+        // 2.70 ms for the general kernel: 32/64-byte rows are too small for the TMA unit.  Not kept.)
 #pragma unroll
-          for (int i = 0; i < 2 * G; ++i) {
-            const int c = lane + 32 * i;
-            const int row = c / (2 * G), part = c % (2 * G);
-            const int r = __shfl_sync(0xffffffffu, rid, row);
-            if (r >= 0) cp_async16(sb + row * S::kRowBytes + part * 16, colbase + static_cast<int64_t>(r) * a.pitch + part * 16);
-          }
+        for (int i = 0; i < 2 * G; ++i) {
+          const int c = lane + 32 * i;
+          const int row = c / (2 * G), part = c % (2 * G);
+          const int r = __shfl_sync(0xffffffffu, rid, row);
+          if (r >= 0) cp_async16(sb + row * S::kRowBytes + part * 16, colbase + static_cast<int64_t>(r) * a.pitch + part * 16);
         }
         if (rid >= 0) cp_async8(sb + kARows * S::kRowBytes + lane * 8, w.gq_ord != nullptr ? w.gq_ord + p0 + lane : a.gq + rid);
         mbar_arrive_on_cp_async(full + slot);

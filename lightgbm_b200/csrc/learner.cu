@@ -731,15 +731,13 @@ class Learner {
     ha.leaves = leaves_.p; ha.ctl = ctl_.p; ha.pool = reinterpret_cast<unsigned long long*>(pool_.p);
     ha.slot_stride = slot_stride_; ha.num_colgroups = Cpad_ / kColGroup;
     ha.scratch = scratch_.p; ha.blk_count = blk_count_.p; ha.blk_cap = blk_cap_;
-    static const int min_rows = std::getenv("LGBMB200_MIN_ROWS") ? std::atoi(std::getenv("LGBMB200_MIN_ROWS")) : 2048;
-    ha.min_rows_per_cta = std::max(32, min_rows);
+    static const float split_k = std::getenv("LGBMB200_SPLIT_K") ? static_cast<float>(std::atof(std::getenv("LGBMB200_SPLIT_K"))) : 0.044f;
+    ha.split_k = split_k;
     ha.explicit_n = -1; ha.explicit_slot = 0; ha.explicit_idx = nullptr;
     ha.use_tma = have_tmap_ ? 1 : 0;
     // L2 prefetch distance of the gathered passes, in stages of one producer warp (LGBMB200_PF overrides it)
     static const int pf_stages = std::getenv("LGBMB200_PF") ? std::atoi(std::getenv("LGBMB200_PF")) : 4;
     ha.l2_prefetch = pf_stages;
-    static const int g4 = std::getenv("LGBMB200_G4") ? std::atoi(std::getenv("LGBMB200_G4")) : 0;
-    ha.use_gather4 = (g4 && have_g4_) ? 1 : 0;
     return ha;
   }
   // the packed-cell kernel of quantized training keeps the round-1 work mapping (hist_common.cuh)
@@ -790,19 +788,6 @@ class Learner {
                                                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       have_tmap_ = (r2 == CUDA_SUCCESS);
     }
-    // tile::gather4 maps (gathered stages): box = {32 G columns, 1 row}, four row coordinates per instruction
-    have_g4_ = false;
-    std::memset(&tmap_g4_1_, 0, sizeof(tmap_g4_1_)); std::memset(&tmap_g4_2_, 0, sizeof(tmap_g4_2_));
-    if (have_tmap_) {
-      const cuuint32_t b1[2] = {kColGroup, 1}, b2[2] = {2 * kColGroup, 1};
-      const CUresult g1 = reinterpret_cast<EncodeTiled>(fn)(&tmap_g4_1_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, bins_.p, gdim, gstride, b1, estride,
-                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      const CUresult g2 = reinterpret_cast<EncodeTiled>(fn)(&tmap_g4_2_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, bins_.p, gdim, gstride, b2, estride,
-                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      have_g4_ = (g1 == CUDA_SUCCESS && g2 == CUDA_SUCCESS);
-    }
   }
 
   // quantized training: packed 16:16 cells whenever a flush interval of at least 4096 rows keeps both fields in
@@ -817,10 +802,10 @@ class Learner {
   void LaunchHist(const HistAArgs& ha, const HistQArgs& qa, bool chain = false) {
     if (PackedQuantHist()) { LaunchChain(chain, k_hist_q, dim3(num_sms_ * 2), dim3(kHistThreads), kQSmemBytes, qa, tmap_); return; }
     if (ConstHessHist()) {
-      LaunchChain(chain, k_hist_a<true>, dim3(num_sms_), dim3(kAThreads), AShape<true>::kSmem, ha, tmap2_, tmap_g4_2_);
+      LaunchChain(chain, k_hist_a<true>, dim3(num_sms_), dim3(kAThreads), AShape<true>::kSmem, ha, tmap2_);
       LaunchChain(true, k_hist_reduce<true>, dim3((hist_sets_ * AShape<true>::G * 128 * 32 + 255) / 256), dim3(256), 0, ha);
     } else {
-      LaunchChain(chain, k_hist_a<false>, dim3(num_sms_), dim3(kAThreads), AShape<false>::kSmem, ha, tmap_, tmap_g4_1_);
+      LaunchChain(chain, k_hist_a<false>, dim3(num_sms_), dim3(kAThreads), AShape<false>::kSmem, ha, tmap_);
       LaunchChain(true, k_hist_reduce<false>, dim3((hist_sets_ * kBinsPerColumn * 32 + 255) / 256), dim3(256), 0, ha);
     }
     ++launches_;
@@ -1047,8 +1032,8 @@ class Learner {
   DevBuf<PartialSum> partials_;
   CommPeers peers_{};
   CUtensorMap tmap_;
-  bool have_tmap_ = false, have_g4_ = false;
-  CUtensorMap tmap2_, tmap_g4_1_, tmap_g4_2_;
+  bool have_tmap_ = false;
+  CUtensorMap tmap2_;
   void* comm_local_ = nullptr;
   int64_t comm_stride_ = 0;
   std::vector<void*> comm_opened_;
