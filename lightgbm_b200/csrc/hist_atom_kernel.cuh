@@ -341,10 +341,14 @@ __global__ void __launch_bounds__(kAThreads, 1) k_hist_a(const HistAArgs a, cons
 }
 
 // Sum the scratch blocks of every column-group set into the leaf's pool slot (plain stores: the slot needs no memset).
-// CH: thread -> (set, column group gs, bin pair m, column); per block it reads hi/lo of bins 2m, 2m+1 and their count
-// word.  General: thread -> (set, bin, column); hi/lo of the gradient and of the hessian.
+// One CTA of 8 warps per 32-column row of cells: CH -> (set, column group gs, bin pair m), general -> (set, bin); lane =
+// column; the blocks of the set are dealt to the 8 warps (4 loads groups in flight each), partial sums meet in shared
+// memory.  (The first version gave every thread ALL blocks of its set: a chain of up to 74 dependent L2 round trips on
+// 64 CTAs when a GPU holds only two sets — 10M x 128, the per-GPU shard of C3 at 8 GPUs — which cost more than the
+// accumulation itself.)
+constexpr int kReduceWarps = 8;
 template <bool CH>
-__global__ void __launch_bounds__(256) k_hist_reduce(const HistAArgs a) {
+__global__ void __launch_bounds__(kReduceWarps * 32) k_hist_reduce(const HistAArgs a) {
   using S = AShape<CH>;
   constexpr int G = S::G;
   pdl_enter();
@@ -356,39 +360,50 @@ __global__ void __launch_bounds__(256) k_hist_reduce(const HistAArgs a) {
     slot = a.leaves[c->smaller].slot;        // a rank holding no row of the leaf (row-shard) claims no block: zeros are written
   }
   const int sets = a.num_colgroups / G, epoch = a_epoch(a);
-  constexpr int kPerSet = CH ? G * 128 * 32 : kBinsPerColumn * 32;        // threads per set
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  const int set = idx / kPerSet;
+  constexpr int kRowsPerSet = CH ? G * 128 : kBinsPerColumn;              // CTAs per set
+  const int set = blockIdx.x / kRowsPerSet, r = blockIdx.x % kRowsPerSet;
   if (set >= sets) return;
-  const int r = idx % kPerSet;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nblk = min(a.blk_count[epoch * sets + set], a.blk_cap);
   const uint32_t* base = reinterpret_cast<const uint32_t*>(a.scratch + static_cast<int64_t>(set) * a.blk_cap * S::kTables);
   constexpr int kBlkWords = S::kTables / 4, kTabWords = kATable / 4;
   unsigned long long* dst_slot = a.pool + static_cast<int64_t>(slot) * a.slot_stride;
+  __shared__ long long s_part[kReduceWarps][4][32];
+  long long v0 = 0, v1 = 0, v2 = 0, v3 = 0;      // CH: g(2m), g(2m+1), count(2m), count(2m+1); general: g, h, -, -
   if (CH) {
-    const int gs = r / 4096, m = (r % 4096) / 32, col = r % 32;
-    const uint32_t* p = base + gs * (S::kCgBytes / 4) + (2 * m) * 32 + col;
-    long long g0 = 0, g1 = 0; long long c0 = 0, c1 = 0;
-    for (int b = 0; b < nblk; ++b, p += kBlkWords) {
+    const int gs = r / 128, m = r % 128;
+    const uint32_t* p0 = base + gs * (S::kCgBytes / 4) + (2 * m) * 32 + lane;
+#pragma unroll 4
+    for (int b = warp; b < nblk; b += kReduceWarps) {
+      const uint32_t* p = p0 + static_cast<int64_t>(b) * kBlkWords;
       const int h0 = static_cast<int>(__ldcg(p)), h1 = static_cast<int>(__ldcg(p + 32));
       const uint32_t l0 = __ldcg(p + kTabWords), l1 = __ldcg(p + kTabWords + 32);
       const uint32_t cw = __ldcg(p + 2 * kTabWords - m * 32);        // count word m of the [128][32] count table
-      g0 += static_cast<long long>(h0) * 65536 + l0; g1 += static_cast<long long>(h1) * 65536 + l1;
-      c0 += cw & 0xffffu; c1 += cw >> 16;
+      v0 += static_cast<long long>(h0) * 65536 + l0; v1 += static_cast<long long>(h1) * 65536 + l1;
+      v2 += cw & 0xffffu; v3 += cw >> 16;
     }
-    const long long hq = a.ctl->h_const_q;
-    longlong2* d = reinterpret_cast<longlong2*>(dst_slot + (static_cast<int64_t>(set * G + gs) * kColGroup + col) * (kBinsPerColumn * 2) + 4 * m);
-    d[0] = make_longlong2(g0, c0 * hq);
-    d[1] = make_longlong2(g1, c1 * hq);
   } else {
-    const int bin = r / 32, col = r % 32;
-    const uint32_t* p = base + bin * 32 + col;
-    long long g = 0, h = 0;
-    for (int b = 0; b < nblk; ++b, p += kBlkWords) {
-      g += static_cast<long long>(static_cast<int>(__ldcg(p))) * 65536 + __ldcg(p + kTabWords);
-      h += static_cast<long long>(static_cast<int>(__ldcg(p + 2 * kTabWords))) * 65536 + __ldcg(p + 3 * kTabWords);
+    const uint32_t* p0 = base + r * 32 + lane;
+#pragma unroll 4
+    for (int b = warp; b < nblk; b += kReduceWarps) {
+      const uint32_t* p = p0 + static_cast<int64_t>(b) * kBlkWords;
+      v0 += static_cast<long long>(static_cast<int>(__ldcg(p))) * 65536 + __ldcg(p + kTabWords);
+      v1 += static_cast<long long>(static_cast<int>(__ldcg(p + 2 * kTabWords))) * 65536 + __ldcg(p + 3 * kTabWords);
     }
-    *reinterpret_cast<longlong2*>(dst_slot + (static_cast<int64_t>(set) * kColGroup + col) * (kBinsPerColumn * 2) + 2 * bin) = make_longlong2(g, h);
+  }
+  s_part[warp][0][lane] = v0; s_part[warp][1][lane] = v1; s_part[warp][2][lane] = v2; s_part[warp][3][lane] = v3;
+  __syncthreads();
+  if (warp != 0) return;
+#pragma unroll
+  for (int w = 1; w < kReduceWarps; ++w) { v0 += s_part[w][0][lane]; v1 += s_part[w][1][lane]; v2 += s_part[w][2][lane]; v3 += s_part[w][3][lane]; }
+  if (CH) {
+    const int gs = r / 128, m = r % 128;
+    const long long hq = a.ctl->h_const_q;
+    longlong2* d = reinterpret_cast<longlong2*>(dst_slot + (static_cast<int64_t>(set * G + gs) * kColGroup + lane) * (kBinsPerColumn * 2) + 4 * m);
+    d[0] = make_longlong2(v0, v2 * hq);
+    d[1] = make_longlong2(v1, v3 * hq);
+  } else {
+    *reinterpret_cast<longlong2*>(dst_slot + (static_cast<int64_t>(set) * kColGroup + lane) * (kBinsPerColumn * 2) + 2 * r) = make_longlong2(v0, v1);
   }
 }
 

@@ -803,10 +803,10 @@ class Learner {
     if (PackedQuantHist()) { LaunchChain(chain, k_hist_q, dim3(num_sms_ * 2), dim3(kHistThreads), kQSmemBytes, qa, tmap_); return; }
     if (ConstHessHist()) {
       LaunchChain(chain, k_hist_a<true>, dim3(num_sms_), dim3(kAThreads), AShape<true>::kSmem, ha, tmap2_);
-      LaunchChain(true, k_hist_reduce<true>, dim3((hist_sets_ * AShape<true>::G * 128 * 32 + 255) / 256), dim3(256), 0, ha);
+      LaunchChain(true, k_hist_reduce<true>, dim3(hist_sets_ * AShape<true>::G * 128), dim3(kReduceWarps * 32), 0, ha);
     } else {
       LaunchChain(chain, k_hist_a<false>, dim3(num_sms_), dim3(kAThreads), AShape<false>::kSmem, ha, tmap_);
-      LaunchChain(true, k_hist_reduce<false>, dim3((hist_sets_ * kBinsPerColumn * 32 + 255) / 256), dim3(256), 0, ha);
+      LaunchChain(true, k_hist_reduce<false>, dim3(hist_sets_ * kBinsPerColumn), dim3(kReduceWarps * 32), 0, ha);
     }
     ++launches_;
   }
