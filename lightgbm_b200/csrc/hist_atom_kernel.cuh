@@ -18,14 +18,15 @@
 //     error per row is max|g| * 2^-31, two orders of magnitude below the fp32 partial sums of round 1.
 //   * A 30-bit q does not fit an int32 accumulator for more than two rows, so it is accumulated as TWO int32 cells:
 //     hi = q >> 16 (signed, |hi| <= 2^14) and lo = q & 0xffff (unsigned 16 bit).  Either cell can take 65 535 rows
-//     before it can wrap; the tables are flushed ( (hi << 16) + lo -> RED.ADD.64 into the int64 pool slot) at least that
-//     often.  Cost: 2 ATOMS per cell and component.
+//     before it can wrap; the tables are flushed (dumped as raw int32 images into a scratch block; k_hist_reduce forms
+//     (hi << 16) + lo in int64 and sums the blocks into the pool slot) at least that often.  Cost: 2 ATOMS per cell and
+//     component.
 //   * Constant hessian (unweighted L2: the BASELINE configs) needs no hessian sums at all: like the reference
 //     (dataset.cpp:1430-1437) the kernel COUNTS rows per cell and scales at the flush.  Counts are 16-bit fields, two
 //     bins per int32 word.  3 ATOMS per cell (g hi, g lo, count); general hessians: 4 (g hi, g lo, h hi, h lo).
 //   * The tables are shared by ALL consumer warps of the CTA ([bin][column] int32, bank = column): one table set per
-//     column group per SM instead of one per warp, so 8 consumer warps (2 per SMSP) hide each other's latencies and the
-//     shared memory left over becomes a 24..48-stage ring (49..61 KB of rows in flight per SM for gathered leaves).
+//     column group per SM instead of one per warp, so 16 consumer warps (4 per SMSP) hide each other's latencies and the
+//     shared memory left over becomes a 28..48-stage ring (60 KB of rows in flight per SM for gathered leaves).
 //   * A lane handles FOUR columns of ONE row: one LDS.32 fetches its four bin bytes from the row-major stage (a flat
 //     array of 32-byte segments), lanes (q, j) = (lane & 7, lane >> 3) take bytes 4q..4q+3 of segment 4u+j, and walk
 //     their four columns in the rotated order (k + j) & 3 so that in every step the 32 lanes of the warp touch 32
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kAThreads, 1) k_hist_a(const HistAArgs a, cons
 
   // The CTA's stages are numbered seq = 0..total-1 along (set, stage); consumer warp cw takes seq = cw, cw + 16, ...
   // The sequence is cut into segments at set boundaries and every kAFlushRows rows; after each segment all consumer
-  // warps meet, flush the tables into the leaf's pool slot and zero them.
+  // warps meet, dump the tables into a scratch block of the set and zero them.
   const int total = static_cast<int>(w.v_hi - w.v_lo);
   int my_seq = cw, slot = cw % NS; unsigned par = 0;
   int sgrp = static_cast<int>(w.v_lo / w.spc);

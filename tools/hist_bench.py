@@ -25,3 +25,11 @@ for label, idx in (("root", None), ("gather50", np.sort(rng.choice(n, n // 2, re
     best = min(ts)
     print(f"{label}: rows={rows} cols={f} best {best:.4f} ms  median {np.median(ts):.4f} ms -> {rows*f/best/1e6:.1f} GB/s bin bytes, "
           f"{rows*f/best/1e6/148/1.9:.2f} cells/clk/SM@1.9GHz")
+# fixed cost per pass: gathered passes over ever smaller leaves (HB_SWEEP=1)
+if os.environ.get("HB_SWEEP"):
+    for rows in (1_000_000, 300_000, 100_000, 30_000, 10_000, 3_000, 1_000, 100):
+        if rows > n:
+            continue
+        idx = np.sort(rng.choice(n, rows, replace=False)).astype(np.int32)
+        ts = [L.construct_histogram(dg, dh, idx, want_hist=False)[1] for _ in range(7)]
+        print(f"sweep rows={rows:8d} cols={f} best {1e3 * min(ts):8.1f} us  median {1e3 * float(np.median(ts)):8.1f} us")

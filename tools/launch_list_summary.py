@@ -6,7 +6,7 @@ UNIT = {"ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "ms": 1e-3, "msecond": 1e-3, "s
         "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
-def main(path, out_json=None, workload=""):
+def main(path, out_json=None, workload="", n_gpus=1):
     rows = list(csv.reader(open(path, errors="replace")))
     h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     H = rows[h]
@@ -17,13 +17,15 @@ def main(path, out_json=None, workload=""):
             continue
         name = r[ki].split("(")[0].replace("void ", "").split("<")[0]
         per[name][r[idi]][r[mi]] = float(r[vi].replace(",", "")) * UNIT.get(r[ui], 1.0)
-    # one full tree = the launches between two consecutive k_prep launches (when the capture holds them)
+    # complete trees = the launches between the first and the last k_prep of the capture
     preps = sorted(int(i) for i in per.get("k_prep", {}))
+    trees = 1
     if len(preps) >= 2:
-        lo, hi = preps[0], preps[1]
+        lo, hi = preps[0], preps[-1]
+        trees = len(preps) - 1
         per = {k: {i: m for i, m in v.items() if lo <= int(i) < hi} for k, v in per.items()}
         per = {k: v for k, v in per.items() if v}
-        print(f"# restricted to one full tree: launch ids [{lo}, {hi})")
+        print(f"# restricted to {trees} complete tree(s): launch ids [{lo}, {hi})")
     tot = sum(m.get("gpu__time_duration.sum", 0.0) for k in per.values() for m in k.values())
     print(f"{'kernel':18s} {'launches':>8s} {'total ms':>10s} {'share':>7s} {'median us':>10s}")
     for name, ls in sorted(per.items(), key=lambda kv: -sum(m.get('gpu__time_duration.sum', 0) for m in kv[1].values())):
@@ -33,11 +35,13 @@ def main(path, out_json=None, workload=""):
     if out_json and hist:
         ls = [m for v in hist.values() for m in v.values()]
         rd = sum(m.get("dram__bytes_read.sum", 0.0) for m in ls); wr = sum(m.get("dram__bytes_write.sum", 0.0) for m in ls)
-        json.dump({"kernel": "+".join(sorted(hist)), "workload": workload, "launches": len(ls),
-                   "dram_bytes_per_launch": (rd + wr) / len(ls), "dram_read_bytes_total": rd, "dram_write_bytes_total": wr,
+        n_a = max(1, len(hist.get("k_hist_a", hist.get("k_hist_q", ls))))      # one k_hist_reduce follows every k_hist_a: count the pair once
+        json.dump({"kernel": "k_hist_a" if "k_hist_a" in hist else "k_hist_q", "includes": sorted(hist), "workload": workload, "n_gpus": int(n_gpus), "launches": n_a, "trees": trees,
+                   "dram_bytes_per_launch": (rd + wr) / n_a, "dram_read_bytes_total": rd, "dram_write_bytes_total": wr,
                    "source": f"{path} (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none)",
                    "hist_time_share_under_ncu": sum(m.get("gpu__time_duration.sum", 0.0) for m in ls) / tot}, open(out_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None, sys.argv[3] if len(sys.argv) > 3 else "")
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None, sys.argv[3] if len(sys.argv) > 3 else "",
+         sys.argv[4] if len(sys.argv) > 4 else 1)
