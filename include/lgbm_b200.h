@@ -121,7 +121,8 @@ LGBMB200_EXPORT const char* LGBMB200_GetLastError(void);
 LGBMB200_EXPORT int LGBMB200_LearnerCreate(const LGBMB200_Config* config, LGBMB200_LearnerHandle* out);
 
 /* TreeLearner::Init(const Dataset*, bool is_constant_hessian) — reference tree_learner.h:38;
- * cuda_single_gpu_tree_learner.cpp:36-93.  Copies the bin matrix (host pointer) to HBM.
+ * cuda_single_gpu_tree_learner.cpp:36-93.  Copies the bin matrix (host pointer, or a device pointer such as the output of
+ * LGBMB200_BinnerTransform) into the learner's own padded HBM layout.
  * is_constant_hessian != 0 promises that every hessian passed to Train equals hessians[0] (the objective's
  * IsConstantHessian(), gbdt.cpp:92); Train then reads only hessians[0] from a host buffer. */
 LGBMB200_EXPORT int LGBMB200_LearnerInit(LGBMB200_LearnerHandle h, const LGBMB200_Layout* layout,
@@ -276,6 +277,55 @@ LGBMB200_EXPORT int LGBMB200_MemcpyH2D(void* dst_dev, const void* src_host, int6
 LGBMB200_EXPORT int LGBMB200_MemcpyD2H(void* dst_host, const void* src_dev, int64_t bytes);
 
 LGBMB200_EXPORT int LGBMB200_LearnerFree(LGBMB200_LearnerHandle h);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Dataset construction: what LGBM_DatasetCreateFromMat does between the caller's dense matrix and
+ * the binned Dataset a tree learner is Init-ed with — reference src/c_api.cpp:1296-1408 (row sample, :981-989),
+ * DatasetLoader::ConstructFromSampleData (src/io/dataset_loader.cpp:600-761), BinMapper::FindBin (src/io/bin.cpp:315-512),
+ * Dataset::Construct / FastFeatureBundling (src/io/dataset.cpp:66-440) under the rules of a `device_type=cuda` Dataset,
+ * Dataset::PushOneRow -> FeatureGroup::PushData (include/LightGBM/feature_group.h:253-267).
+ * Numerical features only; categorical_feature, forcedbins_filename, max_bin_by_feature and max_bin > 255 are not supported. */
+typedef void* LGBMB200_BinnerHandle;
+
+/* the Dataset parameters the construction reads (reference include/LightGBM/config.h "Dataset Parameters") */
+typedef struct {
+  int32_t max_bin;                    /* 2..255 */
+  int32_t min_data_in_bin;
+  int32_t min_data_in_leaf;           /* feature_pre_filter drops features that cannot be split under it */
+  int32_t bin_construct_sample_cnt;
+  int32_t data_random_seed;
+  int32_t feature_pre_filter;
+  int32_t use_missing;
+  int32_t zero_as_missing;
+  int32_t enable_bundle;
+  int32_t gpu_device_id;              /* device of the value->bin pass; -1 = current device */
+} LGBMB200_BinConfig;
+
+LGBMB200_EXPORT int LGBMB200_BinnerCreate(const LGBMB200_BinConfig* config, LGBMB200_BinnerHandle* out);
+
+/* Sample rows, find the bin mappers, bundle the features.  Host work only (no CUDA call).
+ * data: dense host matrix, data_type 0 = float32 / 1 = float64 (C_API_DTYPE_FLOAT32/64, c_api.h:38-39). */
+LGBMB200_EXPORT int LGBMB200_BinnerFit(LGBMB200_BinnerHandle h, const void* data, int32_t data_type, int32_t nrow, int32_t ncol,
+                                       int32_t is_row_major);
+
+/* The layout contract of the fitted Dataset; the arrays stay owned by the handle (valid until the next Fit / Free). */
+LGBMB200_EXPORT int LGBMB200_BinnerGetLayout(LGBMB200_BinnerHandle h, LGBMB200_Layout* out);
+
+/* BinMapper::bin_upper_bound_ of an inner feature (what Dataset::RealThreshold reads, dataset.h:853): num_bin doubles
+ * (the last one +inf; a NaN-missing mapper ends {+inf, 2.0}: the reference stores the enumerator MissingType::NaN there).  upper_bounds_out may be NULL to query num_bin only. */
+LGBMB200_EXPORT int LGBMB200_BinnerGetFeatureBounds(LGBMB200_BinnerHandle h, int32_t inner_feature, double* upper_bounds_out,
+                                                    int32_t* num_bin_out);
+
+/* LGBM_SampleIndices (c_api.h:96): the rows the mappers were found from.  indices_out may be NULL to query the count. */
+LGBMB200_EXPORT int LGBMB200_BinnerGetSampleIndices(LGBMB200_BinnerHandle h, int32_t* indices_out, int32_t* num_out);
+
+/* The value->bin pass over all rows on the device: row-major [nrow x ncol-of-Fit] matrix (host, streamed in chunks, or
+ * already in HBM) -> [nrow x num_columns] stored bytes (host or device pointer).  A device `bins_out` can be handed to
+ * LGBMB200_LearnerInit as is.  elapsed_ms (may be NULL): device time of the whole pass, copies included. */
+LGBMB200_EXPORT int LGBMB200_BinnerTransform(LGBMB200_BinnerHandle h, const void* data, int32_t data_type, int32_t nrow,
+                                             int32_t data_on_device, uint8_t* bins_out, int32_t out_on_device, float* elapsed_ms);
+
+LGBMB200_EXPORT int LGBMB200_BinnerFree(LGBMB200_BinnerHandle h);
 
 #ifdef __cplusplus
 }

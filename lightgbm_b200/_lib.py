@@ -18,6 +18,8 @@ EXPORTS = [
     "LGBMB200_MemcpyH2D", "LGBMB200_MemcpyD2H", "LGBMB200_LearnerFree", "LGBMB200_LearnerGetLeafIndex", "LGBMB200_LearnerGetLeafIndexRange8",
     "LGBMB200_LearnerCommExport", "LGBMB200_LearnerCommConnect", "LGBMB200_LearnerCommExportPool", "LGBMB200_LearnerCommConnectRows",
     "LGBMB200_LearnersConnectLocal", "LGBMB200_LearnerCommExportColumns", "LGBMB200_LearnerCommShareColumns", "LGBMB200_LearnerTimerStart", "LGBMB200_LearnerTimerStop", "LGBMB200_HostAllocPinned", "LGBMB200_HostFreePinned",
+    "LGBMB200_BinnerCreate", "LGBMB200_BinnerFit", "LGBMB200_BinnerGetLayout", "LGBMB200_BinnerGetFeatureBounds",
+    "LGBMB200_BinnerGetSampleIndices", "LGBMB200_BinnerTransform", "LGBMB200_BinnerFree",
 ]
 
 

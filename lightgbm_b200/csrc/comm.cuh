@@ -1,6 +1,7 @@
 // comm.cuh — device-side primitives of the multi-GPU exchange over NVLink peer memory (no NCCL call on the
 // per-split path).  Every rank maps every peer's CommBlock (CUDA IPC); a message is "plain stores into the
-// peer's block, __threadfence_system, st.release.sys of a sequence number"; the receiver spins with
+// peer's block, then st.release.sys of a sequence number by the SAME thread (the release orders its earlier stores at
+// system scope: no separate fence, which would cost one more NVLink round trip)"; the receiver spins with
 // ld.acquire.sys on its OWN memory and reads the payload around L1.  Messages are double-buffered by the parity
 // of the sequence number: a rank can never run two exchanges ahead of a peer, because every exchange needs
 // that peer's contribution.  A watchdog turns a missing peer into an error flag instead of a hang.
@@ -46,7 +47,6 @@ __device__ __forceinline__ void exchange_misc(const CommPeers& P, Ctl* c, const 
     CommBlock* dst = P.block[tid];
 #pragma unroll
     for (int k = 0; k < 8; ++k) dst->misc[par][me][k] = in8[k];
-    __threadfence_system();
     st_release_sys(&dst->misc_seq[par][me], seq);
   }
   __syncthreads();

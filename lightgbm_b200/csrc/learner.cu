@@ -134,7 +134,7 @@ class Learner {
 
     bins_.alloc(static_cast<size_t>(N_) * pitch_);
     if (pitch_ != C_) CUDA_CHECK(cudaMemset(bins_.p, 0, static_cast<size_t>(N_) * pitch_));
-    CUDA_CHECK(cudaMemcpy2D(bins_.p, pitch_, bins_host, C_, C_, N_, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy2D(bins_.p, pitch_, bins_host, C_, C_, N_, cudaMemcpyDefault));      // host or device pointer (UVA)
 
     // column-major copy for the partition kernels (+C*N bytes; LGBMB200_Config.reserved bit 0 disables it)
     if (!(cfg_.reserved & 1) && !(DebugBits() & 1)) {
@@ -1066,9 +1066,139 @@ class Learner {
 
 }  // namespace b200
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Dataset construction: host-side mappers / bundles + the device value->bin pass, see binning.cuh
+#include "binning.cuh"
+
+namespace b200 {
+
+class BinnerCtx {
+ public:
+  explicit BinnerCtx(const LGBMB200_BinConfig& c) : device_(c.gpu_device_id), binner_(ToCfg(c)) {}
+  ~BinnerCtx() { for (auto& s : streams_) if (s) cudaStreamDestroy(s); }
+  int device() const { return device_; }
+
+  void Fit(const void* data, int dtype, int64_t nrow, int32_t ncol, int row_major) {
+    REQUIRE(data != nullptr, "null matrix");
+    REQUIRE(dtype == 0 || dtype == 1, "data_type must be 0 (float32) or 1 (float64)");
+    binner_.Fit(data, dtype, nrow, ncol, row_major != 0);
+    uploaded_ = false; fitted_ = true;
+  }
+  void GetLayout(LGBMB200_Layout* out) const {
+    REQUIRE(fitted_, "Fit first");
+    const BinTable& t = binner_.table();
+    out->num_data = binner_.num_data(); out->num_columns = t.num_columns; out->num_features = t.num_features;
+    out->feat_column = t.feat_column.data(); out->feat_lo = t.feat_lo.data(); out->feat_num_bin = t.feat_num_bin.data();
+    out->feat_most_freq_bin = t.feat_mfb.data(); out->feat_default_bin = t.feat_default.data();
+    out->feat_missing_type = t.feat_missing.data(); out->feat_real_index = t.feat_real.data();
+  }
+  void GetBounds(int f, double* upper, int32_t* num_bin) const {
+    REQUIRE(fitted_, "Fit first");
+    const BinTable& t = binner_.table();
+    REQUIRE(f >= 0 && f < t.num_features, "bad feature index");
+    const BinMapperB& m = binner_.mappers()[t.feat_real[f]];
+    if (num_bin) *num_bin = m.num_bin;
+    if (upper) std::memcpy(upper, m.upper.data(), sizeof(double) * m.num_bin);
+  }
+  int32_t GetSampleRows(int32_t* out) const {
+    REQUIRE(fitted_, "Fit first");
+    const std::vector<int>& r = binner_.sample_rows();
+    if (out) std::memcpy(out, r.data(), sizeof(int32_t) * r.size());
+    return static_cast<int32_t>(r.size());
+  }
+
+  // The N x F pass on the device.  `data` is row-major [nrow x num_total_features]; host data is streamed in row chunks
+  // (copy of chunk i+1 overlaps the kernel of chunk i on the other stream); `out` is [nrow x num_columns] bytes.
+  void Transform(const void* data, int dtype, int64_t nrow, int data_on_device, uint8_t* out, int out_on_device, float* elapsed_ms) {
+    REQUIRE(fitted_, "Fit first");
+    REQUIRE(data != nullptr && out != nullptr && nrow > 0, "bad argument");
+    REQUIRE(dtype == 0 || dtype == 1, "data_type must be 0 (float32) or 1 (float64)");
+    if (device_ >= 0) CUDA_CHECK(cudaSetDevice(device_));
+    Upload();
+    const BinTable& t = binner_.table();
+    const int64_t ncol = t.num_total_features, C = t.num_columns;
+    const size_t esize = dtype == 0 ? 4 : 8;
+    int64_t chunk = std::max<int64_t>(1024, (static_cast<int64_t>(64) << 20) / static_cast<int64_t>(ncol * esize));
+    chunk = std::min(chunk, nrow);
+    for (auto& s : streams_) if (!s) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    DevBuf<unsigned char> dx[2], dout[2];
+    if (!data_on_device) for (auto& b : dx) b.alloc(static_cast<size_t>(chunk) * ncol * esize);
+    if (!out_on_device) for (auto& b : dout) b.alloc(static_cast<size_t>(chunk) * C);
+    BinDevTable dt{d_col_first_.p, d_feat_real_.p, d_feat_lo_.p, d_feat_num_bin_.p, d_feat_mfb_.p, d_feat_missing_.p,
+                   d_bound_first_.p, d_bound_count_.p, d_bounds32_.p, d_bounds64_.p, static_cast<int32_t>(C)};
+    cudaEvent_t e0, e1, ej;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreateWithFlags(&ej, cudaEventDisableTiming));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaEventRecord(e0, streams_[0]));
+    CUDA_CHECK(cudaStreamWaitEvent(streams_[1], e0, 0));
+    int k = 0;
+    for (int64_t r0 = 0; r0 < nrow; r0 += chunk, ++k) {
+      const int64_t rows = std::min(chunk, nrow - r0);
+      cudaStream_t st = streams_[k & 1];
+      const unsigned char* src = static_cast<const unsigned char*>(data) + static_cast<size_t>(r0) * ncol * esize;
+      if (!data_on_device) {
+        CUDA_CHECK(cudaMemcpyAsync(dx[k & 1].p, src, static_cast<size_t>(rows) * ncol * esize, cudaMemcpyHostToDevice, st));
+        src = dx[k & 1].p;
+      }
+      uint8_t* dst = out_on_device ? out + r0 * C : dout[k & 1].p;
+      const dim3 grid(static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, 148 * 32)), static_cast<unsigned>((C + 31) / 32));
+      if (dtype == 0) k_value_to_bin<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C);
+      else k_value_to_bin<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C);
+      CUDA_CHECK(cudaGetLastError());
+      ++launches_;
+      if (!out_on_device) CUDA_CHECK(cudaMemcpyAsync(out + r0 * C, dst, static_cast<size_t>(rows) * C, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_CHECK(cudaEventRecord(ej, streams_[1]));
+    CUDA_CHECK(cudaStreamWaitEvent(streams_[0], ej, 0));
+    CUDA_CHECK(cudaEventRecord(e1, streams_[0]));
+    CUDA_CHECK(cudaStreamSynchronize(streams_[0]));
+    CUDA_CHECK(cudaStreamSynchronize(streams_[1]));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(ej);
+    if (elapsed_ms) *elapsed_ms = ms;
+  }
+  int64_t launches() const { return launches_; }
+
+ private:
+  static BinFitConfig ToCfg(const LGBMB200_BinConfig& c) {
+    BinFitConfig f;
+    f.max_bin = c.max_bin; f.min_data_in_bin = c.min_data_in_bin; f.min_data_in_leaf = c.min_data_in_leaf;
+    f.sample_cnt = c.bin_construct_sample_cnt; f.seed = c.data_random_seed;
+    f.pre_filter = c.feature_pre_filter != 0; f.use_missing = c.use_missing != 0; f.zero_as_missing = c.zero_as_missing != 0;
+    f.enable_bundle = c.enable_bundle != 0;
+    return f;
+  }
+  template <typename T>
+  static void Up(DevBuf<T>& d, const std::vector<T>& h) {
+    d.alloc(h.size());
+    if (!h.empty()) CUDA_CHECK(cudaMemcpy(d.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  }
+  void Upload() {
+    if (uploaded_) return;
+    const BinTable& t = binner_.table();
+    Up(d_col_first_, t.col_first); Up(d_feat_real_, t.feat_real); Up(d_feat_lo_, t.feat_lo); Up(d_feat_num_bin_, t.feat_num_bin);
+    Up(d_feat_mfb_, t.feat_mfb); Up(d_feat_missing_, t.feat_missing); Up(d_bound_first_, t.bound_first); Up(d_bound_count_, t.bound_count);
+    Up(d_bounds32_, t.bounds32); Up(d_bounds64_, t.bounds64);
+    uploaded_ = true;
+  }
+
+  int device_;
+  Binner binner_;
+  bool fitted_ = false, uploaded_ = false;
+  int64_t launches_ = 0;
+  cudaStream_t streams_[2] = {nullptr, nullptr};
+  DevBuf<int32_t> d_col_first_, d_feat_real_, d_feat_lo_, d_feat_num_bin_, d_feat_mfb_, d_feat_missing_, d_bound_first_, d_bound_count_;
+  DevBuf<float> d_bounds32_;
+  DevBuf<double> d_bounds64_;
+};
+
+}  // namespace b200
+
 // ------------------------------------------------------------------------------------------ C-ABI
 using b200::CudaError;
 using b200::Learner;
+using b200::BinnerCtx;
 
 #define API_BEGIN() try {
 #define API_BEGIN_H(h) try { DeviceGuard _dev_guard((h) ? static_cast<Learner*>(h)->inited_device() : -1);
@@ -1349,6 +1479,51 @@ int LGBMB200_MemcpyD2H(void* dst_host, const void* src_dev, int64_t bytes) {
 int LGBMB200_LearnerFree(LGBMB200_LearnerHandle h) {
   API_BEGIN_H(h);
   delete static_cast<Learner*>(h);
+  API_END();
+}
+
+// ---- Dataset construction (binning.cuh)
+int LGBMB200_BinnerCreate(const LGBMB200_BinConfig* config, LGBMB200_BinnerHandle* out) {
+  API_BEGIN();
+  if (!config || !out) throw CudaError{"null argument"};
+  *out = new BinnerCtx(*config);
+  API_END();
+}
+int LGBMB200_BinnerFit(LGBMB200_BinnerHandle h, const void* data, int32_t data_type, int32_t nrow, int32_t ncol, int32_t is_row_major) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  static_cast<BinnerCtx*>(h)->Fit(data, data_type, nrow, ncol, is_row_major);
+  API_END();
+}
+int LGBMB200_BinnerGetLayout(LGBMB200_BinnerHandle h, LGBMB200_Layout* out) {
+  API_BEGIN();
+  if (!h || !out) throw CudaError{"null argument"};
+  static_cast<const BinnerCtx*>(h)->GetLayout(out);
+  API_END();
+}
+int LGBMB200_BinnerGetFeatureBounds(LGBMB200_BinnerHandle h, int32_t inner_feature, double* upper_bounds_out, int32_t* num_bin_out) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  static_cast<const BinnerCtx*>(h)->GetBounds(inner_feature, upper_bounds_out, num_bin_out);
+  API_END();
+}
+int LGBMB200_BinnerGetSampleIndices(LGBMB200_BinnerHandle h, int32_t* indices_out, int32_t* num_out) {
+  API_BEGIN();
+  if (!h || !num_out) throw CudaError{"null argument"};
+  *num_out = static_cast<const BinnerCtx*>(h)->GetSampleRows(indices_out);
+  API_END();
+}
+int LGBMB200_BinnerTransform(LGBMB200_BinnerHandle h, const void* data, int32_t data_type, int32_t nrow, int32_t data_on_device,
+                             uint8_t* bins_out, int32_t out_on_device, float* elapsed_ms) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  DeviceGuard guard(static_cast<BinnerCtx*>(h)->device());
+  static_cast<BinnerCtx*>(h)->Transform(data, data_type, nrow, data_on_device, bins_out, out_on_device, elapsed_ms);
+  API_END();
+}
+int LGBMB200_BinnerFree(LGBMB200_BinnerHandle h) {
+  API_BEGIN();
+  if (h) { DeviceGuard guard(static_cast<BinnerCtx*>(h)->device()); delete static_cast<BinnerCtx*>(h); }
   API_END();
 }
 

@@ -752,7 +752,6 @@ __device__ __noinline__ void select_body(const SelectArgs& a) {
       Cand* slot = &dst->mail[par][me][0];
       slot[0] = a.leaves[smaller].best;
       if (larger >= 0) slot[1] = a.leaves[larger].best;
-      __threadfence_system();
       st_release_sys(&dst->mail_seq[par][me], seq);
     }
     __syncthreads();

@@ -87,7 +87,8 @@ class Config:
 class Layout:
     """Binned training matrix + per-feature metadata: what `Dataset` hands to TreeLearner::Init
     (reference dataset.h:638-647,806-810,985-1000).  See include/lgbm_b200.h LGBMB200_Layout."""
-    bins: np.ndarray                 # [num_data, num_columns] uint8 stored group values
+    bins: object                     # [num_data, num_columns] uint8 stored group values: np.ndarray, or a matrix already in HBM
+                                     # (dataset.DeviceMatrix: anything with .shape and .ptr)
     feat_column: np.ndarray
     feat_lo: np.ndarray
     feat_num_bin: np.ndarray
@@ -234,12 +235,13 @@ class B200TreeLearner:
 
     # TreeLearner::Init(const Dataset* train_data, bool is_constant_hessian)
     def init(self, layout: Layout, is_constant_hessian: bool = False) -> None:
-        bins = np.ascontiguousarray(layout.bins, dtype=np.uint8)
+        on_device = hasattr(layout.bins, "ptr")
+        bins = layout.bins if on_device else np.ascontiguousarray(layout.bins, dtype=np.uint8)
         keep = [np.ascontiguousarray(a, dtype=np.int32) for a in
                 (layout.feat_column, layout.feat_lo, layout.feat_num_bin, layout.feat_mfb, layout.feat_default_bin,
                  layout.feat_missing, layout.feat_real_index)]
         cl = _CLayout(layout.num_data, layout.num_columns, layout.num_features, *[_p(a) for a in keep])
-        check(lib().LGBMB200_LearnerInit(self.handle, C.byref(cl), _p(bins), C.c_int32(1 if is_constant_hessian else 0)))
+        check(lib().LGBMB200_LearnerInit(self.handle, C.byref(cl), bins.ptr if on_device else _p(bins), C.c_int32(1 if is_constant_hessian else 0)))
         self.layout = layout
 
     # TreeLearner::ResetConfig(const Config*)
