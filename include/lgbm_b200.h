@@ -327,6 +327,27 @@ LGBMB200_EXPORT int LGBMB200_BinnerTransform(LGBMB200_BinnerHandle h, const void
 
 LGBMB200_EXPORT int LGBMB200_BinnerFree(LGBMB200_BinnerHandle h);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Prediction with a trained model: LGBM_BoosterPredictForMat with C_API_PREDICT_RAW_SCORE
+ * (reference include/LightGBM/c_api.h:1283-1330) -> GBDT::PredictRaw (src/boosting/gbdt_prediction.cpp:15-34) ->
+ * Tree::Predict / NumericalDecision (include/LightGBM/tree.h:337-355, :587-620).  The model is handed over as the flat
+ * arrays of the model text (Tree::ToString, src/io/tree.cpp:343-413), all trees back to back: per internal node
+ * split_feature (real index), threshold, decision_type, left_child, right_child (>= 0 node, < 0 ~leaf); per leaf
+ * leaf_value.  One tree per iteration (num_class = 1), numerical splits only. */
+typedef void* LGBMB200_PredictorHandle;
+
+LGBMB200_EXPORT int LGBMB200_PredictorCreate(int32_t gpu_device_id, int32_t num_trees, const int32_t* tree_num_leaves,
+                                             const int32_t* split_feature, const double* threshold, const int8_t* decision_type,
+                                             const int32_t* left_child, const int32_t* right_child, const double* leaf_value,
+                                             int32_t max_feature_idx, LGBMB200_PredictorHandle* out);
+
+/* Raw scores (sum of tree outputs in tree order, double) of a row-major [nrow x ncol] float32 (0) / float64 (1) matrix,
+ * host (streamed in row chunks) or device resident; out_raw_score: nrow doubles, host or device. */
+LGBMB200_EXPORT int LGBMB200_PredictorPredict(LGBMB200_PredictorHandle h, const void* data, int32_t data_type, int32_t nrow, int32_t ncol,
+                                              int32_t data_on_device, double* out_raw_score, int32_t out_on_device, float* elapsed_ms);
+
+LGBMB200_EXPORT int LGBMB200_PredictorFree(LGBMB200_PredictorHandle h);
+
 #ifdef __cplusplus
 }
 #endif

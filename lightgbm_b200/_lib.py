@@ -20,6 +20,7 @@ EXPORTS = [
     "LGBMB200_LearnersConnectLocal", "LGBMB200_LearnerCommExportColumns", "LGBMB200_LearnerCommShareColumns", "LGBMB200_LearnerTimerStart", "LGBMB200_LearnerTimerStop", "LGBMB200_HostAllocPinned", "LGBMB200_HostFreePinned",
     "LGBMB200_BinnerCreate", "LGBMB200_BinnerFit", "LGBMB200_BinnerGetLayout", "LGBMB200_BinnerGetFeatureBounds",
     "LGBMB200_BinnerGetSampleIndices", "LGBMB200_BinnerTransform", "LGBMB200_BinnerFree",
+    "LGBMB200_PredictorCreate", "LGBMB200_PredictorPredict", "LGBMB200_PredictorFree",
 ]
 
 

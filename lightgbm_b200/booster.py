@@ -147,6 +147,16 @@ class B200Booster:
         self.trees.append(tree)
         return tree
 
+    def to_model(self, parameters: str = ""):
+        """The trees grown so far as a model-text object (GBDT::SaveModelToString): `.to_string()` is loadable by the
+        reference's LGBM_BoosterLoadModelFromString, `.predict(X)` scores raw float matrices on the device."""
+        from .model import Model, ModelTree
+        lay = self.learner.layout
+        mfi = int(getattr(lay, "num_total_features", 0) or (int(np.max(lay.feat_real_index)) + 1)) - 1
+        obj = "regression" if self.objective == "regression" else f"binary sigmoid:{self.sigmoid:g}"
+        return Model([ModelTree.from_learner_tree(t, lay, t.shrink, t.bias) for t in self.trees], max_feature_idx=mfi, objective=obj,
+                     parameters=parameters)
+
     def scores(self) -> np.ndarray:
         if self.device_resident:
             return self.d_score.download(np.float64, self.n)
@@ -214,3 +224,26 @@ class RowSlicedHostBooster:
         self.host_ms["gradients"] += (t1 - t0) * 1e3; self.host_ms["train"] += (t2 - t1) * 1e3; self.host_ms["score"] += (t3 - t2) * 1e3
         self.trees.append(tree)
         return tree
+
+
+def train(params: dict, train_set, num_boost_round: int = 100) -> B200Booster:
+    """`lightgbm.train(params, lgb.Dataset(X, y), num_boost_round)` for the objectives this mirror knows (regression,
+    binary) — raw floats in, binned on the device (dataset.py), boosted with gradients and scores resident in HBM."""
+    p = dict(params or {})
+    obj = p.get("objective", "regression")
+    obj = {"regression_l2": "regression", "l2": "regression", "mse": "regression"}.get(obj, obj)
+    cfg = Config(num_leaves=int(p.get("num_leaves", 31)), max_depth=int(p.get("max_depth", -1)),
+                 min_data_in_leaf=int(p.get("min_data_in_leaf", 20)), min_sum_hessian_in_leaf=float(p.get("min_sum_hessian_in_leaf", 1e-3)),
+                 lambda_l1=float(p.get("lambda_l1", 0.0)), lambda_l2=float(p.get("lambda_l2", 0.0)),
+                 min_gain_to_split=float(p.get("min_gain_to_split", 0.0)))
+    train_set.params = {**p, **train_set.params}
+    lay = train_set.construct().layout
+    lay.num_total_features = train_set.num_feature()
+    b = B200Booster(lay, train_set.get_label(), cfg, learning_rate=float(p.get("learning_rate", 0.1)),
+                    boost_from_average=str(p.get("boost_from_average", "true")).lower() not in ("false", "0"),
+                    objective=obj, sigmoid=float(p.get("sigmoid", 1.0)),
+                    data_sample_strategy=p.get("data_sample_strategy", "bagging"), top_rate=float(p.get("top_rate", 0.2)),
+                    other_rate=float(p.get("other_rate", 0.1)), bagging_seed=int(p.get("bagging_seed", 3)))
+    for _ in range(num_boost_round):
+        b.update()
+    return b

@@ -1195,10 +1195,120 @@ class BinnerCtx {
 
 }  // namespace b200
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Prediction with a trained model, see predict.cuh
+#include "predict.cuh"
+
+namespace b200 {
+
+class Predictor {
+ public:
+  Predictor(int device, int32_t num_trees, const int32_t* tree_num_leaves, const int32_t* split_feature, const double* threshold,
+            const int8_t* decision_type, const int32_t* left_child, const int32_t* right_child, const double* leaf_value,
+            int32_t max_feature_idx)
+      : device_(device), num_trees_(num_trees), max_feature_idx_(max_feature_idx) {
+    REQUIRE(num_trees >= 0 && tree_num_leaves, "bad model");
+    std::vector<PNode> nodes; std::vector<double> leaves; std::vector<int32_t> nf, lf, nl;
+    int64_t ni = 0, li = 0;
+    for (int t = 0; t < num_trees; ++t) {
+      const int L = tree_num_leaves[t];
+      REQUIRE(L >= 1, "a tree needs at least one leaf");
+      nf.push_back(static_cast<int32_t>(nodes.size())); lf.push_back(static_cast<int32_t>(leaves.size())); nl.push_back(L);
+      for (int i = 0; i < L - 1; ++i, ++ni) {
+        PNode n;
+        n.threshold = threshold[ni]; n.feature = split_feature[ni]; n.left = left_child[ni]; n.right = right_child[ni];
+        n.decision = static_cast<int32_t>(decision_type[ni]) & 0xff;
+        REQUIRE(!(n.decision & 1), "categorical splits are not supported");
+        REQUIRE(n.feature >= 0 && n.feature <= max_feature_idx, "split feature out of range");
+        REQUIRE(n.left < L - 1 && n.right < L - 1 && ~n.left < L && ~n.right < L, "child index out of range");
+        nodes.push_back(n);
+      }
+      for (int i = 0; i < L; ++i, ++li) leaves.push_back(leaf_value[li]);
+    }
+    if (device_ >= 0) CUDA_CHECK(cudaSetDevice(device_));
+    Up(d_nodes_, nodes); Up(d_leaves_, leaves); Up(d_nf_, nf); Up(d_lf_, lf); Up(d_nl_, nl);
+    CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[0], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[1], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaFuncSetAttribute(k_predict<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredTileBytes));
+    CUDA_CHECK(cudaFuncSetAttribute(k_predict<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredTileBytes));
+  }
+  ~Predictor() { for (auto& s : streams_) if (s) cudaStreamDestroy(s); }
+  int device() const { return device_; }
+  int64_t launches() const { return launches_; }
+
+  // raw scores of `nrow` rows of a row-major [nrow x ncol] matrix (host: streamed in row chunks on two streams)
+  void Predict(const void* data, int dtype, int64_t nrow, int32_t ncol, int data_on_device, double* out, int out_on_device, float* elapsed_ms) {
+    REQUIRE(data && out && nrow > 0, "bad argument");
+    REQUIRE(dtype == 0 || dtype == 1, "data_type must be 0 (float32) or 1 (float64)");
+    REQUIRE(ncol > max_feature_idx_, "the matrix has fewer columns than the model's max_feature_idx + 1");
+    const size_t esize = dtype == 0 ? 4 : 8;
+    int64_t chunk = std::max<int64_t>(1024, (static_cast<int64_t>(64) << 20) / static_cast<int64_t>(ncol * esize));
+    chunk = std::min(chunk, nrow);
+    DevBuf<unsigned char> dx[2]; DevBuf<double> dout[2];
+    if (!data_on_device) for (auto& b : dx) b.alloc(static_cast<size_t>(chunk) * ncol * esize);
+    if (!out_on_device) for (auto& b : dout) b.alloc(static_cast<size_t>(chunk));
+    const PredTable pt{d_nodes_.p, d_leaves_.p, d_nf_.p, d_lf_.p, d_nl_.p, num_trees_};
+    const int tile_rows = static_cast<int>(kPredTileBytes / (static_cast<size_t>(ncol) * esize));
+    cudaEvent_t e0, e1, ej;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreateWithFlags(&ej, cudaEventDisableTiming));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaEventRecord(e0, streams_[0]));
+    CUDA_CHECK(cudaStreamWaitEvent(streams_[1], e0, 0));
+    int k = 0;
+    for (int64_t r0 = 0; r0 < nrow; r0 += chunk, ++k) {
+      const int64_t rows = std::min(chunk, nrow - r0);
+      cudaStream_t st = streams_[k & 1];
+      const unsigned char* src = static_cast<const unsigned char*>(data) + static_cast<size_t>(r0) * ncol * esize;
+      if (!data_on_device) {
+        CUDA_CHECK(cudaMemcpyAsync(dx[k & 1].p, src, static_cast<size_t>(rows) * ncol * esize, cudaMemcpyHostToDevice, st));
+        src = dx[k & 1].p;
+      }
+      double* dst = out_on_device ? out + r0 : dout[k & 1].p;
+      if (tile_rows >= 1) {
+        const int tr = std::min(tile_rows, 64);
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + tr - 1) / tr, 148 * 12));
+        const size_t smem = static_cast<size_t>(tr) * ncol * esize;
+        if (dtype == 0) k_predict<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, tr);
+        else k_predict<double><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, rows, ncol, pt, dst, tr);
+      } else {
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
+        if (dtype == 0) k_predict_wide<float><<<grid, kPredThreads, 0, st>>>(reinterpret_cast<const float*>(src), ncol, rows, pt, dst);
+        else k_predict_wide<double><<<grid, kPredThreads, 0, st>>>(reinterpret_cast<const double*>(src), ncol, rows, pt, dst);
+      }
+      CUDA_CHECK(cudaGetLastError());
+      ++launches_;
+      if (!out_on_device) CUDA_CHECK(cudaMemcpyAsync(out + r0, dst, sizeof(double) * static_cast<size_t>(rows), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_CHECK(cudaEventRecord(ej, streams_[1]));
+    CUDA_CHECK(cudaStreamWaitEvent(streams_[0], ej, 0));
+    CUDA_CHECK(cudaEventRecord(e1, streams_[0]));
+    CUDA_CHECK(cudaStreamSynchronize(streams_[0]));
+    CUDA_CHECK(cudaStreamSynchronize(streams_[1]));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(ej);
+    if (elapsed_ms) *elapsed_ms = ms;
+  }
+
+ private:
+  template <typename T>
+  static void Up(DevBuf<T>& d, const std::vector<T>& h) {
+    d.alloc(h.size());
+    if (!h.empty()) CUDA_CHECK(cudaMemcpy(d.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  }
+  int device_; int32_t num_trees_, max_feature_idx_;
+  int64_t launches_ = 0;
+  cudaStream_t streams_[2] = {nullptr, nullptr};
+  DevBuf<PNode> d_nodes_; DevBuf<double> d_leaves_; DevBuf<int32_t> d_nf_, d_lf_, d_nl_;
+};
+
+}  // namespace b200
+
 // ------------------------------------------------------------------------------------------ C-ABI
 using b200::CudaError;
 using b200::Learner;
 using b200::BinnerCtx;
+using b200::Predictor;
 
 #define API_BEGIN() try {
 #define API_BEGIN_H(h) try { DeviceGuard _dev_guard((h) ? static_cast<Learner*>(h)->inited_device() : -1);
@@ -1524,6 +1634,31 @@ int LGBMB200_BinnerTransform(LGBMB200_BinnerHandle h, const void* data, int32_t 
 int LGBMB200_BinnerFree(LGBMB200_BinnerHandle h) {
   API_BEGIN();
   if (h) { DeviceGuard guard(static_cast<BinnerCtx*>(h)->device()); delete static_cast<BinnerCtx*>(h); }
+  API_END();
+}
+
+// ---- Prediction (predict.cuh)
+int LGBMB200_PredictorCreate(int32_t gpu_device_id, int32_t num_trees, const int32_t* tree_num_leaves, const int32_t* split_feature,
+                             const double* threshold, const int8_t* decision_type, const int32_t* left_child, const int32_t* right_child,
+                             const double* leaf_value, int32_t max_feature_idx, LGBMB200_PredictorHandle* out) {
+  API_BEGIN();
+  if (!out) throw CudaError{"null argument"};
+  DeviceGuard guard(gpu_device_id);
+  *out = new Predictor(gpu_device_id, num_trees, tree_num_leaves, split_feature, threshold, decision_type, left_child, right_child,
+                       leaf_value, max_feature_idx);
+  API_END();
+}
+int LGBMB200_PredictorPredict(LGBMB200_PredictorHandle h, const void* data, int32_t data_type, int32_t nrow, int32_t ncol,
+                              int32_t data_on_device, double* out_raw_score, int32_t out_on_device, float* elapsed_ms) {
+  API_BEGIN();
+  if (!h) throw CudaError{"null argument"};
+  DeviceGuard guard(static_cast<Predictor*>(h)->device());
+  static_cast<Predictor*>(h)->Predict(data, data_type, nrow, ncol, data_on_device, out_raw_score, out_on_device, elapsed_ms);
+  API_END();
+}
+int LGBMB200_PredictorFree(LGBMB200_PredictorHandle h) {
+  API_BEGIN();
+  if (h) { DeviceGuard guard(static_cast<Predictor*>(h)->device()); delete static_cast<Predictor*>(h); }
   API_END();
 }
 

@@ -148,14 +148,18 @@ class Tree:
     leaf_depth: np.ndarray
     root_sum_gradient: float
     root_sum_hessian: float
+    shrink: float = 1.0              # product of the rates applied so far / the bias added: the model text needs them for
+    bias: float = 0.0                # the internal node values (lightgbm_b200/model.py)
 
     def shrinkage(self, rate: float) -> None:
         """Tree::Shrinkage (reference include/LightGBM/tree.h:187-200)."""
         self.leaf_value = self.leaf_value * rate
+        self.shrink *= rate
 
     def add_bias(self, val: float) -> None:
         """Tree::AddBias (reference tree.h:211-230)."""
         self.leaf_value = self.leaf_value + val
+        self.bias += val
 
 
 def _p(a):

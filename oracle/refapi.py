@@ -273,6 +273,37 @@ class RefBooster:
             self.handle = None
 
 
+class RefLoadedBooster:
+    """LGBM_BoosterLoadModelFromString + LGBM_BoosterPredictForMat (c_api.h:690, :1283): the reference scoring a dense
+    matrix with a model text — its own, or one written by lightgbm_b200/model.py."""
+
+    def __init__(self, model_str: str):
+        self.handle = C.c_void_p()
+        it = C.c_int(0)
+        _check(lib().LGBM_BoosterLoadModelFromString(C.c_char_p(model_str.encode()), C.byref(it), C.byref(self.handle)))
+        self.num_iterations = it.value
+
+    def predict(self, X: np.ndarray, raw_score: bool = True) -> np.ndarray:
+        X = np.ascontiguousarray(X)
+        assert X.dtype in (np.float32, np.float64) and X.ndim == 2
+        out = np.zeros(X.shape[0], np.float64)
+        n = C.c_int64(0)
+        _check(lib().LGBM_BoosterPredictForMat(self.handle, X.ctypes.data_as(C.c_void_p),
+                                               C.c_int(C_API_DTYPE_FLOAT32 if X.dtype == np.float32 else C_API_DTYPE_FLOAT64),
+                                               C.c_int32(X.shape[0]), C.c_int32(X.shape[1]), C.c_int(1),
+                                               C.c_int(1 if raw_score else 0), C.c_int(0), C.c_int(-1), C.c_char_p(b"verbosity=-1"),
+                                               C.byref(n), out.ctypes.data_as(C.c_void_p)))
+        assert n.value == X.shape[0]
+        return out
+
+    model_string = RefBooster.model_string
+
+    def free(self):
+        if self.handle:
+            lib().LGBM_BoosterFree(self.handle)
+            self.handle = None
+
+
 class RefDatasetStreamed(RefDataset):
     """The reference's own streaming ingestion (c_api.h LGBM_DatasetCreateByReference + LGBM_DatasetPushRows): bin
     mappers come from a sample Dataset built with LGBM_DatasetCreateFromMat on the first `sample_rows` rows, then the

@@ -14,8 +14,8 @@ INT_KEYS = ("num_leaves", "max_depth", "min_data_in_leaf")
 
 
 def names():
-    # binning_*.npz are the Dataset-construction fixtures of tests/test_binning.py (no trees inside)
-    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith("binning_"))
+    # binning_*.npz / model_*.npz are the fixtures of tests/test_binning.py / tests/test_model.py (different contents)
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith(("binning_", "model_")))
 
 
 class Golden:
