@@ -1072,6 +1072,48 @@ class Learner {
 
 namespace b200 {
 
+// Host -> device streaming of a pageable matrix: chunks are copied by a few host threads into one of two pinned buffers
+// and sent with cudaMemcpyAsync (a pageable cudaMemcpyAsync runs at ~11 GB/s here and blocks the host; pinned, the link
+// speed).  Filling buffer k overlaps the transfer + kernel of the chunk before it.
+class PinnedStager {
+ public:
+  ~PinnedStager() { for (int i = 0; i < 2; ++i) { if (buf_[i]) cudaFreeHost(buf_[i]); if (ev_[i]) cudaEventDestroy(ev_[i]); } }
+  void Reserve(size_t bytes) {
+    if (bytes <= cap_) return;
+    for (int i = 0; i < 2; ++i) {
+      if (buf_[i]) cudaFreeHost(buf_[i]);
+      CUDA_CHECK(cudaMallocHost(&buf_[i], bytes));
+      if (!ev_[i]) CUDA_CHECK(cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming));
+    }
+    cap_ = bytes;
+  }
+  // copy `bytes` from pageable `src` to `dst_dev` on `st` through pinned buffer `k & 1`
+  void Send(int k, void* dst_dev, const void* src, size_t bytes, cudaStream_t st) {
+    const int b = k & 1;
+    if (used_[b]) CUDA_CHECK(cudaEventSynchronize(ev_[b]));       // the transfer that last read this buffer has finished
+    const int nt = static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, bytes >> 22)));
+    if (nt == 1) std::memcpy(buf_[b], src, bytes);
+    else {
+      std::vector<std::thread> pool;
+      const size_t per = (bytes / nt + 63) / 64 * 64;
+      for (int t = 0; t < nt; ++t) {
+        const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
+        pool.emplace_back([=]() { if (hi > lo) std::memcpy(static_cast<char*>(buf_[b]) + lo, static_cast<const char*>(src) + lo, hi - lo); });
+      }
+      for (auto& th : pool) th.join();
+    }
+    CUDA_CHECK(cudaMemcpyAsync(dst_dev, buf_[b], bytes, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaEventRecord(ev_[b], st));
+    used_[b] = true;
+  }
+
+ private:
+  void* buf_[2] = {nullptr, nullptr};
+  cudaEvent_t ev_[2] = {nullptr, nullptr};
+  bool used_[2] = {false, false};
+  size_t cap_ = 0;
+};
+
 class BinnerCtx {
  public:
   explicit BinnerCtx(const LGBMB200_BinConfig& c) : device_(c.gpu_device_id), binner_(ToCfg(c)) {}
@@ -1122,7 +1164,7 @@ class BinnerCtx {
     chunk = std::min(chunk, nrow);
     for (auto& s : streams_) if (!s) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     DevBuf<unsigned char> dx[2], dout[2];
-    if (!data_on_device) for (auto& b : dx) b.alloc(static_cast<size_t>(chunk) * ncol * esize);
+    if (!data_on_device) { for (auto& b : dx) b.alloc(static_cast<size_t>(chunk) * ncol * esize); stager_.Reserve(static_cast<size_t>(chunk) * ncol * esize); }
     if (!out_on_device) for (auto& b : dout) b.alloc(static_cast<size_t>(chunk) * C);
     BinDevTable dt{d_col_first_.p, d_feat_real_.p, d_feat_lo_.p, d_feat_num_bin_.p, d_feat_mfb_.p, d_feat_missing_.p,
                    d_bound_first_.p, d_bound_count_.p, d_bounds32_.p, d_bounds64_.p, static_cast<int32_t>(C)};
@@ -1137,12 +1179,23 @@ class BinnerCtx {
       cudaStream_t st = streams_[k & 1];
       const unsigned char* src = static_cast<const unsigned char*>(data) + static_cast<size_t>(r0) * ncol * esize;
       if (!data_on_device) {
-        CUDA_CHECK(cudaMemcpyAsync(dx[k & 1].p, src, static_cast<size_t>(rows) * ncol * esize, cudaMemcpyHostToDevice, st));
+        stager_.Send(k, dx[k & 1].p, src, static_cast<size_t>(rows) * ncol * esize, st);
         src = dx[k & 1].p;
       }
       uint8_t* dst = out_on_device ? out + r0 * C : dout[k & 1].p;
       const dim3 grid(static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, 148 * 32)), static_cast<unsigned>((C + 31) / 32));
-      if (dtype == 0) k_value_to_bin<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C);
+      const size_t smem = static_cast<size_t>(max_bounds_) * esize + sizeof(VbFeat) * max_feats_ + static_cast<size_t>(kVbRows) * (kVbCols + 1) * esize +
+                          kVbRows * kVbCols;
+      if (smem <= 200 * 1024 && !simple_kernel_) {
+        const dim3 tgrid(static_cast<unsigned>(std::min<int64_t>((rows + kVbRows - 1) / kVbRows, 148 * 16)), static_cast<unsigned>((C + kVbCols - 1) / kVbCols));
+        if (dtype == 0) {
+          CUDA_CHECK(cudaFuncSetAttribute(k_value_to_bin_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+          k_value_to_bin_tile<float><<<tgrid, kVbThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C, max_bounds_, max_feats_);
+        } else {
+          CUDA_CHECK(cudaFuncSetAttribute(k_value_to_bin_tile<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+          k_value_to_bin_tile<double><<<tgrid, kVbThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C, max_bounds_, max_feats_);
+        }
+      } else if (dtype == 0) k_value_to_bin<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C);
       else k_value_to_bin<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C);
       CUDA_CHECK(cudaGetLastError());
       ++launches_;
@@ -1180,12 +1233,24 @@ class BinnerCtx {
     Up(d_col_first_, t.col_first); Up(d_feat_real_, t.feat_real); Up(d_feat_lo_, t.feat_lo); Up(d_feat_num_bin_, t.feat_num_bin);
     Up(d_feat_mfb_, t.feat_mfb); Up(d_feat_missing_, t.feat_missing); Up(d_bound_first_, t.bound_first); Up(d_bound_count_, t.bound_count);
     Up(d_bounds32_, t.bounds32); Up(d_bounds64_, t.bounds64);
+    // shared-memory needs of k_value_to_bin_tile: the widest 32-column tile
+    max_bounds_ = 1; max_feats_ = 1;
+    for (int c0 = 0; c0 < t.num_columns; c0 += kVbCols) {
+      const int c1 = std::min(t.num_columns, c0 + kVbCols);
+      const int f0 = t.col_first[c0], f1 = t.col_first[c1];
+      max_feats_ = std::max(max_feats_, f1 - f0);
+      max_bounds_ = std::max(max_bounds_, t.bound_first[f1] - t.bound_first[f0]);
+    }
+    max_bounds_ = (max_bounds_ + 3) / 4 * 4;
     uploaded_ = true;
   }
 
   int device_;
   Binner binner_;
   bool fitted_ = false, uploaded_ = false;
+  bool simple_kernel_ = std::getenv("LGBMB200_BIN_SIMPLE") != nullptr;       // developer A/B: the one-lane-per-column kernel
+  int max_bounds_ = 1, max_feats_ = 1;
+  PinnedStager stager_;
   int64_t launches_ = 0;
   cudaStream_t streams_[2] = {nullptr, nullptr};
   DevBuf<int32_t> d_col_first_, d_feat_real_, d_feat_lo_, d_feat_num_bin_, d_feat_mfb_, d_feat_missing_, d_bound_first_, d_bound_count_;
@@ -1245,7 +1310,7 @@ class Predictor {
     int64_t chunk = std::max<int64_t>(1024, (static_cast<int64_t>(64) << 20) / static_cast<int64_t>(ncol * esize));
     chunk = std::min(chunk, nrow);
     DevBuf<unsigned char> dx[2]; DevBuf<double> dout[2];
-    if (!data_on_device) for (auto& b : dx) b.alloc(static_cast<size_t>(chunk) * ncol * esize);
+    if (!data_on_device) { for (auto& b : dx) b.alloc(static_cast<size_t>(chunk) * ncol * esize); stager_.Reserve(static_cast<size_t>(chunk) * ncol * esize); }
     if (!out_on_device) for (auto& b : dout) b.alloc(static_cast<size_t>(chunk));
     const PredTable pt{d_nodes_.p, d_leaves_.p, d_nf_.p, d_lf_.p, d_nl_.p, num_trees_};
     const int tile_rows = static_cast<int>(kPredTileBytes / (static_cast<size_t>(ncol) * esize));
@@ -1260,7 +1325,7 @@ class Predictor {
       cudaStream_t st = streams_[k & 1];
       const unsigned char* src = static_cast<const unsigned char*>(data) + static_cast<size_t>(r0) * ncol * esize;
       if (!data_on_device) {
-        CUDA_CHECK(cudaMemcpyAsync(dx[k & 1].p, src, static_cast<size_t>(rows) * ncol * esize, cudaMemcpyHostToDevice, st));
+        stager_.Send(k, dx[k & 1].p, src, static_cast<size_t>(rows) * ncol * esize, st);
         src = dx[k & 1].p;
       }
       double* dst = out_on_device ? out + r0 : dout[k & 1].p;
@@ -1297,6 +1362,7 @@ class Predictor {
     if (!h.empty()) CUDA_CHECK(cudaMemcpy(d.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
   }
   int device_; int32_t num_trees_, max_feature_idx_;
+  PinnedStager stager_;
   int64_t launches_ = 0;
   cudaStream_t streams_[2] = {nullptr, nullptr};
   DevBuf<PNode> d_nodes_; DevBuf<double> d_leaves_; DevBuf<int32_t> d_nf_, d_lf_, d_nl_;

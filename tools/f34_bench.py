@@ -1,0 +1,83 @@
+"""Measurement of the two "next" rows built in round 2, each with the reference's CPU path timed
+beside it on the same host (oracle/_ref through the reference's own C API) and the device-resident kernel against the HBM
+roofline:
+  f-3  Dataset construction: raw float32 matrix -> binned Dataset      (reference: LGBM_DatasetCreateFromMat)
+  f-4  prediction: 100 trees x 127 leaves over the same matrix         (reference: LGBM_BoosterPredictForMat, raw score)
+Prints one JSON object."""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lightgbm_b200 as lgb
+from lightgbm_b200.tree_learner import DeviceArray
+
+n = int(os.environ.get("FB_ROWS", 2_000_000)); f = int(os.environ.get("FB_COLS", 256)); trees = int(os.environ.get("FB_TREES", 100))
+threads = int(os.environ.get("FB_THREADS", os.cpu_count() or 8))
+peak = 6567.4
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+r = np.random.default_rng(0)
+X = np.empty((n, f), np.float32)
+for lo in range(0, n, 1 << 18):
+    X[lo:lo + (1 << 18)] = r.standard_normal((min(1 << 18, n - lo), f), dtype=np.float32)
+X[r.random(n) < 0.01, 3] = np.nan
+w = r.normal(size=32)
+y = (X[:, 4:36] @ w + 0.5 * r.standard_normal(n)).astype(np.float32)
+res = {"rows": n, "cols": f, "host_threads": threads, "hbm_peak_gbs": peak}
+
+# ---- f-3
+t0 = time.time(); b = lgb.Binner({}).fit(X); t_fit = time.time() - t0
+t0 = time.time(); bins_dev, ms_h = b.transform(X, to_device=True); t_tr = time.time() - t0
+dx = DeviceArray(X.nbytes).upload(X)
+ms_d = min(b.transform((dx, np.float32), to_device=True, data_rows=n)[1] for _ in range(5))
+C = b.layout_meta()["num_columns"]
+alg = n * (f * 4 + C)
+res["dataset_construction"] = {
+    "b200": {"fit_host_s": t_fit, "transform_from_host_s": t_tr, "total_s": t_fit + t_tr, "rows_per_s": n / (t_fit + t_tr),
+             "kernel": "k_value_to_bin", "device_resident_ms": ms_d, "achieved_gbs": alg / ms_d / 1e6, "frac_of_hbm_peak": alg / ms_d / 1e6 / peak,
+             "alg_bytes": alg, "h2d_bytes": int(X.nbytes)}}
+from oracle import refapi
+if refapi.available():
+    t0 = time.time()
+    ds = refapi.RefDataset(X, y, dict(device_type="cuda", num_threads=threads, verbosity=-1))
+    t_ref = time.time() - t0
+    res["dataset_construction"]["reference_cpu"] = {"total_s": t_ref, "rows_per_s": n / t_ref, "api": "LGBM_DatasetCreateFromMat", "threads": threads}
+    lay = ds.layout()
+    same = bool(np.array_equal(bins_dev.download(), lay.bins))
+    res["dataset_construction"]["identical_to_reference"] = same
+    ds.free()
+del dx
+
+# ---- f-4: a model of `trees` trees grown on the device-binned matrix
+layout = b.layout(bins_dev); layout.num_total_features = f
+B = lgb.B200Booster(layout, y, lgb.Config(num_leaves=127, min_data_in_leaf=20), learning_rate=0.1)
+t0 = time.time()
+for _ in range(trees):
+    B.update()
+res["train"] = {"trees": trees, "leaves": 127, "wall_s": time.time() - t0}
+m = B.to_model()
+text = m.to_string()
+raw, ms_h = m.predict_raw(X, return_ms=True)
+t0 = time.time(); raw = m.predict_raw(X); t_pred = time.time() - t0
+# device-resident input / output
+import ctypes as Ct
+from lightgbm_b200._lib import lib, check
+dx = DeviceArray(X.nbytes).upload(X); dout = DeviceArray(n * 8)
+best = 1e30
+for _ in range(5):
+    ms = Ct.c_float(0)
+    check(lib().LGBMB200_PredictorPredict(m._predictor(), dx.ptr, Ct.c_int32(0), Ct.c_int32(n), Ct.c_int32(f), Ct.c_int32(1), dout.ptr, Ct.c_int32(1), Ct.byref(ms)))
+    best = min(best, ms.value)
+assert dout.download(np.float64, n).tobytes() == raw.tobytes()
+alg = n * (f * 4 + 8)
+res["predict"] = {"b200": {"from_host_s": t_pred, "rows_per_s": n / t_pred, "kernel": "k_predict", "device_resident_ms": best,
+                           "achieved_gbs": alg / best / 1e6, "frac_of_hbm_peak": alg / best / 1e6 / peak, "alg_bytes": alg,
+                           "tree_visits_per_s": n * trees / (best * 1e-3)}}
+if refapi.available():
+    loaded = refapi.RefLoadedBooster(text)
+    sub = min(n, int(os.environ.get("FB_REF_PRED_ROWS", 500_000)))
+    t0 = time.time(); ref_raw = loaded.predict(X[:sub], raw_score=True); t_ref = time.time() - t0
+    res["predict"]["reference_cpu"] = {"rows": sub, "total_s": t_ref, "rows_per_s": sub / t_ref, "api": "LGBM_BoosterPredictForMat (model text written by this repo)"}
+    res["predict"]["bit_identical_to_reference"] = bool(ref_raw.tobytes() == raw[:sub].tobytes())
+    loaded.free()
+print(json.dumps(res))
