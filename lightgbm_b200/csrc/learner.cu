@@ -1241,7 +1241,7 @@ class BinnerCtx {
       max_feats_ = std::max(max_feats_, f1 - f0);
       max_bounds_ = std::max(max_bounds_, t.bound_first[f1] - t.bound_first[f0]);
     }
-    max_bounds_ = (max_bounds_ + 3) / 4 * 4;
+    max_bounds_ = (max_bounds_ + (max_bounds_ >> 5) + 4) / 4 * 4;            // skewed layout: one pad word per 32 (binning.cuh vb_skew)
     uploaded_ = true;
   }
 
@@ -1273,29 +1273,27 @@ class Predictor {
             int32_t max_feature_idx)
       : device_(device), num_trees_(num_trees), max_feature_idx_(max_feature_idx) {
     REQUIRE(num_trees >= 0 && tree_num_leaves, "bad model");
-    std::vector<PNode> nodes; std::vector<double> leaves; std::vector<int32_t> nf, lf, nl;
+    std::vector<PNodeA> na; std::vector<PNodeB> nb; std::vector<double> leaves; std::vector<int32_t> nf, lf, nl;
     int64_t ni = 0, li = 0;
     for (int t = 0; t < num_trees; ++t) {
       const int L = tree_num_leaves[t];
       REQUIRE(L >= 1, "a tree needs at least one leaf");
-      nf.push_back(static_cast<int32_t>(nodes.size())); lf.push_back(static_cast<int32_t>(leaves.size())); nl.push_back(L);
+      nf.push_back(static_cast<int32_t>(na.size())); lf.push_back(static_cast<int32_t>(leaves.size())); nl.push_back(L);
       for (int i = 0; i < L - 1; ++i, ++ni) {
-        PNode n;
-        n.threshold = threshold[ni]; n.feature = split_feature[ni]; n.left = left_child[ni]; n.right = right_child[ni];
-        n.decision = static_cast<int32_t>(decision_type[ni]) & 0xff;
-        REQUIRE(!(n.decision & 1), "categorical splits are not supported");
-        REQUIRE(n.feature >= 0 && n.feature <= max_feature_idx, "split feature out of range");
-        REQUIRE(n.left < L - 1 && n.right < L - 1 && ~n.left < L && ~n.right < L, "child index out of range");
-        nodes.push_back(n);
+        PNodeA a; PNodeB b;
+        a.threshold = threshold[ni]; a.feature = split_feature[ni]; b.left = left_child[ni]; b.right = right_child[ni];
+        a.decision = static_cast<int32_t>(decision_type[ni]) & 0xff;
+        REQUIRE(!(a.decision & 1), "categorical splits are not supported");
+        REQUIRE(a.feature >= 0 && a.feature <= max_feature_idx, "split feature out of range");
+        REQUIRE(b.left < L - 1 && b.right < L - 1 && ~b.left < L && ~b.right < L, "child index out of range");
+        na.push_back(a); nb.push_back(b);
       }
       for (int i = 0; i < L; ++i, ++li) leaves.push_back(leaf_value[li]);
     }
     if (device_ >= 0) CUDA_CHECK(cudaSetDevice(device_));
-    Up(d_nodes_, nodes); Up(d_leaves_, leaves); Up(d_nf_, nf); Up(d_lf_, lf); Up(d_nl_, nl);
+    Up(d_na_, na); Up(d_nb_, nb); Up(d_leaves_, leaves); Up(d_nf_, nf); Up(d_lf_, lf); Up(d_nl_, nl);
     CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[0], cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[1], cudaStreamNonBlocking));
-    CUDA_CHECK(cudaFuncSetAttribute(k_predict<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredTileBytes));
-    CUDA_CHECK(cudaFuncSetAttribute(k_predict<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPredTileBytes));
   }
   ~Predictor() { for (auto& s : streams_) if (s) cudaStreamDestroy(s); }
   int device() const { return device_; }
@@ -1312,8 +1310,11 @@ class Predictor {
     DevBuf<unsigned char> dx[2]; DevBuf<double> dout[2];
     if (!data_on_device) { for (auto& b : dx) b.alloc(static_cast<size_t>(chunk) * ncol * esize); stager_.Reserve(static_cast<size_t>(chunk) * ncol * esize); }
     if (!out_on_device) for (auto& b : dout) b.alloc(static_cast<size_t>(chunk));
-    const PredTable pt{d_nodes_.p, d_leaves_.p, d_nf_.p, d_lf_.p, d_nl_.p, num_trees_};
-    const int tile_rows = static_cast<int>(kPredTileBytes / (static_cast<size_t>(ncol) * esize));
+    const PredTable pt{d_na_.p, d_nb_.p, d_leaves_.p, d_nf_.p, d_lf_.p, d_nl_.p, num_trees_};
+    // odd row stride (in elements): 32 lanes reading one feature of 32 rows hit 32 different banks
+    const int stride = ncol | 1;
+    int tile_rows = static_cast<int>(kPredTileBytes / (static_cast<size_t>(stride) * esize));
+    tile_rows = std::min(tile_rows, kPredThreads) / 32 * 32;           // whole warps of rows; 0 => rows too wide to stage
     cudaEvent_t e0, e1, ej;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreateWithFlags(&ej, cudaEventDisableTiming));
     CUDA_CHECK(cudaDeviceSynchronize());
@@ -1329,14 +1330,19 @@ class Predictor {
         src = dx[k & 1].p;
       }
       double* dst = out_on_device ? out + r0 : dout[k & 1].p;
-      if (tile_rows >= 1) {
-        const int tr = std::min(tile_rows, 64);
-        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + tr - 1) / tr, 148 * 12));
-        const size_t smem = static_cast<size_t>(tr) * ncol * esize;
-        if (dtype == 0) k_predict<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, tr);
-        else k_predict<double><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, rows, ncol, pt, dst, tr);
+      if (tile_rows >= 32) {
+        const size_t smem = static_cast<size_t>(tile_rows) * stride * esize;
+        const int per_sm = std::max<int>(1, static_cast<int>((220 * 1024) / smem));
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + tile_rows - 1) / tile_rows, 148 * per_sm));
+        if (dtype == 0) {
+          CUDA_CHECK(cudaFuncSetAttribute(k_predict<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+          k_predict<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride);
+        } else {
+          CUDA_CHECK(cudaFuncSetAttribute(k_predict<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+          k_predict<double><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride);
+        }
       } else {
-        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, 148 * 8));
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + kPredThreads - 1) / kPredThreads, 148 * 8));
         if (dtype == 0) k_predict_wide<float><<<grid, kPredThreads, 0, st>>>(reinterpret_cast<const float*>(src), ncol, rows, pt, dst);
         else k_predict_wide<double><<<grid, kPredThreads, 0, st>>>(reinterpret_cast<const double*>(src), ncol, rows, pt, dst);
       }
@@ -1365,7 +1371,7 @@ class Predictor {
   PinnedStager stager_;
   int64_t launches_ = 0;
   cudaStream_t streams_[2] = {nullptr, nullptr};
-  DevBuf<PNode> d_nodes_; DevBuf<double> d_leaves_; DevBuf<int32_t> d_nf_, d_lf_, d_nl_;
+  DevBuf<PNodeA> d_na_; DevBuf<PNodeB> d_nb_; DevBuf<double> d_leaves_; DevBuf<int32_t> d_nf_, d_lf_, d_nl_;
 };
 
 }  // namespace b200
