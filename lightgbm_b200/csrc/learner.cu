@@ -1160,8 +1160,9 @@ class BinnerCtx {
     const BinTable& t = binner_.table();
     const int64_t ncol = t.num_total_features, C = t.num_columns;
     const size_t esize = dtype == 0 ? 4 : 8;
-    int64_t chunk = std::max<int64_t>(1024, (static_cast<int64_t>(64) << 20) / static_cast<int64_t>(ncol * esize));
+    int64_t chunk = std::max<int64_t>(1024, (static_cast<int64_t>(128) << 20) / static_cast<int64_t>(ncol * esize));
     chunk = std::min(chunk, nrow);
+    if (data_on_device && out_on_device) chunk = nrow;          // nothing to stage: one launch over all rows
     for (auto& s : streams_) if (!s) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     DevBuf<unsigned char> dx[2], dout[2];
     if (!data_on_device) { for (auto& b : dx) b.alloc(static_cast<size_t>(chunk) * ncol * esize); stager_.Reserve(static_cast<size_t>(chunk) * ncol * esize); }
@@ -1187,7 +1188,10 @@ class BinnerCtx {
       const size_t smem = static_cast<size_t>(max_bounds_) * esize + sizeof(VbFeat) * max_feats_ + static_cast<size_t>(kVbRows) * (kVbCols + 1) * esize +
                           kVbRows * kVbCols;
       if (smem <= 200 * 1024 && !simple_kernel_) {
-        const dim3 tgrid(static_cast<unsigned>(std::min<int64_t>((rows + kVbRows - 1) / kVbRows, 148 * 16)), static_cast<unsigned>((C + kVbCols - 1) / kVbCols));
+        // a CTA loads its column tile's bounds once and then walks >= 8 row tiles; 148 SMs x 5 resident CTAs to fill
+        const int64_t row_tiles = (rows + kVbRows - 1) / kVbRows, col_tiles = (C + kVbCols - 1) / kVbCols;
+        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>((row_tiles + 7) / 8, std::max<int64_t>(1, (148 * 10 + col_tiles - 1) / col_tiles)));
+        const dim3 tgrid(static_cast<unsigned>(gx), static_cast<unsigned>(col_tiles));
         if (dtype == 0) {
           CUDA_CHECK(cudaFuncSetAttribute(k_value_to_bin_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
           k_value_to_bin_tile<float><<<tgrid, kVbThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C, max_bounds_, max_feats_);
@@ -1307,14 +1311,16 @@ class Predictor {
     const size_t esize = dtype == 0 ? 4 : 8;
     int64_t chunk = std::max<int64_t>(1024, (static_cast<int64_t>(64) << 20) / static_cast<int64_t>(ncol * esize));
     chunk = std::min(chunk, nrow);
+    if (data_on_device && out_on_device) chunk = nrow;          // nothing to stage: one launch over all rows
     DevBuf<unsigned char> dx[2]; DevBuf<double> dout[2];
     if (!data_on_device) { for (auto& b : dx) b.alloc(static_cast<size_t>(chunk) * ncol * esize); stager_.Reserve(static_cast<size_t>(chunk) * ncol * esize); }
     if (!out_on_device) for (auto& b : dout) b.alloc(static_cast<size_t>(chunk));
     const PredTable pt{d_na_.p, d_nb_.p, d_leaves_.p, d_nf_.p, d_lf_.p, d_nl_.p, num_trees_};
     // odd row stride (in elements): 32 lanes reading one feature of 32 rows hit 32 different banks
     const int stride = ncol | 1;
-    int tile_rows = static_cast<int>(kPredTileBytes / (static_cast<size_t>(stride) * esize));
-    tile_rows = std::min(tile_rows, kPredThreads) / 32 * 32;           // whole warps of rows; 0 => rows too wide to stage
+    // rows per CTA tile: 64 when two such CTAs fit an SM, else 32; 0 => rows too wide to stage
+    auto tile_bytes = [&](int R) { return static_cast<size_t>(kPredPass) * R * 8 + static_cast<size_t>(R) * stride * esize; };
+    const int tile_rows = tile_bytes(64) <= 110 * 1024 ? 64 : (tile_bytes(32) <= 220 * 1024 ? 32 : 0);
     cudaEvent_t e0, e1, ej;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreateWithFlags(&ej, cudaEventDisableTiming));
     CUDA_CHECK(cudaDeviceSynchronize());
@@ -1331,8 +1337,8 @@ class Predictor {
       }
       double* dst = out_on_device ? out + r0 : dout[k & 1].p;
       if (tile_rows >= 32) {
-        const size_t smem = static_cast<size_t>(tile_rows) * stride * esize;
-        const int per_sm = std::max<int>(1, static_cast<int>((220 * 1024) / smem));
+        const size_t smem = tile_bytes(tile_rows);
+        const int per_sm = std::max<int>(1, std::min<int>(8, static_cast<int>((220 * 1024) / smem)));
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + tile_rows - 1) / tile_rows, 148 * per_sm));
         if (dtype == 0) {
           CUDA_CHECK(cudaFuncSetAttribute(k_predict<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -6,10 +6,9 @@
 //
 // Layout: a CTA stages a tile of rows in shared memory with coalesced loads — X is read from HBM exactly once, 4 or 8
 // bytes per cell, the only traffic that scales with the data — with an odd row stride, so that 32 lanes reading one
-// feature of 32 different rows hit 32 banks.  A THREAD owns a row and walks the trees in order, two at a time (two
-// independent chains per lane), adding their outputs in tree order: the double-precision sum is the reference's sequential
-// `output += tree->Predict(row)` bit for bit.  The 32 lanes of a warp are on the same tree, so near the root they read
-// the same node (one L1 wavefront) and a tree's 126 nodes (3 KB) stay in L1 while the warp is on it.
+// feature of 32 different rows hit 32 banks.  The lanes of a warp are 32 ROWS on the same tree: near the root they read
+// the same node (one L1 wavefront) and a tree's 126 nodes (3 KB) stay in L1 while the warp is on it.  Tree outputs are
+// added in tree order: the double-precision sum is the reference's sequential `output += tree->Predict(row)` bit for bit.
 // (The first version put the lanes on 32 different TREES: every node load touched 32 cache lines — 11.6 G tree visits/s,
 // 1.8 % of the HBM roofline at 2M x 256 x 100 trees.)
 #pragma once
@@ -50,40 +49,71 @@ __device__ __forceinline__ int pred_step(const PNodeA* __restrict__ na, const PN
   return (v <= a.threshold) ? b.left : b.right;
 }
 
+// leaf values of trees ta and tb (tb < 0: only ta) for one row, the two walks interleaved (two independent chains per lane)
+template <typename T>
+__device__ __forceinline__ void pred_pair(const PredTable& m, int ta, int tb, const T* row, double* va, double* vb) {
+  const int fa = m.node_first[ta], fb = tb >= 0 ? m.node_first[tb] : 0;
+  int na = m.num_leaves[ta] > 1 ? 0 : -1;                   // a single-leaf tree: ~0 = leaf 0
+  int nb = (tb >= 0 && m.num_leaves[tb] > 1) ? 0 : -1;
+  while (na >= 0 || nb >= 0) {
+    if (na >= 0) na = pred_step<T>(m.node_a + fa, m.node_b + fa, na, row);
+    if (nb >= 0) nb = pred_step<T>(m.node_a + fb, m.node_b + fb, nb, row);
+  }
+  *va = m.leaf_value[m.leaf_first[ta] + ~na];
+  if (tb >= 0) *vb = m.leaf_value[m.leaf_first[tb] + ~nb];
+}
+
 template <typename T>
 __device__ __forceinline__ double pred_row(const PredTable& m, const T* row) {
   double sum = 0.0;
   for (int t = 0; t < m.num_trees; t += 2) {
-    const bool two = t + 1 < m.num_trees;
-    const int f0 = m.node_first[t], f1 = two ? m.node_first[t + 1] : 0;
-    int n0 = m.num_leaves[t] > 1 ? 0 : -1;                 // a single-leaf tree: ~0 = leaf 0
-    int n1 = (two && m.num_leaves[t + 1] > 1) ? 0 : -1;
-    while (n0 >= 0 || n1 >= 0) {
-      if (n0 >= 0) n0 = pred_step<T>(m.node_a + f0, m.node_b + f0, n0, row);
-      if (n1 >= 0) n1 = pred_step<T>(m.node_a + f1, m.node_b + f1, n1, row);
-    }
-    sum += m.leaf_value[m.leaf_first[t] + ~n0];             // tree order: the reference's summation
-    if (two) sum += m.leaf_value[m.leaf_first[t + 1] + ~n1];
+    double va = 0.0, vb = 0.0;
+    pred_pair<T>(m, t, t + 1 < m.num_trees ? t + 1 : -1, row, &va, &vb);
+    sum += va;                                               // tree order: the reference's summation
+    if (t + 1 < m.num_trees) sum += vb;
   }
   return sum;
 }
 
+// A CTA of 256 threads scores a tile of R = 64 (or 32) rows: thread = (row, tree group g of G = 256 / R).  The trees are
+// taken kPredPass at a time: group g walks trees g, g + G, ... of the pass and parks the leaf values in shared memory,
+// then the row's g = 0 thread adds the pass IN TREE ORDER to its running sum.  All 256 threads walk trees (the earlier
+// one-thread-per-row form left a CTA with 160 busy threads and one CTA per SM: 40 ms for 2M x 256 x 100 trees; the walks
+// are latency-bound, so what counts is the number of independent chains in flight per SM).
+constexpr int kPredPass = 32;
+
 template <typename T>
 __global__ void __launch_bounds__(kPredThreads) k_predict(const T* __restrict__ x, int64_t ld, int64_t nrow, int32_t ncol, const PredTable m,
-                                                          double* __restrict__ out, int32_t tile_rows, int32_t stride) {
+                                                          double* __restrict__ out, int32_t R, int32_t stride) {
   extern __shared__ __align__(16) unsigned char psmem[];
-  T* tile = reinterpret_cast<T*>(psmem);
+  double* vals = reinterpret_cast<double*>(psmem);                       // [kPredPass][R]
+  T* tile = reinterpret_cast<T*>(vals + kPredPass * R);                  // [R][stride]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kPredThreads / 32;
-  for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * tile_rows; r0 < nrow; r0 += static_cast<int64_t>(gridDim.x) * tile_rows) {
-    const int rows = static_cast<int>(min(static_cast<int64_t>(tile_rows), nrow - r0));
-    for (int r = warp; r < rows; r += kWarps) {
-      const T* src = x + (r0 + r) * ld;
+  const int row = threadIdx.x & (R - 1), g = threadIdx.x / R, G = kPredThreads / R;
+  for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * R; r0 < nrow; r0 += static_cast<int64_t>(gridDim.x) * R) {
+    const int rows = static_cast<int>(min(static_cast<int64_t>(R), nrow - r0));
+    for (int r = warp; r < R; r += kWarps) {
+      const T* src = x + (r0 + min(r, rows - 1)) * ld;                   // ragged last tile: repeat its last row
       for (int c = lane; c < ncol; c += 32) tile[r * stride + c] = src[c];
     }
     __syncthreads();
-    if (static_cast<int>(threadIdx.x) < rows) out[r0 + threadIdx.x] = pred_row<T>(m, tile + threadIdx.x * stride);
-    __syncthreads();
+    const T* my = tile + row * stride;
+    double sum = 0.0;
+    for (int t0 = 0; t0 < m.num_trees; t0 += kPredPass) {
+      const int cnt = min(kPredPass, m.num_trees - t0);
+      for (int k = g; k < cnt; k += 2 * G) {
+        double va = 0.0, vb = 0.0;
+        const int kb = k + G;
+        pred_pair<T>(m, t0 + k, kb < cnt ? t0 + kb : -1, my, &va, &vb);
+        vals[k * R + row] = va;
+        if (kb < cnt) vals[kb * R + row] = vb;
+      }
+      __syncthreads();
+      if (g == 0) { for (int k = 0; k < cnt; ++k) sum += vals[k * R + row]; }   // tree order: the reference's summation
+      __syncthreads();
+    }
+    if (g == 0 && row < rows) out[r0 + row] = sum;
   }
 }
 
