@@ -1237,15 +1237,21 @@ class BinnerCtx {
     Up(d_col_first_, t.col_first); Up(d_feat_real_, t.feat_real); Up(d_feat_lo_, t.feat_lo); Up(d_feat_num_bin_, t.feat_num_bin);
     Up(d_feat_mfb_, t.feat_mfb); Up(d_feat_missing_, t.feat_missing); Up(d_bound_first_, t.bound_first); Up(d_bound_count_, t.bound_count);
     Up(d_bounds32_, t.bounds32); Up(d_bounds64_, t.bounds64);
-    // shared-memory needs of k_value_to_bin_tile: the widest 32-column tile
+    // shared-memory needs of k_value_to_bin_tile: the widest 32-column tile (padded, skewed bound layout: binning.cuh)
     max_bounds_ = 1; max_feats_ = 1;
     for (int c0 = 0; c0 < t.num_columns; c0 += kVbCols) {
       const int c1 = std::min(t.num_columns, c0 + kVbCols);
       const int f0 = t.col_first[c0], f1 = t.col_first[c1];
       max_feats_ = std::max(max_feats_, f1 - f0);
-      max_bounds_ = std::max(max_bounds_, t.bound_first[f1] - t.bound_first[f0]);
+      int words = 0;
+      for (int f = f0; f < f1; ++f) {
+        int depth = 0;
+        while ((1 << depth) - 1 < t.bound_count[f]) ++depth;
+        words += vb_slots(depth);
+      }
+      max_bounds_ = std::max(max_bounds_, words);
     }
-    max_bounds_ = (max_bounds_ + (max_bounds_ >> 5) + 4) / 4 * 4;            // skewed layout: one pad word per 32 (binning.cuh vb_skew)
+    max_bounds_ = (max_bounds_ + 3) / 4 * 4;
     uploaded_ = true;
   }
 
@@ -1319,7 +1325,8 @@ class Predictor {
     // odd row stride (in elements): 32 lanes reading one feature of 32 rows hit 32 different banks
     const int stride = ncol | 1;
     // rows per CTA tile: 64 when two such CTAs fit an SM, else 32; 0 => rows too wide to stage
-    auto tile_bytes = [&](int R) { return static_cast<size_t>(kPredPass) * R * 8 + static_cast<size_t>(R) * stride * esize; };
+    const int pass = std::getenv("LGBMB200_PRED_PASS") ? std::max(2, std::min(kPredPassMax, std::atoi(std::getenv("LGBMB200_PRED_PASS")))) : kPredPassMax;
+    auto tile_bytes = [&](int R) { return static_cast<size_t>(pass) * R * 8 + static_cast<size_t>(R) * stride * esize; };
     const int tile_rows = tile_bytes(64) <= 110 * 1024 ? 64 : (tile_bytes(32) <= 220 * 1024 ? 32 : 0);
     cudaEvent_t e0, e1, ej;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreateWithFlags(&ej, cudaEventDisableTiming));
@@ -1342,10 +1349,10 @@ class Predictor {
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + tile_rows - 1) / tile_rows, 148 * per_sm));
         if (dtype == 0) {
           CUDA_CHECK(cudaFuncSetAttribute(k_predict<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-          k_predict<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride);
+          k_predict<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride, pass);
         } else {
           CUDA_CHECK(cudaFuncSetAttribute(k_predict<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-          k_predict<double><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride);
+          k_predict<double><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride, pass);
         }
       } else {
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + kPredThreads - 1) / kPredThreads, 148 * 8));

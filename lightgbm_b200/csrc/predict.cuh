@@ -14,7 +14,14 @@
 #pragma once
 #include <cstdint>
 
+#include "hist_common.cuh"
+
 namespace b200 {
+
+__device__ __forceinline__ void cp_async_elem(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(double* smem_dst, const double* gsrc) { cp_async8(smem_dst, gsrc); }
 
 struct __align__(16) PNodeA { double threshold; int32_t feature; int32_t decision; };   // decision_type_: bit 1 default left, bits 2..3 missing type
 struct __align__(8) PNodeB { int32_t left, right; };                                    // >= 0: node, < 0: ~leaf
@@ -76,32 +83,35 @@ __device__ __forceinline__ double pred_row(const PredTable& m, const T* row) {
 }
 
 // A CTA of 256 threads scores a tile of R = 64 (or 32) rows: thread = (row, tree group g of G = 256 / R).  The trees are
-// taken kPredPass at a time: group g walks trees g, g + G, ... of the pass and parks the leaf values in shared memory,
+// taken `pass` (32) at a time: group g walks trees g, g + G, ... of the pass and parks the leaf values in shared memory,
 // then the row's g = 0 thread adds the pass IN TREE ORDER to its running sum.  All 256 threads walk trees (the earlier
 // one-thread-per-row form left a CTA with 160 busy threads and one CTA per SM: 40 ms for 2M x 256 x 100 trees; the walks
 // are latency-bound, so what counts is the number of independent chains in flight per SM).
-constexpr int kPredPass = 32;
+constexpr int kPredPassMax = 32;
 
 template <typename T>
 __global__ void __launch_bounds__(kPredThreads) k_predict(const T* __restrict__ x, int64_t ld, int64_t nrow, int32_t ncol, const PredTable m,
-                                                          double* __restrict__ out, int32_t R, int32_t stride) {
+                                                          double* __restrict__ out, int32_t R, int32_t stride, int32_t pass) {
   extern __shared__ __align__(16) unsigned char psmem[];
-  double* vals = reinterpret_cast<double*>(psmem);                       // [kPredPass][R]
-  T* tile = reinterpret_cast<T*>(vals + kPredPass * R);                  // [R][stride]
+  double* vals = reinterpret_cast<double*>(psmem);                       // [pass][R]
+  T* tile = reinterpret_cast<T*>(vals + pass * R);                       // [R][stride]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kPredThreads / 32;
   const int row = threadIdx.x & (R - 1), g = threadIdx.x / R, G = kPredThreads / R;
   for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * R; r0 < nrow; r0 += static_cast<int64_t>(gridDim.x) * R) {
     const int rows = static_cast<int>(min(static_cast<int64_t>(R), nrow - r0));
+    // asynchronous element copies (LDGSTS): every thread has its whole share of the tile in flight at once
     for (int r = warp; r < R; r += kWarps) {
       const T* src = x + (r0 + min(r, rows - 1)) * ld;                   // ragged last tile: repeat its last row
-      for (int c = lane; c < ncol; c += 32) tile[r * stride + c] = src[c];
+      for (int c = lane; c < ncol; c += 32) cp_async_elem(tile + r * stride + c, src + c);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     const T* my = tile + row * stride;
     double sum = 0.0;
-    for (int t0 = 0; t0 < m.num_trees; t0 += kPredPass) {
-      const int cnt = min(kPredPass, m.num_trees - t0);
+    for (int t0 = 0; t0 < m.num_trees; t0 += pass) {
+      const int cnt = min(pass, m.num_trees - t0);
       for (int k = g; k < cnt; k += 2 * G) {
         double va = 0.0, vb = 0.0;
         const int kb = k + G;
@@ -110,7 +120,10 @@ __global__ void __launch_bounds__(kPredThreads) k_predict(const T* __restrict__ 
         if (kb < cnt) vals[kb * R + row] = vb;
       }
       __syncthreads();
-      if (g == 0) { for (int k = 0; k < cnt; ++k) sum += vals[k * R + row]; }   // tree order: the reference's summation
+      if (g == 0) {
+#pragma unroll 8
+        for (int k = 0; k < cnt; ++k) sum += vals[k * R + row];          // tree order: the reference's summation
+      }
       __syncthreads();
     }
     if (g == 0 && row < rows) out[r0 + row] = sum;
