@@ -1169,6 +1169,8 @@ class BinnerCtx {
     if (!out_on_device) for (auto& b : dout) b.alloc(static_cast<size_t>(chunk) * C);
     BinDevTable dt{d_col_first_.p, d_feat_real_.p, d_feat_lo_.p, d_feat_num_bin_.p, d_feat_mfb_.p, d_feat_missing_.p,
                    d_bound_first_.p, d_bound_count_.p, d_bounds32_.p, d_bounds64_.p, static_cast<int32_t>(C)};
+    BinDevTable ro{d_ro_col_first_.p, d_ro_real_.p, d_ro_lo_.p, d_ro_num_bin_.p, d_ro_mfb_.p, d_ro_missing_.p,
+                   d_ro_bound_first_.p, d_ro_bound_count_.p, d_bounds32_.p, d_bounds64_.p, static_cast<int32_t>(t.num_features)};
     cudaEvent_t e0, e1, ej;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreateWithFlags(&ej, cudaEventDisableTiming));
     CUDA_CHECK(cudaDeviceSynchronize());
@@ -1184,25 +1186,56 @@ class BinnerCtx {
         src = dx[k & 1].p;
       }
       uint8_t* dst = out_on_device ? out + r0 * C : dout[k & 1].p;
-      const dim3 grid(static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, 148 * 32)), static_cast<unsigned>((C + 31) / 32));
       const size_t smem = static_cast<size_t>(max_bounds_) * esize + sizeof(VbFeat) * max_feats_ + static_cast<size_t>(kVbRows) * (kVbCols + 1) * esize +
                           kVbRows * kVbCols;
       if (smem <= 200 * 1024 && !simple_kernel_) {
-        // a CTA loads its column tile's bounds once and then walks >= 8 row tiles; 148 SMs x 5 resident CTAs to fill
-        const int64_t row_tiles = (rows + kVbRows - 1) / kVbRows, col_tiles = (C + kVbCols - 1) / kVbCols;
-        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>((row_tiles + 7) / 8, std::max<int64_t>(1, (148 * 10 + col_tiles - 1) / col_tiles)));
-        const dim3 tgrid(static_cast<unsigned>(gx), static_cast<unsigned>(col_tiles));
+        // Step 1 reads the matrix in REAL feature order (coalesced whatever the stored column order is) and writes one byte
+        // per feature; step 2 (k_bundle_columns) moves the bytes to their stored columns.  Both run over row pieces whose
+        // byte image fits L2, so the intermediate never reaches DRAM.  Identity layouts skip step 2.
+        const int64_t Fu = t.num_features;
+        const bool direct = t.identity_order;
+        const int64_t piece = direct ? rows : std::max<int64_t>(kVbRows, std::min<int64_t>(rows, (static_cast<int64_t>(48) << 20) / Fu / kVbRows * kVbRows));
+        if (!direct && tmp_[k & 1].n < static_cast<size_t>(piece * Fu)) tmp_[k & 1].alloc(static_cast<size_t>(piece * Fu));
+        int per_sm = 1, sms = 148;
         if (dtype == 0) {
           CUDA_CHECK(cudaFuncSetAttribute(k_value_to_bin_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-          k_value_to_bin_tile<float><<<tgrid, kVbThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C, max_bounds_, max_feats_);
+          CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_value_to_bin_tile<float>, kVbThreads, smem));
         } else {
           CUDA_CHECK(cudaFuncSetAttribute(k_value_to_bin_tile<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-          k_value_to_bin_tile<double><<<tgrid, kVbThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C, max_bounds_, max_feats_);
+          CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_value_to_bin_tile<double>, kVbThreads, smem));
         }
-      } else if (dtype == 0) k_value_to_bin<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C);
-      else k_value_to_bin<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C);
+        { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        const int64_t slots = static_cast<int64_t>(std::max(1, per_sm)) * sms;
+        const int64_t col_tiles = (Fu + kVbCols - 1) / kVbCols;
+        const size_t bsmem = static_cast<size_t>(kBcRows) * ((Fu + 3) / 4 * 4 + 4);
+        if (!direct) CUDA_CHECK(cudaFuncSetAttribute(k_bundle_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bsmem)));
+        for (int64_t p0 = 0; p0 < rows; p0 += piece) {
+          const int64_t prow = std::min(piece, rows - p0);
+          // a CTA loads its feature tile's bounds once and then walks its share of the row tiles; the grid is ONE wave of
+          // resident CTAs (the tiles of a CTA are many and equal: a partial second wave would cost a whole one)
+          const int64_t row_tiles = (prow + kVbRows - 1) / kVbRows;
+          const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(row_tiles, std::max<int64_t>(1, slots / col_tiles)));
+          const dim3 tgrid(static_cast<unsigned>(gx), static_cast<unsigned>(col_tiles));
+          uint8_t* o1 = direct ? dst + p0 * C : tmp_[k & 1].p;
+          const int64_t pitch1 = direct ? C : Fu;
+          const unsigned char* s1 = src + static_cast<size_t>(p0) * ncol * esize;
+          if (dtype == 0) k_value_to_bin_tile<float><<<tgrid, kVbThreads, smem, st>>>(reinterpret_cast<const float*>(s1), ncol, static_cast<int32_t>(prow), ro, o1, pitch1, max_bounds_, max_feats_);
+          else k_value_to_bin_tile<double><<<tgrid, kVbThreads, smem, st>>>(reinterpret_cast<const double*>(s1), ncol, static_cast<int32_t>(prow), ro, o1, pitch1, max_bounds_, max_feats_);
+          ++launches_;
+          if (!direct) {
+            const unsigned g2 = static_cast<unsigned>(std::min<int64_t>((prow + kBcRows - 1) / kBcRows, static_cast<int64_t>(sms) * 8));
+            k_bundle_columns<<<g2, 256, bsmem, st>>>(tmp_[k & 1].p, Fu, static_cast<int32_t>(prow), static_cast<int32_t>(Fu), d_col_first_.p, d_feat_pos_.p,
+                                                    static_cast<int32_t>(C), dst + p0 * C, C);
+            ++launches_;
+          }
+        }
+      } else {
+        const dim3 grid(static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, 148 * 32)), static_cast<unsigned>((C + 31) / 32));
+        if (dtype == 0) k_value_to_bin<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C);
+        else k_value_to_bin<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(src), ncol, static_cast<int32_t>(rows), dt, dst, C);
+        ++launches_;
+      }
       CUDA_CHECK(cudaGetLastError());
-      ++launches_;
       if (!out_on_device) CUDA_CHECK(cudaMemcpyAsync(out + r0 * C, dst, static_cast<size_t>(rows) * C, cudaMemcpyDeviceToHost, st));
     }
     CUDA_CHECK(cudaEventRecord(ej, streams_[1]));
@@ -1237,16 +1270,18 @@ class BinnerCtx {
     Up(d_col_first_, t.col_first); Up(d_feat_real_, t.feat_real); Up(d_feat_lo_, t.feat_lo); Up(d_feat_num_bin_, t.feat_num_bin);
     Up(d_feat_mfb_, t.feat_mfb); Up(d_feat_missing_, t.feat_missing); Up(d_bound_first_, t.bound_first); Up(d_bound_count_, t.bound_count);
     Up(d_bounds32_, t.bounds32); Up(d_bounds64_, t.bounds64);
+    Up(d_ro_col_first_, t.ro_col_first); Up(d_ro_real_, t.ro_feat_real); Up(d_ro_lo_, t.ro_feat_lo); Up(d_ro_num_bin_, t.ro_feat_num_bin);
+    Up(d_ro_mfb_, t.ro_feat_mfb); Up(d_ro_missing_, t.ro_feat_missing); Up(d_ro_bound_first_, t.ro_bound_first); Up(d_ro_bound_count_, t.ro_bound_count);
+    Up(d_feat_pos_, t.feat_pos);
     // shared-memory needs of k_value_to_bin_tile: the widest 32-column tile (padded, skewed bound layout: binning.cuh)
     max_bounds_ = 1; max_feats_ = 1;
-    for (int c0 = 0; c0 < t.num_columns; c0 += kVbCols) {
-      const int c1 = std::min(t.num_columns, c0 + kVbCols);
-      const int f0 = t.col_first[c0], f1 = t.col_first[c1];
-      max_feats_ = std::max(max_feats_, f1 - f0);
+    for (int p0 = 0; p0 < t.num_features; p0 += kVbCols) {            // tiles of the real-order pass: 32 features each
+      const int p1 = std::min(t.num_features, p0 + kVbCols);
+      max_feats_ = std::max(max_feats_, p1 - p0);
       int words = 0;
-      for (int f = f0; f < f1; ++f) {
+      for (int p = p0; p < p1; ++p) {
         int depth = 0;
-        while ((1 << depth) - 1 < t.bound_count[f]) ++depth;
+        while ((1 << depth) - 1 < t.ro_bound_count[p]) ++depth;
         words += vb_slots(depth);
       }
       max_bounds_ = std::max(max_bounds_, words);
@@ -1266,6 +1301,8 @@ class BinnerCtx {
   DevBuf<int32_t> d_col_first_, d_feat_real_, d_feat_lo_, d_feat_num_bin_, d_feat_mfb_, d_feat_missing_, d_bound_first_, d_bound_count_;
   DevBuf<float> d_bounds32_;
   DevBuf<double> d_bounds64_;
+  DevBuf<int32_t> d_ro_col_first_, d_ro_real_, d_ro_lo_, d_ro_num_bin_, d_ro_mfb_, d_ro_missing_, d_ro_bound_first_, d_ro_bound_count_, d_feat_pos_;
+  DevBuf<uint8_t> tmp_[2];
 };
 
 }  // namespace b200
@@ -1325,7 +1362,7 @@ class Predictor {
     // odd row stride (in elements): 32 lanes reading one feature of 32 rows hit 32 different banks
     const int stride = ncol | 1;
     // rows per CTA tile: 64 when two such CTAs fit an SM, else 32; 0 => rows too wide to stage
-    const int pass = std::getenv("LGBMB200_PRED_PASS") ? std::max(2, std::min(kPredPassMax, std::atoi(std::getenv("LGBMB200_PRED_PASS")))) : kPredPassMax;
+    const int pass = std::getenv("LGBMB200_PRED_PASS") ? std::max(2, std::min(kPredPassMax, std::atoi(std::getenv("LGBMB200_PRED_PASS")))) : 16;      // 16: measured 10.6 ms against 13.7 ms with 32 (2M x 256 x 100 trees: the nodes of a pass stay in L1)
     auto tile_bytes = [&](int R) { return static_cast<size_t>(pass) * R * 8 + static_cast<size_t>(R) * stride * esize; };
     const int tile_rows = tile_bytes(64) <= 110 * 1024 ? 64 : (tile_bytes(32) <= 220 * 1024 ? 32 : 0);
     cudaEvent_t e0, e1, ej;
