@@ -1187,15 +1187,15 @@ class BinnerCtx {
       }
       uint8_t* dst = out_on_device ? out + r0 * C : dout[k & 1].p;
       const size_t smem = static_cast<size_t>(max_bounds_) * esize + sizeof(VbFeat) * max_feats_ + static_cast<size_t>(kVbRows) * (kVbCols + 1) * esize +
-                          kVbRows * kVbCols;
+                          static_cast<size_t>(kVbRows) * (kVbCols / 4 + 1) * 4;
       if (smem <= 200 * 1024 && !simple_kernel_) {
         // Step 1 reads the matrix in REAL feature order (coalesced whatever the stored column order is) and writes one byte
         // per feature; step 2 (k_bundle_columns) moves the bytes to their stored columns.  Both run over row pieces whose
         // byte image fits L2, so the intermediate never reaches DRAM.  Identity layouts skip step 2.
-        const int64_t Fu = t.num_features;
+        const int64_t Fu = t.num_features, Fp = (Fu + 15) / 16 * 16;        // Fp: row pitch of the intermediate (16-byte rows)
         const bool direct = t.identity_order;
-        const int64_t piece = direct ? rows : std::max<int64_t>(kVbRows, std::min<int64_t>(rows, (static_cast<int64_t>(48) << 20) / Fu / kVbRows * kVbRows));
-        if (!direct && tmp_[k & 1].n < static_cast<size_t>(piece * Fu)) tmp_[k & 1].alloc(static_cast<size_t>(piece * Fu));
+        const int64_t piece = direct ? rows : std::max<int64_t>(kVbRows, std::min<int64_t>(rows, (static_cast<int64_t>(48) << 20) / Fp / kVbRows * kVbRows));
+        if (!direct && tmp_[k & 1].n < static_cast<size_t>(piece * Fp)) tmp_[k & 1].alloc(static_cast<size_t>(piece * Fp));
         int per_sm = 1, sms = 148;
         if (dtype == 0) {
           CUDA_CHECK(cudaFuncSetAttribute(k_value_to_bin_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1207,7 +1207,7 @@ class BinnerCtx {
         { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
         const int64_t slots = static_cast<int64_t>(std::max(1, per_sm)) * sms;
         const int64_t col_tiles = (Fu + kVbCols - 1) / kVbCols;
-        const size_t bsmem = static_cast<size_t>(kBcRows) * ((Fu + 3) / 4 * 4 + 4);
+        const size_t bsmem = static_cast<size_t>(kBcRows) * (Fp + 16);
         if (!direct) CUDA_CHECK(cudaFuncSetAttribute(k_bundle_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bsmem)));
         for (int64_t p0 = 0; p0 < rows; p0 += piece) {
           const int64_t prow = std::min(piece, rows - p0);
@@ -1217,15 +1217,15 @@ class BinnerCtx {
           const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(row_tiles, std::max<int64_t>(1, slots / col_tiles)));
           const dim3 tgrid(static_cast<unsigned>(gx), static_cast<unsigned>(col_tiles));
           uint8_t* o1 = direct ? dst + p0 * C : tmp_[k & 1].p;
-          const int64_t pitch1 = direct ? C : Fu;
+          const int64_t pitch1 = direct ? C : Fp;
           const unsigned char* s1 = src + static_cast<size_t>(p0) * ncol * esize;
           if (dtype == 0) k_value_to_bin_tile<float><<<tgrid, kVbThreads, smem, st>>>(reinterpret_cast<const float*>(s1), ncol, static_cast<int32_t>(prow), ro, o1, pitch1, max_bounds_, max_feats_);
           else k_value_to_bin_tile<double><<<tgrid, kVbThreads, smem, st>>>(reinterpret_cast<const double*>(s1), ncol, static_cast<int32_t>(prow), ro, o1, pitch1, max_bounds_, max_feats_);
           ++launches_;
           if (!direct) {
             const unsigned g2 = static_cast<unsigned>(std::min<int64_t>((prow + kBcRows - 1) / kBcRows, static_cast<int64_t>(sms) * 8));
-            k_bundle_columns<<<g2, 256, bsmem, st>>>(tmp_[k & 1].p, Fu, static_cast<int32_t>(prow), static_cast<int32_t>(Fu), d_col_first_.p, d_feat_pos_.p,
-                                                    static_cast<int32_t>(C), dst + p0 * C, C);
+            k_bundle_columns<<<g2, 256, bsmem, st>>>(tmp_[k & 1].p, Fp, static_cast<int32_t>(prow), static_cast<int32_t>(Fu), d_col_first_.p, d_feat_pos_.p,
+                                                    d_col_pos_.p, static_cast<int32_t>(C), dst + p0 * C, C);
             ++launches_;
           }
         }
@@ -1272,7 +1272,7 @@ class BinnerCtx {
     Up(d_bounds32_, t.bounds32); Up(d_bounds64_, t.bounds64);
     Up(d_ro_col_first_, t.ro_col_first); Up(d_ro_real_, t.ro_feat_real); Up(d_ro_lo_, t.ro_feat_lo); Up(d_ro_num_bin_, t.ro_feat_num_bin);
     Up(d_ro_mfb_, t.ro_feat_mfb); Up(d_ro_missing_, t.ro_feat_missing); Up(d_ro_bound_first_, t.ro_bound_first); Up(d_ro_bound_count_, t.ro_bound_count);
-    Up(d_feat_pos_, t.feat_pos);
+    Up(d_feat_pos_, t.feat_pos); Up(d_col_pos_, t.col_pos);
     // shared-memory needs of k_value_to_bin_tile: the widest 32-column tile (padded, skewed bound layout: binning.cuh)
     max_bounds_ = 1; max_feats_ = 1;
     for (int p0 = 0; p0 < t.num_features; p0 += kVbCols) {            // tiles of the real-order pass: 32 features each
@@ -1301,7 +1301,7 @@ class BinnerCtx {
   DevBuf<int32_t> d_col_first_, d_feat_real_, d_feat_lo_, d_feat_num_bin_, d_feat_mfb_, d_feat_missing_, d_bound_first_, d_bound_count_;
   DevBuf<float> d_bounds32_;
   DevBuf<double> d_bounds64_;
-  DevBuf<int32_t> d_ro_col_first_, d_ro_real_, d_ro_lo_, d_ro_num_bin_, d_ro_mfb_, d_ro_missing_, d_ro_bound_first_, d_ro_bound_count_, d_feat_pos_;
+  DevBuf<int32_t> d_ro_col_first_, d_ro_real_, d_ro_lo_, d_ro_num_bin_, d_ro_mfb_, d_ro_missing_, d_ro_bound_first_, d_ro_bound_count_, d_feat_pos_, d_col_pos_;
   DevBuf<uint8_t> tmp_[2];
 };
 
