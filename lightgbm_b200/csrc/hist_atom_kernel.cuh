@@ -342,14 +342,15 @@ __global__ void __launch_bounds__(kAThreads, 1) k_hist_a(const HistAArgs a, cons
 }
 
 // Sum the scratch blocks of every column-group set into the leaf's pool slot (plain stores: the slot needs no memset).
-// One CTA of 8 warps per 32-column row of cells: CH -> (set, column group gs, bin pair m), general -> (set, bin); lane =
-// column; the blocks of the set are dealt to the 8 warps (4 loads groups in flight each), partial sums meet in shared
-// memory.  (The first version gave every thread ALL blocks of its set: a chain of up to 74 dependent L2 round trips on
+// A 32-column row of cells — CH -> (set, column group gs, bin pair m), general -> (set, bin); lane = column — is summed by
+// `wpr` warps that deal the set's blocks among themselves (4 load groups in flight each) and meet in shared memory.  (The first version gave every thread ALL blocks of its set: a chain of up to 74 dependent L2 round trips on
 // 64 CTAs when a GPU holds only two sets — 10M x 128, the per-GPU shard of C3 at 8 GPUs — which cost more than the
 // accumulation itself.)
 constexpr int kReduceWarps = 8;
+// `wpr` (1, 2, 4 or 8, chosen by the host so that the grid has a few hundred CTAs) warps share one 32-column row of
+// cells; a CTA of 8 warps therefore covers 8 / wpr rows.
 template <bool CH>
-__global__ void __launch_bounds__(kReduceWarps * 32) k_hist_reduce(const HistAArgs a) {
+__global__ void __launch_bounds__(kReduceWarps * 32) k_hist_reduce(const HistAArgs a, const int wpr) {
   using S = AShape<CH>;
   constexpr int G = S::G;
   pdl_enter();
@@ -361,12 +362,14 @@ __global__ void __launch_bounds__(kReduceWarps * 32) k_hist_reduce(const HistAAr
     slot = a.leaves[c->smaller].slot;        // a rank holding no row of the leaf (row-shard) claims no block: zeros are written
   }
   const int sets = a.num_colgroups / G, epoch = a_epoch(a);
-  constexpr int kRowsPerSet = CH ? G * 128 : kBinsPerColumn;              // CTAs per set
-  const int set = blockIdx.x / kRowsPerSet, r = blockIdx.x % kRowsPerSet;
-  if (set >= sets) return;
+  constexpr int kRowsPerSet = CH ? G * 128 : kBinsPerColumn;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nblk = min(a.blk_count[epoch * sets + set], a.blk_cap);
-  const uint32_t* base = reinterpret_cast<const uint32_t*>(a.scratch + static_cast<int64_t>(set) * a.blk_cap * S::kTables);
+  const int sub = warp % wpr;                                               // this warp's share of the blocks
+  const int grow = blockIdx.x * (kReduceWarps / wpr) + warp / wpr;          // global row of cells
+  const int set = grow / kRowsPerSet, r = grow % kRowsPerSet;
+  const bool live = set < sets;
+  const int nblk = live ? min(a.blk_count[epoch * sets + set], a.blk_cap) : 0;
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(a.scratch + static_cast<int64_t>(live ? set : 0) * a.blk_cap * S::kTables);
   constexpr int kBlkWords = S::kTables / 4, kTabWords = kATable / 4;
   unsigned long long* dst_slot = a.pool + static_cast<int64_t>(slot) * a.slot_stride;
   __shared__ long long s_part[kReduceWarps][4][32];
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(kReduceWarps * 32) k_hist_reduce(const HistAAr
     const int gs = r / 128, m = r % 128;
     const uint32_t* p0 = base + gs * (S::kCgBytes / 4) + (2 * m) * 32 + lane;
 #pragma unroll 4
-    for (int b = warp; b < nblk; b += kReduceWarps) {
+    for (int b = sub; b < nblk; b += wpr) {
       const uint32_t* p = p0 + static_cast<int64_t>(b) * kBlkWords;
       const int h0 = static_cast<int>(__ldcg(p)), h1 = static_cast<int>(__ldcg(p + 32));
       const uint32_t l0 = __ldcg(p + kTabWords), l1 = __ldcg(p + kTabWords + 32);
@@ -386,17 +389,19 @@ __global__ void __launch_bounds__(kReduceWarps * 32) k_hist_reduce(const HistAAr
   } else {
     const uint32_t* p0 = base + r * 32 + lane;
 #pragma unroll 4
-    for (int b = warp; b < nblk; b += kReduceWarps) {
+    for (int b = sub; b < nblk; b += wpr) {
       const uint32_t* p = p0 + static_cast<int64_t>(b) * kBlkWords;
       v0 += static_cast<long long>(static_cast<int>(__ldcg(p))) * 65536 + __ldcg(p + kTabWords);
       v1 += static_cast<long long>(static_cast<int>(__ldcg(p + 2 * kTabWords))) * 65536 + __ldcg(p + 3 * kTabWords);
     }
   }
-  s_part[warp][0][lane] = v0; s_part[warp][1][lane] = v1; s_part[warp][2][lane] = v2; s_part[warp][3][lane] = v3;
-  __syncthreads();
-  if (warp != 0) return;
-#pragma unroll
-  for (int w = 1; w < kReduceWarps; ++w) { v0 += s_part[w][0][lane]; v1 += s_part[w][1][lane]; v2 += s_part[w][2][lane]; v3 += s_part[w][3][lane]; }
+  if (wpr > 1) {
+    s_part[warp][0][lane] = v0; s_part[warp][1][lane] = v1; s_part[warp][2][lane] = v2; s_part[warp][3][lane] = v3;
+    __syncthreads();
+    if (sub != 0) return;
+    for (int w = 1; w < wpr; ++w) { v0 += s_part[warp + w][0][lane]; v1 += s_part[warp + w][1][lane]; v2 += s_part[warp + w][2][lane]; v3 += s_part[warp + w][3][lane]; }
+  }
+  if (!live) return;
   if (CH) {
     const int gs = r / 128, m = r % 128;
     const long long hq = a.ctl->h_const_q;

@@ -801,12 +801,23 @@ class Learner {
   // the packed-cell kernel of quantized training still adds into a zeroed slot with RED.ADD.64
   void LaunchHist(const HistAArgs& ha, const HistQArgs& qa, bool chain = false) {
     if (PackedQuantHist()) { LaunchChain(chain, k_hist_q, dim3(num_sms_ * 2), dim3(kHistThreads), kQSmemBytes, qa, tmap_); return; }
+    // k_hist_reduce: warps per 32-column row of cells such that the grid has about two CTAs per SM — one warp per row when
+    // the shard is wide (C3 on one GPU: 4096 rows), all eight when a GPU holds two sets (its share of C3 at 8 GPUs)
+    auto reduce_grid = [&](int rows_total, int* wpr) {
+      int w = 1;
+      while (w < kReduceWarps && rows_total * w / kReduceWarps < 2 * num_sms_) w *= 2;
+      *wpr = w;
+      return dim3(static_cast<unsigned>((rows_total * w + kReduceWarps - 1) / kReduceWarps));
+    };
+    int wpr = 1;
     if (ConstHessHist()) {
       LaunchChain(chain, k_hist_a<true>, dim3(num_sms_), dim3(kAThreads), AShape<true>::kSmem, ha, tmap2_);
-      LaunchChain(true, k_hist_reduce<true>, dim3(hist_sets_ * AShape<true>::G * 128), dim3(kReduceWarps * 32), 0, ha);
+      const dim3 g = reduce_grid(hist_sets_ * AShape<true>::G * 128, &wpr);
+      LaunchChain(true, k_hist_reduce<true>, g, dim3(kReduceWarps * 32), 0, ha, wpr);
     } else {
       LaunchChain(chain, k_hist_a<false>, dim3(num_sms_), dim3(kAThreads), AShape<false>::kSmem, ha, tmap_);
-      LaunchChain(true, k_hist_reduce<false>, dim3(hist_sets_ * kBinsPerColumn), dim3(kReduceWarps * 32), 0, ha);
+      const dim3 g = reduce_grid(hist_sets_ * kBinsPerColumn, &wpr);
+      LaunchChain(true, k_hist_reduce<false>, g, dim3(kReduceWarps * 32), 0, ha, wpr);
     }
     ++launches_;
   }
