@@ -530,12 +530,27 @@ def main():
     rows, cols, leaves = wl["rows"], wl["cols"], wl["leaves"]
     dist = None
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: NCCL's own log lines (version banner, NCCL_DEBUG=INFO) go to stderr
+        # rank 0 prints ONE JSON line on stdout.  NCCL writes its version banner (NCCL_DEBUG=VERSION, which this image sets)
+        # and its INFO lines to stdout when the communicator is created, and honours NCCL_DEBUG_FILE only above the VERSION
+        # level: raise VERSION to WARN, point the log at stderr, and create the communicator (init + first collective)
+        # with file descriptor 1 parked on stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", rank=rank, world_size=world)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", rank=rank, world_size=world)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     host_threads = max(4, (os.cpu_count() or 8) // max(world, 1))
     ncols = wl_columns(wl)
     lc = LABEL_COLS[wl["kind"]]

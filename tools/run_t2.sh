@@ -7,7 +7,7 @@ if [ "$N" = "2" ]; then
 fi
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02t_bench_c3_${N}gpu.json 2> gpurun_out/r02t_bench_c3_${N}gpu.err
 tail -2 gpurun_out/r02t_bench_c3_${N}gpu.err | cut -c1-300; cut -c1-2600 gpurun_out/r02t_bench_c3_${N}gpu.json
-if [ "$N" != "4" ]; then
+if [ "$N" = "2" ]; then
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus $N --workload C5 --steps 20 --warmup 10 --no-cpu-baseline > gpurun_out/r02t_bench_c5_${N}gpu.json 2> gpurun_out/r02t_bench_c5_${N}gpu.err
 tail -2 gpurun_out/r02t_bench_c5_${N}gpu.err | cut -c1-300; cut -c1-1500 gpurun_out/r02t_bench_c5_${N}gpu.json
 fi
