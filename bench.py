@@ -639,9 +639,11 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_hist_a (+ k_hist_reduce)" if not args.quantized else "k_hist_q", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_kind": peak_kind,
                 "traffic": tr["dram_bytes_per_launch"] if tr else None,
-                # the capture covers the same trees (warm-up 3, 1 step, then these 3 profiled ones) of the same seeded run;
-                # under ncu every launch starts with a flushed L2, so k_hist_reduce's re-read of the dumped tables counts too
-                "traffic_over_alg": (tr["dram_bytes_per_launch"] / (alg_bytes / max(hist_launches, 1))) if tr else None,
+                # traffic: DRAM bytes per launch from the committed ncu capture (trees 4-5 of the same seeded run); the ratio is
+                # taken against the algorithmic bytes of THOSE trees (later trees build fewer rows per launch); under ncu every
+                # launch starts with a flushed L2, so k_hist_reduce's re-read of the dumped tables counts too
+                "traffic_over_alg": (tr["dram_bytes_per_launch"] / tr.get("alg_bytes_per_launch_same_run", alg_bytes / max(hist_launches, 1))) if tr else None,
+                "traffic_note": tr.get("note") if tr else None,
                 "hist_share_of_step": (hist_ms / prof_steps) / ms_per_step,
                 "alg_bytes_per_launch": alg_bytes / max(hist_launches, 1),
                 "avg_launch_ms": hist_ms / max(hist_launches, 1), "rows_built_factor_k": hist_rows / root_rows,

@@ -1350,6 +1350,7 @@ class Predictor {
     }
     if (device_ >= 0) CUDA_CHECK(cudaSetDevice(device_));
     Up(d_na_, na); Up(d_nb_, nb); Up(d_leaves_, leaves); Up(d_nf_, nf); Up(d_lf_, lf); Up(d_nl_, nl);
+    h_nf_ = nf; h_nl_ = nl; total_nodes_ = static_cast<int>(na.size());
     CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[0], cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[1], cudaStreamNonBlocking));
   }
@@ -1391,17 +1392,28 @@ class Predictor {
         src = dx[k & 1].p;
       }
       double* dst = out_on_device ? out + r0 : dout[k & 1].p;
-      if (tile_rows >= 32) {
-        const size_t smem = tile_bytes(tile_rows);
-        const int per_sm = std::max<int>(1, std::min<int>(8, static_cast<int>((220 * 1024) / smem)));
-        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + tile_rows - 1) / tile_rows, 148 * per_sm));
-        if (dtype == 0) {
-          CUDA_CHECK(cudaFuncSetAttribute(k_predict<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-          k_predict<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride, pass);
-        } else {
-          CUDA_CHECK(cudaFuncSetAttribute(k_predict<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-          k_predict<double><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride, pass);
+      // narrow rows and no tree larger than a pass: pass-major with the nodes in shared memory (predict.cuh)
+      bool pass_major = static_cast<size_t>(ncol) * esize <= 2048 && num_trees_ > 0 && !std::getenv("LGBMB200_PRED_TILE_MAJOR");
+      for (int t = 0; t < num_trees_ && pass_major; ++t) if (h_nl_[t] - 1 > kPredPassNodes) pass_major = false;
+      if (pass_major) {
+        const int R = 64;
+        const size_t fixed = static_cast<size_t>(kPredPassNodes) * (sizeof(PNodeA) + sizeof(PNodeB)) + static_cast<size_t>(kPredPassMax) * R * 8;
+        const size_t tile_b = static_cast<size_t>(R) * stride * esize;
+        const int nbuf = fixed + 2 * tile_b <= 220 * 1024 ? 2 : 1;
+        const size_t smem = fixed + nbuf * tile_b;
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + R - 1) / R, 148));
+        if (dtype == 0) CUDA_CHECK(cudaFuncSetAttribute(k_predict_pass<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        else CUDA_CHECK(cudaFuncSetAttribute(k_predict_pass<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        for (int t0 = 0; t0 < num_trees_;) {
+          int cnt = 0, nodes = 0;
+          while (t0 + cnt < num_trees_ && cnt < kPredPassMax && nodes + (h_nl_[t0 + cnt] - 1) <= kPredPassNodes) { nodes += h_nl_[t0 + cnt] - 1; ++cnt; }
+          if (dtype == 0) k_predict_pass<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, R, stride, t0, cnt, h_nf_[t0], nodes, nbuf);
+          else k_predict_pass<double><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, rows, ncol, pt, dst, R, stride, t0, cnt, h_nf_[t0], nodes, nbuf);
+          ++launches_;
+          t0 += cnt;
         }
+      } else if (tile_rows >= 32) {
+        const size_t smem = tile_bytes(tile_rows);
       } else {
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + kPredThreads - 1) / kPredThreads, 148 * 8));
         if (dtype == 0) k_predict_wide<float><<<grid, kPredThreads, 0, st>>>(reinterpret_cast<const float*>(src), ncol, rows, pt, dst);
@@ -1432,6 +1444,7 @@ class Predictor {
   PinnedStager stager_;
   int64_t launches_ = 0;
   cudaStream_t streams_[2] = {nullptr, nullptr};
+  std::vector<int32_t> h_nf_, h_nl_; int total_nodes_ = 0;
   DevBuf<PNodeA> d_na_; DevBuf<PNodeB> d_nb_; DevBuf<double> d_leaves_; DevBuf<int32_t> d_nf_, d_lf_, d_nl_;
 };
 
