@@ -1331,7 +1331,7 @@ class Predictor {
             int32_t max_feature_idx)
       : device_(device), num_trees_(num_trees), max_feature_idx_(max_feature_idx) {
     REQUIRE(num_trees >= 0 && tree_num_leaves, "bad model");
-    std::vector<PNodeA> na; std::vector<PNodeB> nb; std::vector<double> leaves; std::vector<int32_t> nf, lf, nl;
+    std::vector<PNodeA> na; std::vector<PNodeB> nb; std::vector<PNodeF> nfl; std::vector<double> leaves; std::vector<int32_t> nf, lf, nl;
     int64_t ni = 0, li = 0;
     for (int t = 0; t < num_trees; ++t) {
       const int L = tree_num_leaves[t];
@@ -1345,11 +1345,17 @@ class Predictor {
         REQUIRE(a.feature >= 0 && a.feature <= max_feature_idx, "split feature out of range");
         REQUIRE(b.left < L - 1 && b.right < L - 1 && ~b.left < L && ~b.right < L, "child index out of range");
         na.push_back(a); nb.push_back(b);
+        REQUIRE(a.feature < (1 << 24), "feature index too large");
+        PNodeF fn;
+        fn.thr = static_cast<float>(a.threshold);
+        if (static_cast<double>(fn.thr) > a.threshold) fn.thr = std::nextafterf(fn.thr, -INFINITY);     // the largest float <= threshold
+        fn.fd = static_cast<uint32_t>(a.feature) | (static_cast<uint32_t>(a.decision) << 24); fn.left = b.left; fn.right = b.right;
+        nfl.push_back(fn);
       }
       for (int i = 0; i < L; ++i, ++li) leaves.push_back(leaf_value[li]);
     }
     if (device_ >= 0) CUDA_CHECK(cudaSetDevice(device_));
-    Up(d_na_, na); Up(d_nb_, nb); Up(d_leaves_, leaves); Up(d_nf_, nf); Up(d_lf_, lf); Up(d_nl_, nl);
+    Up(d_na_, na); Up(d_nb_, nb); Up(d_nfl_, nfl); Up(d_leaves_, leaves); Up(d_nf_, nf); Up(d_lf_, lf); Up(d_nl_, nl);
     h_nf_ = nf; h_nl_ = nl; total_nodes_ = static_cast<int>(na.size());
     CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[0], cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[1], cudaStreamNonBlocking));
@@ -1370,7 +1376,7 @@ class Predictor {
     DevBuf<unsigned char> dx[2]; DevBuf<double> dout[2];
     if (!data_on_device) { for (auto& b : dx) b.alloc(static_cast<size_t>(chunk) * ncol * esize); stager_.Reserve(static_cast<size_t>(chunk) * ncol * esize); }
     if (!out_on_device) for (auto& b : dout) b.alloc(static_cast<size_t>(chunk));
-    const PredTable pt{d_na_.p, d_nb_.p, d_leaves_.p, d_nf_.p, d_lf_.p, d_nl_.p, num_trees_};
+    const PredTable pt{d_na_.p, d_nb_.p, d_nfl_.p, d_leaves_.p, d_nf_.p, d_lf_.p, d_nl_.p, num_trees_};
     // odd row stride (in elements): 32 lanes reading one feature of 32 rows hit 32 different banks
     const int stride = ncol | 1;
     // rows per CTA tile: 64 when two such CTAs fit an SM, else 32; 0 => rows too wide to stage
@@ -1392,27 +1398,7 @@ class Predictor {
         src = dx[k & 1].p;
       }
       double* dst = out_on_device ? out + r0 : dout[k & 1].p;
-      // narrow rows and no tree larger than a pass: pass-major with the nodes in shared memory (predict.cuh)
-      bool pass_major = static_cast<size_t>(ncol) * esize <= 2048 && num_trees_ > 0 && !std::getenv("LGBMB200_PRED_TILE_MAJOR");
-      for (int t = 0; t < num_trees_ && pass_major; ++t) if (h_nl_[t] - 1 > kPredPassNodes) pass_major = false;
-      if (pass_major) {
-        const int R = 64;
-        const size_t fixed = static_cast<size_t>(kPredPassNodes) * (sizeof(PNodeA) + sizeof(PNodeB)) + static_cast<size_t>(kPredPassMax) * R * 8;
-        const size_t tile_b = static_cast<size_t>(R) * stride * esize;
-        const int nbuf = fixed + 2 * tile_b <= 220 * 1024 ? 2 : 1;
-        const size_t smem = fixed + nbuf * tile_b;
-        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + R - 1) / R, 148));
-        if (dtype == 0) CUDA_CHECK(cudaFuncSetAttribute(k_predict_pass<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        else CUDA_CHECK(cudaFuncSetAttribute(k_predict_pass<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        for (int t0 = 0; t0 < num_trees_;) {
-          int cnt = 0, nodes = 0;
-          while (t0 + cnt < num_trees_ && cnt < kPredPassMax && nodes + (h_nl_[t0 + cnt] - 1) <= kPredPassNodes) { nodes += h_nl_[t0 + cnt] - 1; ++cnt; }
-          if (dtype == 0) k_predict_pass<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, R, stride, t0, cnt, h_nf_[t0], nodes, nbuf);
-          else k_predict_pass<double><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, rows, ncol, pt, dst, R, stride, t0, cnt, h_nf_[t0], nodes, nbuf);
-          ++launches_;
-          t0 += cnt;
-        }
-      } else if (tile_rows >= 32) {
+      if (tile_rows >= 32) {
         const size_t smem = tile_bytes(tile_rows);
       } else {
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + kPredThreads - 1) / kPredThreads, 148 * 8));
@@ -1445,7 +1431,7 @@ class Predictor {
   int64_t launches_ = 0;
   cudaStream_t streams_[2] = {nullptr, nullptr};
   std::vector<int32_t> h_nf_, h_nl_; int total_nodes_ = 0;
-  DevBuf<PNodeA> d_na_; DevBuf<PNodeB> d_nb_; DevBuf<double> d_leaves_; DevBuf<int32_t> d_nf_, d_lf_, d_nl_;
+  DevBuf<PNodeA> d_na_; DevBuf<PNodeB> d_nb_; DevBuf<PNodeF> d_nfl_; DevBuf<double> d_leaves_; DevBuf<int32_t> d_nf_, d_lf_, d_nl_;
 };
 
 }  // namespace b200

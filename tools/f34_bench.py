@@ -21,8 +21,9 @@ X = np.empty((n, f), np.float32)
 for lo in range(0, n, 1 << 18):
     X[lo:lo + (1 << 18)] = r.standard_normal((min(1 << 18, n - lo), f), dtype=np.float32)
 X[r.random(n) < 0.01, 3] = np.nan
-w = r.normal(size=32)
-y = (X[:, 4:36] @ w + 0.5 * r.standard_normal(n)).astype(np.float32)
+nw = min(32, f - 4)
+w = r.normal(size=nw)
+y = (np.nan_to_num(X[:, 4:4 + nw]) @ w + 0.5 * r.standard_normal(n)).astype(np.float32)
 res = {"rows": n, "cols": f, "host_threads": threads, "hbm_peak_gbs": peak}
 
 # ---- f-3 (a tiny first pass creates the CUDA context and the staging buffers outside the timed region; the reference has no such one-off)
