@@ -1356,7 +1356,7 @@ class Predictor {
     }
     if (device_ >= 0) CUDA_CHECK(cudaSetDevice(device_));
     Up(d_na_, na); Up(d_nb_, nb); Up(d_nfl_, nfl); Up(d_leaves_, leaves); Up(d_nf_, nf); Up(d_lf_, lf); Up(d_nl_, nl);
-    h_nf_ = nf; h_nl_ = nl; total_nodes_ = static_cast<int>(na.size());
+
     CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[0], cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[1], cudaStreamNonBlocking));
   }
@@ -1400,6 +1400,15 @@ class Predictor {
       double* dst = out_on_device ? out + r0 : dout[k & 1].p;
       if (tile_rows >= 32) {
         const size_t smem = tile_bytes(tile_rows);
+        const int per_sm = std::max<int>(1, std::min<int>(8, static_cast<int>((220 * 1024) / smem)));
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + tile_rows - 1) / tile_rows, 148 * per_sm));
+        if (dtype == 0) {
+          CUDA_CHECK(cudaFuncSetAttribute(k_predict<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+          k_predict<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride, pass);
+        } else {
+          CUDA_CHECK(cudaFuncSetAttribute(k_predict<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+          k_predict<double><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride, pass);
+        }
       } else {
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + kPredThreads - 1) / kPredThreads, 148 * 8));
         if (dtype == 0) k_predict_wide<float><<<grid, kPredThreads, 0, st>>>(reinterpret_cast<const float*>(src), ncol, rows, pt, dst);
@@ -1430,7 +1439,6 @@ class Predictor {
   PinnedStager stager_;
   int64_t launches_ = 0;
   cudaStream_t streams_[2] = {nullptr, nullptr};
-  std::vector<int32_t> h_nf_, h_nl_; int total_nodes_ = 0;
   DevBuf<PNodeA> d_na_; DevBuf<PNodeB> d_nb_; DevBuf<PNodeF> d_nfl_; DevBuf<double> d_leaves_; DevBuf<int32_t> d_nf_, d_lf_, d_nl_;
 };
 
