@@ -147,3 +147,35 @@ def test_full_size_properties_1m_x_256(built_lib):
     half, _ = b.transform(np.ascontiguousarray(X[: n // 2]), to_device=False)
     np.testing.assert_array_equal(half, out[: n // 2])
     print(f"1M x 256 float32 -> bins: {ms:.1f} ms device time incl. H2D/D2H ({n * f * 5 / ms / 1e6:.1f} GB/s)")
+
+
+# ---------------------------------------------------------------------------------------------------- C4-shaped EFB at 200 K x 256
+def _efb4():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    d = np.load(os.path.join(ROOT, "tests", "golden", "efb4_200k_x256.npz"))
+    _, raw, _, _, _ = make_golden.efb4_inputs()
+    X = np.ascontiguousarray(raw, dtype=np.float32)
+    params = dict(max_bin=255, min_data_in_bin=1, feature_pre_filter="false", enable_bundle="true")
+    return d, X, params
+
+
+def test_fit_reproduces_the_reference_bundles_of_the_c4_fixture(built_lib):
+    """tests/golden/efb4_200k_x256.npz: the layout the UNMODIFIED reference built from the bench generator's C4-shaped data (256
+    sparse features, exclusive in blocks of 4 -> 64 bundled columns, through LGBM_DatasetCreateFromSampledColumn + PushRows).
+    The binner must arrive at the same 64 columns: same members, same order inside a column, same offsets."""
+    import lightgbm_b200 as lgb
+    d, X, params = _efb4()
+    m = lgb.Binner(params).fit(X).layout_meta()
+    assert (m["num_columns"], m["num_features"]) == (64, 256) == (int(d["dims"][1]), int(d["dims"][2]))
+    for mine, ref in META:
+        np.testing.assert_array_equal(m[mine], d[ref], err_msg=mine)
+
+
+@pytest.mark.gpu
+def test_transform_reproduces_the_reference_bytes_of_the_c4_fixture(built_lib):
+    import lightgbm_b200 as lgb
+    d, X, params = _efb4()
+    bins = lgb.Binner(params).fit(X).transform(X, to_device=True)[0].download()
+    cs = np.array([int(bins.astype(np.uint64).sum()), int((bins.astype(np.uint64) * (np.arange(bins.shape[1], dtype=np.uint64) + 1)).sum())], np.uint64)
+    np.testing.assert_array_equal(cs, d["bins_checksum"])
