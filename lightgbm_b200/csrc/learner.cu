@@ -1382,7 +1382,7 @@ class Predictor {
     // rows per CTA tile: 64 when two such CTAs fit an SM, else 32; 0 => rows too wide to stage
     const int pass = std::getenv("LGBMB200_PRED_PASS") ? std::max(2, std::min(kPredPassMax, std::atoi(std::getenv("LGBMB200_PRED_PASS")))) : 16;      // 16: measured 10.6 ms against 13.7 ms with 32 (2M x 256 x 100 trees: the nodes of a pass stay in L1)
     auto tile_bytes = [&](int R) { return static_cast<size_t>(pass) * R * 8 + static_cast<size_t>(R) * stride * esize; };
-    const int tile_rows = tile_bytes(64) <= 110 * 1024 ? 64 : (tile_bytes(32) <= 220 * 1024 ? 32 : 0);
+    const int tile_rows = tile_bytes(64) <= 112 * 1024 ? 64 : (tile_bytes(32) <= 224 * 1024 ? 32 : 0);
     cudaEvent_t e0, e1, ej;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreateWithFlags(&ej, cudaEventDisableTiming));
     CUDA_CHECK(cudaDeviceSynchronize());
@@ -1400,13 +1400,19 @@ class Predictor {
       double* dst = out_on_device ? out + r0 : dout[k & 1].p;
       if (tile_rows >= 32) {
         const size_t smem = tile_bytes(tile_rows);
-        const int per_sm = std::max<int>(1, std::min<int>(8, static_cast<int>((220 * 1024) / smem)));
-        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + tile_rows - 1) / tile_rows, 148 * per_sm));
+        int per_sm = 1;
         if (dtype == 0) {
           CUDA_CHECK(cudaFuncSetAttribute(k_predict<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-          k_predict<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride, pass);
+          CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_predict<float>, kPredThreads, smem));
         } else {
           CUDA_CHECK(cudaFuncSetAttribute(k_predict<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+          CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_predict<double>, kPredThreads, smem));
+        }
+        per_sm = std::max(1, per_sm);
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + tile_rows - 1) / tile_rows, 148 * per_sm));
+        if (dtype == 0) {
+          k_predict<float><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride, pass);
+        } else {
           k_predict<double><<<grid, kPredThreads, smem, st>>>(reinterpret_cast<const double*>(src), ncol, rows, ncol, pt, dst, tile_rows, stride, pass);
         }
       } else {
