@@ -760,17 +760,30 @@ __device__ __noinline__ void select_body(const SelectArgs& a) {
       if (!wait_seq(&mine->mail_seq[par][tid], seq)) c->error = 1;
     }
     __syncthreads();
-    if (tid < 2) {
-      const int which = tid;
+    // warps 0 / 1 reduce the smaller / larger leaf: lane r reads only the KEY of rank r's candidate (gain, feature, real
+    // index), the warp agrees on the winning rank by shuffles (the comparator of the sequential scan; among equals the
+    // lower rank), and one lane copies the winner's full record.  (Reading all W records one after the other in one thread
+    // was a chain of W dependent L2 round trips: several microseconds per split at 8 GPUs.)
+    if (warp < 2) {
+      const int which = warp;
       const int leaf = which == 0 ? smaller : larger;
       if (leaf >= 0) {
         CommBlock* mine = a.peers.block[me];
-        Cand best = load_cand_sys(&mine->mail[par][0][which]);
-        for (int r = 1; r < W; ++r) {
-          const Cand o = load_cand_sys(&mine->mail[par][r][which]);
-          if (cand_better(o.gain, o.feature < 0 ? 0x7fffffff : o.real, best.gain, best.feature < 0 ? 0x7fffffff : best.real)) best = o;
+        double g = -INFINITY; int real = 0x7fffffff, win = 0x7fffffff;
+        if (lane < W) {
+          const Cand* p = &mine->mail[par][lane][which];
+          g = __ldcv(&p->gain);
+          const int f = __ldcv(&p->feature);
+          real = f < 0 ? 0x7fffffff : __ldcv(&p->real);
+          win = lane;
         }
-        a.leaves[leaf].best = best;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+          const double og = __shfl_xor_sync(0xffffffffu, g, d);
+          const int orl = __shfl_xor_sync(0xffffffffu, real, d), ow = __shfl_xor_sync(0xffffffffu, win, d);
+          if (ow != 0x7fffffff && (win == 0x7fffffff || cand_better(og, orl, g, real) || (!cand_better(g, real, og, orl) && ow < win))) { g = og; real = orl; win = ow; }
+        }
+        if (lane == 0) a.leaves[leaf].best = load_cand_sys(&mine->mail[par][win][which]);
       }
     }
     __syncthreads();
