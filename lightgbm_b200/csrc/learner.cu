@@ -1355,21 +1355,7 @@ class Predictor {
       for (int i = 0; i < L; ++i, ++li) leaves.push_back(leaf_value[li]);
     }
     if (device_ >= 0) CUDA_CHECK(cudaSetDevice(device_));
-    Up(d_na_, na); Up(d_nb_, nb); Up(d_nfl_, nfl); Up(d_leaves_, leaves);
-    // passes of k_predict_f: <= kPredSmemPass trees and <= kPredSmemNodes nodes each (a tree larger than that: global-node kernel)
-    total_nodes_ = static_cast<int32_t>(na.size());
-    smem_nodes_ok_ = num_trees > 0;
-    std::vector<int32_t> ps;
-    for (int t = 0; t < num_trees && smem_nodes_ok_;) {
-      ps.push_back(t);
-      int cnt = 0, nodes = 0;
-      while (t + cnt < num_trees && cnt < kPredSmemPass && nodes + nl[t + cnt] - 1 <= kPredSmemNodes) { nodes += nl[t + cnt] - 1; ++cnt; }
-      if (cnt == 0) smem_nodes_ok_ = false;
-      t += cnt;
-    }
-    ps.push_back(num_trees);
-    num_passes_ = static_cast<int32_t>(ps.size()) - 1;
-    Up(d_pass_start_, ps); Up(d_nf_, nf); Up(d_lf_, lf); Up(d_nl_, nl);
+    Up(d_na_, na); Up(d_nb_, nb); Up(d_nfl_, nfl); Up(d_leaves_, leaves); Up(d_nf_, nf); Up(d_lf_, lf); Up(d_nl_, nl);
 
     CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[0], cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[1], cudaStreamNonBlocking));
@@ -1412,15 +1398,7 @@ class Predictor {
         src = dx[k & 1].p;
       }
       double* dst = out_on_device ? out + r0 : dout[k & 1].p;
-      const size_t fsmem = static_cast<size_t>(kPredSmemNodes) * sizeof(PNodeF) + static_cast<size_t>(kPredSmemPass) * 64 * 8 + static_cast<size_t>(64) * stride * 4;
-      if (dtype == 0 && smem_nodes_ok_ && fsmem <= 112 * 1024 && !std::getenv("LGBMB200_PRED_GLOBAL_NODES")) {
-        // float32 input, two 64-row CTAs per SM with the current pass's nodes in shared memory
-        int per_sm = 1;
-        CUDA_CHECK(cudaFuncSetAttribute(k_predict_f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsmem)));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_predict_f, kPredThreads, fsmem));
-        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((rows + 63) / 64, 148 * static_cast<int64_t>(std::max(1, per_sm))));
-        k_predict_f<<<grid, kPredThreads, fsmem, st>>>(reinterpret_cast<const float*>(src), ncol, rows, ncol, pt, d_pass_start_.p, num_passes_, total_nodes_, dst, 64, stride);
-      } else if (tile_rows >= 32) {
+      if (tile_rows >= 32) {
         const size_t smem = tile_bytes(tile_rows);
         int per_sm = 1;
         if (dtype == 0) {
@@ -1467,8 +1445,6 @@ class Predictor {
   PinnedStager stager_;
   int64_t launches_ = 0;
   cudaStream_t streams_[2] = {nullptr, nullptr};
-  int32_t total_nodes_ = 0, num_passes_ = 0; bool smem_nodes_ok_ = false;
-  DevBuf<int32_t> d_pass_start_;
   DevBuf<PNodeA> d_na_; DevBuf<PNodeB> d_nb_; DevBuf<PNodeF> d_nfl_; DevBuf<double> d_leaves_; DevBuf<int32_t> d_nf_, d_lf_, d_nl_;
 };
 

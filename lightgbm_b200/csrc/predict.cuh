@@ -154,75 +154,12 @@ __global__ void __launch_bounds__(kPredThreads) k_predict(const T* __restrict__ 
   }
 }
 
-// float32 input, final form: the same tile-major loop, but the nodes of the current pass (<= 16 trees, <= 2048 nodes = 32 KB of
-// PNodeF) are copied into shared memory before they are walked.  ncu of the kernel above (profiles/r02z_predict_*.txt): the
-// walk waits on the node loads (long-scoreboard 9.0 per issue, L2 hit rate 53 %: 16 warps on 48 trees do not fit L1 next
-// to the tile).  A node visit becomes two LDS.  (Copying per LAUNCH instead — the pass-major variant below — re-reads X
-// once per pass and was slower.)
-constexpr int kPredSmemNodes = 2048;
-constexpr int kPredSmemPass = 16;
-
-__device__ __forceinline__ void pred_pair_fs(const PNodeF* sn, const PredTable& m, int node0, int ta, int tb, const float* row, double* va, double* vb) {
-  const int fa = m.node_first[ta] - node0, fb = tb >= 0 ? m.node_first[tb] - node0 : 0;
-  int a = m.num_leaves[ta] > 1 ? 0 : -1;
-  int b = (tb >= 0 && m.num_leaves[tb] > 1) ? 0 : -1;
-  while (a >= 0 || b >= 0) {
-    if (a >= 0) a = pred_step_f(sn + fa, a, row);
-    if (b >= 0) b = pred_step_f(sn + fb, b, row);
-  }
-  *va = m.leaf_value[m.leaf_first[ta] + ~a];
-  if (tb >= 0) *vb = m.leaf_value[m.leaf_first[tb] + ~b];
-}
-
-__global__ void __launch_bounds__(kPredThreads) k_predict_f(const float* __restrict__ x, int64_t ld, int64_t nrow, int32_t ncol, const PredTable m,
-                                                            const int32_t* __restrict__ pass_start, int32_t num_passes, int32_t total_nodes,
-                                                            double* __restrict__ out, int32_t R, int32_t stride) {
-  extern __shared__ __align__(16) unsigned char psmem[];
-  PNodeF* s_nodes = reinterpret_cast<PNodeF*>(psmem);                           // [kPredSmemNodes]
-  double* vals = reinterpret_cast<double*>(s_nodes + kPredSmemNodes);           // [kPredSmemPass][R]
-  float* tile = reinterpret_cast<float*>(vals + kPredSmemPass * R);             // [R][stride]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int kWarps = kPredThreads / 32;
-  const int row = threadIdx.x & (R - 1), g = threadIdx.x / R, G = kPredThreads / R;
-  for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * R; r0 < nrow; r0 += static_cast<int64_t>(gridDim.x) * R) {
-    const int rows = static_cast<int>(min(static_cast<int64_t>(R), nrow - r0));
-    for (int r = warp; r < R; r += kWarps) {
-      const float* src = x + (r0 + min(r, rows - 1)) * ld;               // ragged last tile: repeat its last row
-      for (int c = lane; c < ncol; c += 32) cp_async_elem(tile + r * stride + c, src + c);
-    }
-    cp_async_commit();
-    const float* my = tile + row * stride;
-    double sum = 0.0;
-    for (int p = 0; p < num_passes; ++p) {
-      const int t0 = pass_start[p], cnt = pass_start[p + 1] - t0;
-      const int node0 = m.node_first[t0];
-      const int nn = (t0 + cnt < m.num_trees ? m.node_first[t0 + cnt] : total_nodes) - node0;
-      for (int i = threadIdx.x; i < nn; i += kPredThreads) s_nodes[i] = m.node_f[node0 + i];
-      if (p == 0) cp_async_wait<0>();
-      __syncthreads();                                                    // nodes (and, first pass, the tile) in place
-      for (int k = g; k < cnt; k += 2 * G) {
-        double va = 0.0, vb = 0.0;
-        const int kb = k + G;
-        pred_pair_fs(s_nodes, m, node0, t0 + k, kb < cnt ? t0 + kb : -1, my, &va, &vb);
-        vals[k * R + row] = va;
-        if (kb < cnt) vals[kb * R + row] = vb;
-      }
-      __syncthreads();
-      if (g == 0) {
-#pragma unroll 8
-        for (int k = 0; k < cnt; ++k) sum += vals[k * R + row];          // tree order: the reference's summation
-      }
-      // the next pass's node copy may start at once (every walk is past the barrier above); its barrier orders these
-      // reads of vals before the next writes
-    }
-    if (g == 0 && row < rows) out[r0 + row] = sum;
-    __syncthreads();                                                      // tile and vals free for the next row tile
-  }
-}
-
-// (A pass-major form — one launch per 16 trees, the pass's nodes in shared memory for the whole launch, running sums kept in
-// `out` between passes — was built and measured: 16.9 ms against 10.6 ms for the tile-major kernel on 2M x 256 x 100
-// trees: X is re-read once per pass and every (tile, pass) pays the 4-byte cp.async staging of the tile; removed.)
+// (Two variants with the nodes in SHARED memory were built, checked bit-identical and measured on 2M x 256 x 100 trees:
+// pass-major — one launch per 16 trees, running sums kept in `out` between passes — 16.9 ms (X is re-read once per pass and
+// every (tile, pass) pays the 4-byte cp.async staging); tile-major with the current pass's nodes copied per (tile, pass) —
+// 7.2 ms, the same as this kernel: ncu shows the long-scoreboard stalls gone (9.0 -> 1.7 per issue) and the issue slots
+// 34 % busy with the same 110 M warp instructions — the leaf-wise trees are 30-60 levels deep on their main branch and the
+// 32 rows of a warp diverge, so the walk is bound by instructions issued for the longest path.  Both removed.)
 // rows too wide for a shared-memory tile of 32: a thread reads its row straight from global memory (L1 / L2 hold the
 // sectors it has touched)
 template <typename T>
