@@ -159,7 +159,9 @@ __global__ void __launch_bounds__(kPredThreads) k_predict(const T* __restrict__ 
 // every (tile, pass) pays the 4-byte cp.async staging); tile-major with the current pass's nodes copied per (tile, pass) —
 // 7.2 ms, the same as this kernel: ncu shows the long-scoreboard stalls gone (9.0 -> 1.7 per issue) and the issue slots
 // 34 % busy with the same 110 M warp instructions — the leaf-wise trees are 30-60 levels deep on their main branch and the
-// 32 rows of a warp diverge, so the walk is bound by instructions issued for the longest path.  Both removed.)
+// 32 rows of a warp diverge, so the walk is bound by instructions issued for the longest path.  Both removed.  A flat per-lane
+// loop over the lane's trees of a pass (a chain moves on to its next tree the moment it reaches a leaf, so that the warp pays
+// for sums of paths instead of the longest path once per tree) needs more instructions per step than it saves: 12.8 ms.)
 // rows too wide for a shared-memory tile of 32: a thread reads its row straight from global memory (L1 / L2 hold the
 // sectors it has touched)
 template <typename T>
