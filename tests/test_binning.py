@@ -179,3 +179,51 @@ def test_transform_reproduces_the_reference_bytes_of_the_c4_fixture(built_lib):
     bins = lgb.Binner(params).fit(X).transform(X, to_device=True)[0].download()
     cs = np.array([int(bins.astype(np.uint64).sum()), int((bins.astype(np.uint64) * (np.arange(bins.shape[1], dtype=np.uint64) + 1)).sum())], np.uint64)
     np.testing.assert_array_equal(cs, d["bins_checksum"])
+
+
+@pytest.mark.gpu
+def test_random_small_shapes_against_the_live_reference(built_lib):
+    """Eight seeded random configurations (1 .. 70 columns, 40 .. 3000 rows, mixed dense / sparse / NaN / few-valued columns,
+    random Dataset parameters) through the compiled reference and through the binner + device pass: same layout, same bounds,
+    same bytes — or the same refusal when no feature survives."""
+    import lightgbm_b200 as lgb
+    from oracle import refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not built")
+    checked = 0
+    for seed in range(8):
+        r = np.random.default_rng(1000 + seed)
+        n, f = int(r.integers(40, 3000)), int(r.integers(1, 71))
+        X = r.normal(size=(n, f)).astype(np.float32 if seed % 2 == 0 else np.float64)
+        for j in range(f):
+            kind = r.integers(0, 5)
+            if kind == 0:
+                X[r.random(n) < 0.9, j] = 0.0
+            elif kind == 1:
+                X[:, j] = r.integers(-3, 4, n)
+            elif kind == 2:
+                X[r.random(n) < 0.2, j] = np.nan
+            elif kind == 3:
+                X[:, j] = np.where(r.random(n) < 0.97, 0.0, r.integers(1, 30, n))
+        params = dict(max_bin=int(r.choice([15, 63, 255])), min_data_in_bin=int(r.choice([1, 3])), min_data_in_leaf=int(r.choice([1, 20])),
+                      bin_construct_sample_cnt=int(r.choice([200000, max(20, n // 2)])), data_random_seed=int(r.integers(1, 100)),
+                      feature_pre_filter="true", use_missing="true", zero_as_missing=str(bool(r.integers(0, 2))).lower(), enable_bundle="true")
+        try:
+            ds = refapi.RefDataset(X, None, dict(params, device_type="cuda", verbosity=-1))
+        except RuntimeError:
+            ds = None
+        if ds is None or ds.layout().num_features == 0:
+            with pytest.raises(RuntimeError):
+                lgb.Binner(params).fit(X)
+            continue
+        ref = ds.layout(); ds.free()
+        b = lgb.Binner(params).fit(X)
+        m = b.layout_meta()
+        assert (m["num_columns"], m["num_features"]) == (ref.num_columns, ref.num_features), seed
+        for mine, theirs in META:
+            np.testing.assert_array_equal(m[mine], getattr(ref, theirs), err_msg=f"seed {seed} {mine}")
+        for fi, ub in enumerate(b.bin_upper_bounds()):
+            assert ub.tobytes() == np.asarray(ref.bin_upper_bound[fi], np.float64).tobytes(), (seed, fi)
+        np.testing.assert_array_equal(b.transform(np.ascontiguousarray(X), to_device=False)[0], ref.bins, err_msg=f"seed {seed}")
+        checked += 1
+    assert checked >= 5

@@ -124,3 +124,44 @@ def test_raw_floats_to_model_text_to_reference_predict(built_lib, objective):
         assert loaded.predict(Xt, raw_score=True).tobytes() == mine.tobytes()
         np.testing.assert_allclose(loaded.predict(Xt, raw_score=False), m.predict(Xt), rtol=1e-15, atol=1e-15)
         loaded.free()
+
+
+def _single_leaf_model():
+    """A model whose only tree is a single leaf (no split satisfies min_data_in_leaf), written by the live reference."""
+    from oracle import refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not built")
+    r = np.random.default_rng(0)
+    X = r.normal(size=(500, 4)).astype(np.float32); y = r.normal(size=500).astype(np.float32)
+    p = dict(objective="regression", num_leaves=7, min_data_in_leaf=400, verbosity=-1, num_threads=2)
+    ds = refapi.RefDataset(X, y, p); b = refapi.RefBooster(ds, p)
+    for _ in range(3):
+        b.update()
+    text = b.model_string()
+    b.free(); ds.free()
+    return text, X
+
+
+def test_single_leaf_tree_text_round_trips():
+    from lightgbm_b200.model import Model
+    text, _ = _single_leaf_model()
+    m = Model.from_string(text)
+    assert [t.num_leaves for t in m.trees] == [1]
+    assert m.to_string().split("\nparameters:\n")[0] == text.split("\nparameters:\n")[0]
+
+
+@pytest.mark.gpu
+def test_single_leaf_tree_and_tiny_inputs_predict(built_lib):
+    from lightgbm_b200.model import Model
+    from oracle import refapi
+    text, X = _single_leaf_model()
+    m = Model.from_string(text)
+    loaded = refapi.RefLoadedBooster(text)
+    for rows in (1, 2, 31, 33, 500):
+        assert m.predict_raw(X[:rows]).tobytes() == loaded.predict(X[:rows], raw_score=True).tobytes()
+    loaded.free()
+    # a real model on 1 .. 65 rows (less than one tile, exactly one, one more)
+    d = np.load([p for p in GOLD if p.endswith("model_regression_missing_nan.npz")][0])
+    m2 = Model.from_string(bytes(d["model"]).decode())
+    for rows in (1, 7, 63, 64, 65):
+        assert m2.predict_raw(d["X"][:rows]).tobytes() == d["raw"][:rows].tobytes()
